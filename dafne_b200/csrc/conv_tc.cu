@@ -1,0 +1,585 @@
+// im2col-free NHWC convolution (1x1 / 3x3, stride 1 / 2) as a persistent, warp-specialised tcgen05 kernel for sm_100a.
+//
+// Replaces, for the inference hot path, every cuDNN conv2d the reference reaches through torch:
+//   ResNet bottlenecks + FrozenBN (+ReLU, +shortcut)   detectron2 v0.5 BottleneckBlock via dafne/modeling/backbone/fpn.py:72
+//   FPN lateral / output convs, P6 / P7                 dafne/modeling/backbone/fpn.py:16-37,83-90
+//   head tower convs and prediction convs               dafne/modeling/dafne/dafne.py:287-348, 209-230, 388-414, 462-471
+//
+// GEMM view: M = output pixels (tile = 128 pixels = one tw x th x nb patch), N = Cout (tile BLOCK_N), K = taps x Cin in
+// blocks of 64 channels (one 128-byte swizzle row). For each (tap, channel block) ONE 4-D TMA box load of the shifted
+// input patch lands directly in the canonical K-major SWIZZLE_128B operand layout; out-of-image coordinates are
+// zero-filled by TMA, which is exactly the conv zero padding. Nothing im2col-shaped ever exists in HBM.
+//
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (TMEM -> registers -> scale/shift/residual/ReLU -> fp16 -> swizzled smem -> TMA store).
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace dafne {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+template <int BLOCK_N>
+struct ConvCfg {
+    static constexpr int A_BYTES = 128 * 128;      // 128 pixels x 64 ch fp16
+    static constexpr int B_BYTES = BLOCK_N * 128;  // BLOCK_N couts x 64 ch fp16
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int EPI_BYTES = BLOCK_N >= 64 ? 2 * 16384 : 0;
+    static constexpr int AUX_BYTES = 256 + 2 * BLOCK_N * 4;  // barriers + tmem ptr, then scale/shift
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + AUX_BYTES;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+};
+
+// Sum 16 per-lane values across the warp; lane l returns the total of value index
+// 8*b4 + 4*b3 + 2*b2 + b1 (b_i = bit i of l). 16 shuffles instead of 80.
+__device__ __forceinline__ float warp_reduce16_scatter(const float (&v)[16], uint32_t lane) {
+    const uint32_t full = 0xffffffffu;
+    float a[8], b[4], c[2];
+    bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float send = hi ? v[i] : v[i + 8];
+        float keep = hi ? v[i + 8] : v[i];
+        a[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+    hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float send = hi ? a[i] : a[i + 4];
+        float keep = hi ? a[i + 4] : a[i];
+        b[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+    hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float send = hi ? b[i] : b[i + 2];
+        float keep = hi ? b[i + 2] : b[i];
+        c[i] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    hi = lane & 2;
+    float send = hi ? c[0] : c[1];
+    float keep = hi ? c[1] : c[0];
+    float d = keep + __shfl_xor_sync(full, send, 2);
+    d += __shfl_xor_sync(full, d, 1);
+    return d;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1)
+    conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                   const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (threadIdx.x == 0 && (smem_base & 1023u) != 0) {
+        printf("dafne conv_tc: dynamic smem base not 1024-aligned (%u)\n", smem_base);
+        __trap();
+    }
+
+    // carve-up: [stages x (A | B)] [epilogue staging] [barriers | tmem ptr] [scale | shift]
+    const uint32_t s_tiles = smem_base;
+    const uint32_t s_epi = smem_base + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t s_aux = s_epi + Cfg::EPI_BYTES;
+    uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES;
+    const uint32_t bar_full = s_aux;                     // STAGES x 8 B
+    const uint32_t bar_empty = s_aux + 8 * STAGES;       // STAGES x 8 B
+    const uint32_t bar_tfull = s_aux + 16 * STAGES;      // 2 x 8 B
+    const uint32_t bar_tempty = s_aux + 16 * STAGES + 16;  // 2 x 8 B
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(aux + 16 * STAGES + 32);
+    float* s_scale = reinterpret_cast<float*>(aux + 256);
+    float* s_shift = s_scale + BLOCK_N;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA0);
+        tma_prefetch_desc(&tmB);
+        if (BLOCK_N >= 64) tma_prefetch_desc(&tmOut);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_kb = p.num_taps * p.cin_blocks;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+                const int tx = mt % p.tiles_x;
+                const int r = mt / p.tiles_x;
+                const int ty = r % p.tiles_y, tn = r / p.tiles_y;
+                const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tn * p.nb;
+                for (int tap = 0; tap < p.num_taps; ++tap) {
+                    const int view = p.tap_view[tap];
+                    const CUtensorMap* mA = view == 0 ? &tmA0 : (view == 1 ? &tmA1 : (view == 2 ? &tmA2 : &tmA3));
+                    const int cx = x0 + p.tap_dx[tap], cy = y0 + p.tap_dy[tap];
+                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t full = bar_full + 8 * stage;
+                        mbar_arrive_expect_tx(full, Cfg::STAGE_BYTES);
+                        const uint32_t sA = s_tiles + stage * Cfg::STAGE_BYTES;
+                        tma_load_4d(sA, mA, full, cb * 64, cx, cy, n0);
+                        tma_load_2d(sA + Cfg::A_BYTES, &tmB, full, tap * p.Cin + cb * 64, nt * BLOCK_N);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(128, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sA = s_tiles + stage * Cfg::STAGE_BYTES;
+                    const uint64_t ad = umma_desc_sw128(sA);
+                    const uint64_t bd = umma_desc_sw128(sA + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // +32 B along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
+                        umma_f16(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(bar_empty + 8 * stage);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(bar_tfull + 8 * acc);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue
+        const int wi = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32*wi, 32*wi+32)
+        const int et = threadIdx.x - 128;
+        const int row = wi * 32 + lane;
+        const int rx = row % p.tw;
+        const int ry = (row / p.tw) % p.th;
+        const int rn = row / (p.tw * p.th);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int store_buf = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+            const int tx = mt % p.tiles_x;
+            const int r = mt / p.tiles_x;
+            const int ty = r % p.tiles_y, tn = r / p.tiles_y;
+            const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tn * p.nb;
+            const int x = x0 + rx, y = y0 + ry, n = n0 + rn;
+            const bool valid = x < p.Wout && y < p.Hout && n < p.N;
+
+            named_bar_sync(1, 128);  // everyone is done reading the previous tile's scale/shift
+            for (int i = et; i < BLOCK_N; i += 128) {
+                const int ch = nt * BLOCK_N + i;
+                s_scale[i] = (p.scale != nullptr && ch < p.Cout) ? __ldg(p.scale + ch) : 1.0f;
+                s_shift[i] = (p.shift != nullptr && ch < p.Cout) ? __ldg(p.shift + ch) : 0.0f;
+            }
+            named_bar_sync(1, 128);
+
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wi * 32) << 16) + acc * BLOCK_N;
+
+            if constexpr (BLOCK_N >= 64) {
+                constexpr int CHUNKS = BLOCK_N / 64;
+#pragma unroll 1
+                for (int j = 0; j < CHUNKS; ++j) {
+                    const int chbase = j * 64;
+                    uint4 resv[8];
+                    if (p.residual != nullptr) {
+                        const __half* rp =
+                            p.residual +
+                            ((static_cast<size_t>(n) * p.res_H + (y >> p.res_shift)) * p.res_W + (x >> p.res_shift)) *
+                                p.Cout +
+                            nt * BLOCK_N + chbase;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            resv[q] = valid ? __ldg(reinterpret_cast<const uint4*>(rp) + q) : make_uint4(0, 0, 0, 0);
+                    }
+                    uint32_t v[64];
+                    DAFNE_TMEM_LD_X32(taddr + chbase, v);
+                    DAFNE_TMEM_LD_X32(taddr + chbase + 32, (v + 32));
+                    tmem_ld_wait();
+                    if (j == CHUNKS - 1) {
+                        // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    }
+                    uint32_t packed[32];
+                    float gs[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) gs[i] = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 64; c += 2) {
+                        float a0 = fmaf(__uint_as_float(v[c]), s_scale[chbase + c], s_shift[chbase + c]);
+                        float a1 = fmaf(__uint_as_float(v[c + 1]), s_scale[chbase + c + 1], s_shift[chbase + c + 1]);
+                        if (p.residual != nullptr) {
+                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(resv);
+                            const __half2 rh = *reinterpret_cast<const __half2*>(&rw[c >> 1]);
+                            const float2 rf = __half22float2(rh);
+                            a0 += rf.x;
+                            a1 += rf.y;
+                        }
+                        if (p.relu) {
+                            a0 = fmaxf(a0, 0.0f);
+                            a1 = fmaxf(a1, 0.0f);
+                        }
+                        const __half2 h = __floats2half2_rn(a0, a1);
+                        packed[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                        if (p.gn_sums != nullptr) {
+                            const float2 f = __half22float2(h);  // statistics of what the next layer will read
+                            gs[(c >> 3) * 2] += f.x + f.y;
+                            gs[(c >> 3) * 2 + 1] += f.x * f.x + f.y * f.y;
+                        }
+                    }
+                    if (p.gn_sums != nullptr) {
+                        const int groups = p.Cout >> 3;
+                        const int n_lo = __shfl_sync(0xffffffffu, n, 0);
+                        int n_hi = __shfl_sync(0xffffffffu, n, 31);
+                        if (n_hi > p.N - 1) n_hi = p.N - 1;
+                        for (int img = n_lo; img <= n_hi; ++img) {
+                            const bool mine = valid && n == img;
+                            float mv[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) mv[i] = mine ? gs[i] : 0.0f;
+                            const float tot = warp_reduce16_scatter(mv, lane);
+                            if ((lane & 1) == 0) {
+                                const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
+                                                ((lane >> 1) & 1);
+                                const int g = (nt * BLOCK_N + chbase) / 8 + (idx >> 1);
+                                atomicAdd(p.gn_sums + (static_cast<size_t>(img) * groups + g) * 2 + (idx & 1), tot);
+                            }
+                        }
+                    }
+                    // stage through swizzled smem, then one TMA store per 128 px x 64 ch chunk
+                    const uint32_t buf = s_epi + store_buf * 16384;
+                    if (et == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained
+                    named_bar_sync(1, 128);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t dst = buf + row * 128 + ((q ^ (row & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * q]),
+                                     "r"(packed[4 * q + 1]), "r"(packed[4 * q + 2]), "r"(packed[4 * q + 3])
+                                     : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (et == 0) {
+                        tma_store_4d(&tmOut, buf, nt * BLOCK_N + chbase, x0, y0, n0);
+                        tma_store_commit();
+                    }
+                    store_buf ^= 1;
+                }
+            } else {
+                // small-Cout prediction convs: fp32 NHWC rows written straight from registers
+                uint32_t v[BLOCK_N];
+                if constexpr (BLOCK_N == 16) {
+                    DAFNE_TMEM_LD_X16(taddr, v);
+                } else {
+                    DAFNE_TMEM_LD_X32(taddr, v);
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                if (valid) {
+                    float* op = p.out_f32 + ((static_cast<size_t>(n) * p.Hout + y) * p.Wout + x) * p.out_ld;
+#pragma unroll
+                    for (int c = 0; c < BLOCK_N; c += 4) {
+                        if (c < p.out_ld) {
+                            float4 o;
+                            o.x = fmaf(__uint_as_float(v[c]), s_scale[c], s_shift[c]);
+                            o.y = fmaf(__uint_as_float(v[c + 1]), s_scale[c + 1], s_shift[c + 1]);
+                            o.z = fmaf(__uint_as_float(v[c + 2]), s_scale[c + 2], s_shift[c + 2]);
+                            o.w = fmaf(__uint_as_float(v[c + 3]), s_scale[c + 3], s_shift[c + 3]);
+                            if (p.relu) {
+                                o.x = fmaxf(o.x, 0.f);
+                                o.y = fmaxf(o.y, 0.f);
+                                o.z = fmaxf(o.z, 0.f);
+                                o.w = fmaxf(o.w, 0.f);
+                            }
+                            *reinterpret_cast<float4*>(op + c) = o;
+                        }
+                    }
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (BLOCK_N >= 64 && et == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+        set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+        return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, CUtensorMapL2promotion promo, const char* what) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bdim[5];
+    cuuint32_t estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+    }
+    for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu %llu %llu %llu box %u %u %u %u)", what,
+                  (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                  box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+        return -1;
+    }
+    return 0;
+}
+
+static int pow2ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
+    memset(plan, 0, sizeof(*plan));
+    if (d.Cin % 64 != 0) {
+        set_error("conv_tc: Cin=%d must be a multiple of 64", d.Cin);
+        return -1;
+    }
+    if (!(d.ksize == 1 || d.ksize == 3) || !(d.stride == 1 || d.stride == 2)) {
+        set_error("conv_tc: unsupported ksize=%d stride=%d", d.ksize, d.stride);
+        return -1;
+    }
+    const bool small = d.out_f32 != nullptr;
+    int bn;
+    if (small) {
+        if (d.Cout > 32 || d.out_ld % 4 != 0 || d.out_ld < d.Cout) {
+            set_error("conv_tc: fp32-output path needs Cout<=32 and out_ld%%4==0 (Cout=%d ld=%d)", d.Cout, d.out_ld);
+            return -1;
+        }
+        bn = d.Cout <= 16 ? 16 : 32;
+    } else {
+        if (d.Cout % 64 != 0) {
+            set_error("conv_tc: Cout=%d must be a multiple of 64", d.Cout);
+            return -1;
+        }
+        bn = d.Cout % 256 == 0 ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
+    }
+    ConvParams& p = plan->p;
+    p.N = d.N;
+    p.Hout = d.Hout;
+    p.Wout = d.Wout;
+    p.Cin = d.Cin;
+    p.Cout = d.Cout;
+    p.num_taps = d.ksize * d.ksize;
+    p.cin_blocks = d.Cin / 64;
+    p.tw = pow2ceil(d.Wout) < 16 ? pow2ceil(d.Wout) : 16;
+    p.th = pow2ceil(d.Hout) < 128 / p.tw ? pow2ceil(d.Hout) : 128 / p.tw;
+    p.nb = 128 / (p.tw * p.th);
+    p.tiles_x = (d.Wout + p.tw - 1) / p.tw;
+    p.tiles_y = (d.Hout + p.th - 1) / p.th;
+    p.tiles_n = (d.N + p.nb - 1) / p.nb;
+    p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+    p.n_tiles = (d.Cout + bn - 1) / bn;
+    p.total_tiles = p.m_tiles * p.n_tiles;
+    p.scale = d.scale;
+    p.shift = d.shift;
+    p.relu = d.relu;
+    p.residual = d.residual;
+    p.res_H = d.res_H;
+    p.res_W = d.res_W;
+    p.res_shift = d.res_shift;
+    p.gn_sums = d.gn_sums;
+    p.out_f32 = d.out_f32;
+    p.out_ld = d.out_ld;
+    plan->block_n = bn;
+    plan->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    plan->flops = 2.0 * d.N * d.Hout * d.Wout * (double)d.Cout * p.num_taps * d.Cin;
+
+    const uint64_t C = d.Cin, W = d.Win, H = d.Hin;
+    const uint32_t boxA[4] = {64u, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.nb};
+    bool view_empty[4] = {false, false, false, false};
+    if (d.stride == 1) {
+        const uint64_t dims[4] = {C, W, H, (uint64_t)d.N};
+        const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+        if (encode_map(&plan->tmA[0], d.in, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A")) return -1;
+        for (int v = 1; v < 4; ++v) plan->tmA[v] = plan->tmA[0];
+        for (int t = 0; t < p.num_taps; ++t) {
+            p.tap_view[t] = 0;
+            p.tap_dy[t] = d.ksize == 3 ? t / 3 - 1 : 0;
+            p.tap_dx[t] = d.ksize == 3 ? t % 3 - 1 : 0;
+        }
+    } else {
+        // stride 2: four parity views (rows py, py+2, ...; cols px, px+2, ...) of the same tensor; every tap of the
+        // 3x3 (or the single 1x1 tap) becomes a unit-stride box in one of them.
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                const int v = py * 2 + px;
+                uint64_t vw = (W - px + 1) / 2, vh = (H - py + 1) / 2;
+                if ((int64_t)W - px <= 0) vw = 0;
+                if ((int64_t)H - py <= 0) vh = 0;
+                if (vw == 0 || vh == 0) {
+                    view_empty[v] = true;
+                    vw = vw ? vw : 1;
+                    vh = vh ? vh : 1;
+                }
+                const uint64_t dims[4] = {C, vw, vh, (uint64_t)d.N};
+                const uint64_t str[3] = {2 * C * 2, 2 * W * C * 2, H * W * C * 2};
+                const __half* base = d.in + ((size_t)py * W + px) * C;
+                if (view_empty[v]) base = d.in;
+                if (encode_map(&plan->tmA[v], base, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A-s2"))
+                    return -1;
+            }
+        for (int t = 0; t < p.num_taps; ++t) {
+            const int ky = d.ksize == 3 ? t / 3 : 1, kx = d.ksize == 3 ? t % 3 : 1;
+            const int py = ky == 1 ? 0 : 1, px = kx == 1 ? 0 : 1;
+            p.tap_view[t] = py * 2 + px;
+            p.tap_dy[t] = ky == 0 ? -1 : 0;
+            p.tap_dx[t] = kx == 0 ? -1 : 0;
+            if (view_empty[p.tap_view[t]]) p.tap_dx[t] = 1 << 20;  // whole box out of bounds -> zeros
+        }
+    }
+    {
+        const uint64_t K = (uint64_t)p.num_taps * d.Cin;
+        const uint64_t dims[2] = {K, (uint64_t)d.Cout};
+        const uint64_t str[1] = {K * 2};
+        const uint32_t box[2] = {64u, (uint32_t)bn};
+        if (encode_map(&plan->tmB, d.w, 2, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "B")) return -1;
+    }
+    if (!small) {
+        const uint64_t Co = d.Cout, Wo = d.Wout, Ho = d.Hout;
+        const uint64_t dims[4] = {Co, Wo, Ho, (uint64_t)d.N};
+        const uint64_t str[3] = {Co * 2, Wo * Co * 2, Ho * Wo * Co * 2};
+        if (encode_map(&plan->tmOut, d.out, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "Out")) return -1;
+    } else {
+        plan->tmOut = plan->tmB;
+    }
+    switch (bn) {
+        case 16: plan->smem_bytes = ConvCfg<16>::SMEM_BYTES; break;
+        case 32: plan->smem_bytes = ConvCfg<32>::SMEM_BYTES; break;
+        case 64: plan->smem_bytes = ConvCfg<64>::SMEM_BYTES; break;
+        case 128: plan->smem_bytes = ConvCfg<128>::SMEM_BYTES; break;
+        default: plan->smem_bytes = ConvCfg<256>::SMEM_BYTES; break;
+    }
+    return 0;
+}
+
+template <int BN>
+static int launch_bn(const ConvPlan& pl, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             ConvCfg<BN>::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(conv_tc_kernel<%d>, smem=%d): %s", BN, ConvCfg<BN>::SMEM_BYTES,
+                      cudaGetErrorString(e));
+            return -1;
+        }
+        configured = true;
+    }
+    conv_tc_kernel<BN><<<pl.grid, 256, ConvCfg<BN>::SMEM_BYTES, stream>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmA[3],
+                                                                           pl.tmB, pl.tmOut, pl.p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("conv_tc_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
+int conv_plan_launch(const ConvPlan& pl, cudaStream_t stream) {
+    if (pl.p.total_tiles == 0) return 0;
+    switch (pl.block_n) {
+        case 16: return launch_bn<16>(pl, stream);
+        case 32: return launch_bn<32>(pl, stream);
+        case 64: return launch_bn<64>(pl, stream);
+        case 128: return launch_bn<128>(pl, stream);
+        case 256: return launch_bn<256>(pl, stream);
+    }
+    set_error("conv_tc: bad block_n %d", pl.block_n);
+    return -1;
+}
+
+}  // namespace dafne

@@ -1,0 +1,69 @@
+// Host-side description + plan for the tcgen05 implicit-GEMM convolution (see conv_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dafne {
+
+// What one convolution launch computes. Activations are NHWC fp16; weights are packed
+// [Cout][tap][Cin] fp16 (tap = ky*k+kx); the epilogue is out = relu?(acc*scale + shift (+ residual)).
+struct ConvDesc {
+    const __half* in = nullptr;
+    int N = 0, Hin = 0, Win = 0, Cin = 0;
+    const __half* w = nullptr;
+    int Cout = 0, ksize = 1, stride = 1;  // ksize 1|3 (pad = ksize/2), stride 1|2
+    int Hout = 0, Wout = 0;               // filled by conv_out_dims()
+    __half* out = nullptr;                // NHWC fp16 output (Cout % 64 == 0), or
+    float* out_f32 = nullptr;             // NHWC fp32 output with row pitch out_ld (small-Cout prediction convs)
+    int out_ld = 0;
+    const float* scale = nullptr;  // per-Cout multiplier (folded FrozenBN), nullptr = 1
+    const float* shift = nullptr;  // per-Cout addend (folded FrozenBN shift or conv bias), nullptr = 0
+    int relu = 0;
+    const __half* residual = nullptr;  // NHWC fp16 [N, res_H, res_W, Cout]; added at (y>>res_shift, x>>res_shift)
+    int res_H = 0, res_W = 0, res_shift = 0;
+    float* gn_sums = nullptr;  // [N][Cout/8][2] fp32 (sum, sum of squares of the fp16-rounded output), accumulated
+};
+
+struct ConvParams {
+    int N, Hout, Wout, Cin, Cout;
+    int num_taps, cin_blocks;
+    int tw, th, nb;
+    int tiles_x, tiles_y, tiles_n, m_tiles, n_tiles, total_tiles;
+    int tap_view[9], tap_dy[9], tap_dx[9];
+    const float* scale;
+    const float* shift;
+    int relu;
+    const __half* residual;
+    int res_H, res_W, res_shift;
+    float* gn_sums;
+    float* out_f32;
+    int out_ld;
+};
+
+struct ConvPlan {
+    alignas(64) CUtensorMap tmA[4];
+    alignas(64) CUtensorMap tmB;
+    alignas(64) CUtensorMap tmOut;
+    ConvParams p;
+    int block_n;
+    int grid;
+    size_t smem_bytes;
+    double flops;  // 2*MACs, algorithmic (unpadded)
+};
+
+inline void conv_out_dims(ConvDesc& d) {
+    int pad = d.ksize / 2;
+    d.Hout = (d.Hin + 2 * pad - d.ksize) / d.stride + 1;
+    d.Wout = (d.Win + 2 * pad - d.ksize) / d.stride + 1;
+}
+
+// Returns 0 on success; on failure writes a message retrievable with dafne_last_error().
+int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms);
+int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream);
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+}  // namespace dafne

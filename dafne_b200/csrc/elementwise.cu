@@ -1,0 +1,335 @@
+// HBM-bound helper kernels of the dense forward: input normalisation, the 3-channel stem, max-pool, GroupNorm apply,
+// and the one-time weight packing. Each restates a torch/ATen call the reference reaches on its inference path:
+//   normalise + pad          dafne/modeling/one_stage_detector.py:100-107 (ImageList.from_tensors pads with 0 AFTER normalising)
+//   stem conv+BN+ReLU, pool  detectron2 v0.5 BasicStem via dafne/modeling/backbone/fpn.py:72
+//   GroupNorm(32) + ReLU     dafne/modeling/dafne/dafne.py:326-345
+#include "conv_tc.cuh"
+#include "elementwise.cuh"
+
+namespace dafne {
+
+#define DAFNE_CHECK_LAUNCH(name)                                        \
+    do {                                                                \
+        cudaError_t e__ = cudaGetLastError();                           \
+        if (e__ != cudaSuccess) {                                       \
+            set_error("%s launch: %s", name, cudaGetErrorString(e__)); \
+            return -1;                                                  \
+        }                                                               \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ preprocess
+template <typename T>
+__global__ void preprocess_kernel(const T* __restrict__ img, const int32_t* __restrict__ sizes, int N, int H, int W,
+                                  float m0, float m1, float m2, float s0, float s1, float s2,
+                                  __half* __restrict__ out) {
+    const size_t total = static_cast<size_t>(N) * H * W;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = i % W;
+        const int y = (i / W) % H;
+        const int n = i / (static_cast<size_t>(W) * H);
+        const int h = sizes[2 * n], w = sizes[2 * n + 1];
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        if (y < h && x < w) {
+            const size_t plane = static_cast<size_t>(H) * W;
+            const size_t base = static_cast<size_t>(n) * 3 * plane + static_cast<size_t>(y) * W + x;
+            v0 = (static_cast<float>(img[base]) - m0) / s0;
+            v1 = (static_cast<float>(img[base + plane]) - m1) / s1;
+            v2 = (static_cast<float>(img[base + 2 * plane]) - m2) / s2;
+        }
+        const __half2 a = __floats2half2_rn(v0, v1);
+        const __half2 b = __floats2half2_rn(v2, 0.f);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&a);
+        o.y = *reinterpret_cast<const uint32_t*>(&b);
+        reinterpret_cast<uint2*>(out)[i] = o;
+    }
+}
+
+int launch_preprocess(const void* images, int dtype, const int32_t* sizes_dev, int N, int H, int W, const float* mean3,
+                      const float* std3, __half* out, cudaStream_t s) {
+    const size_t total = static_cast<size_t>(N) * H * W;
+    const int threads = 256;
+    const int blocks = static_cast<int>((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads
+                                                                                   : 148 * 16);
+    if (dtype == 0)
+        preprocess_kernel<uint8_t><<<blocks, threads, 0, s>>>(static_cast<const uint8_t*>(images), sizes_dev, N, H, W,
+                                                              mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2],
+                                                              out);
+    else if (dtype == 1)
+        preprocess_kernel<float><<<blocks, threads, 0, s>>>(static_cast<const float*>(images), sizes_dev, N, H, W,
+                                                            mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2],
+                                                            out);
+    else {
+        set_error("preprocess: dtype %d (0 = uint8, 1 = float32)", dtype);
+        return -1;
+    }
+    DAFNE_CHECK_LAUNCH("preprocess_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ stem
+// One block = 16x16 output pixels of one image, all 64 output channels; one thread = one pixel.
+constexpr int STEM_T = 16;
+constexpr int STEM_P = 2 * STEM_T + 5;  // input patch edge (37)
+constexpr int STEM_SMEM = 49 * 4 * 64 * 4 + STEM_P * STEM_P * 8;
+
+__global__ void __launch_bounds__(256) stem_kernel(const __half* __restrict__ in, int N, int H, int W,
+                                                   const float* __restrict__ wp, const float* __restrict__ scale,
+                                                   const float* __restrict__ shift, __half* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    float4* s_w = reinterpret_cast<float4*>(sm);                       // [49*4][16] float4
+    uint2* s_in = reinterpret_cast<uint2*>(sm + 49 * 4 * 64 * 4);      // [37][37] x 4 halves
+    const int Ho = H / 2, Wo = W / 2;
+    const int n = blockIdx.z;
+    const int oy0 = blockIdx.y * STEM_T, ox0 = blockIdx.x * STEM_T;
+    for (int i = threadIdx.x; i < 49 * 4 * 16; i += 256) s_w[i] = reinterpret_cast<const float4*>(wp)[i];
+    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+    for (int i = threadIdx.x; i < STEM_P * STEM_P; i += 256) {
+        const int py = i / STEM_P, px = i % STEM_P;
+        const int iy = iy0 + py, ix = ix0 + px;
+        uint2 v = make_uint2(0, 0);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+            v = reinterpret_cast<const uint2*>(in)[(static_cast<size_t>(n) * H + iy) * W + ix];
+        s_in[i] = v;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / STEM_T, tx = threadIdx.x % STEM_T;
+    float acc[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+#pragma unroll 1
+    for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll 1
+        for (int kx = 0; kx < 7; ++kx) {
+            const uint2 pv = s_in[(2 * ty + ky) * STEM_P + 2 * tx + kx];
+            const float2 p01 = __half22float2(*reinterpret_cast<const __half2*>(&pv.x));
+            const float2 p23 = __half22float2(*reinterpret_cast<const __half2*>(&pv.y));
+            const float pin[3] = {p01.x, p01.y, p23.x};
+            const float4* wt = s_w + (ky * 7 + kx) * 4 * 16;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float4 w4 = wt[ci * 16 + q];
+                    acc[4 * q] = fmaf(pin[ci], w4.x, acc[4 * q]);
+                    acc[4 * q + 1] = fmaf(pin[ci], w4.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(pin[ci], w4.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(pin[ci], w4.w, acc[4 * q + 3]);
+                }
+            }
+        }
+    }
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    if (oy < Ho && ox < Wo) {
+        uint4* op = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * 64);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = q * 8 + 2 * j;
+                const float a0 = fmaxf(fmaf(acc[c], __ldg(scale + c), __ldg(shift + c)), 0.f);
+                const float a1 = fmaxf(fmaf(acc[c + 1], __ldg(scale + c + 1), __ldg(shift + c + 1)), 0.f);
+                const __half2 h = __floats2half2_rn(a0, a1);
+                pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            op[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+int launch_stem(const __half* in, int N, int H, int W, const float* wp, const float* scale, const float* shift,
+                __half* out, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+        if (e != cudaSuccess) {
+            set_error("stem_kernel smem attribute: %s", cudaGetErrorString(e));
+            return -1;
+        }
+        configured = true;
+    }
+    const int Ho = H / 2, Wo = W / 2;
+    dim3 grid((Wo + STEM_T - 1) / STEM_T, (Ho + STEM_T - 1) / STEM_T, N);
+    stem_kernel<<<grid, 256, STEM_SMEM, s>>>(in, N, H, W, wp, scale, shift, out);
+    DAFNE_CHECK_LAUNCH("stem_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ max pool
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+__global__ void maxpool_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int Ho, int Wo,
+                               __half* __restrict__ out) {
+    const int c8 = C / 8;
+    const size_t total = static_cast<size_t>(N) * Ho * Wo * c8;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int cv = i % c8;
+        const int ox = (i / c8) % Wo;
+        const int oy = (i / (static_cast<size_t>(c8) * Wo)) % Ho;
+        const int n = i / (static_cast<size_t>(c8) * Wo * Ho);
+        uint4 m;
+        bool first = true;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy - 1 + ky;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                if (ix < 0 || ix >= W) continue;
+                const uint4 v =
+                    __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(n) * H + iy) * W + ix) * C) + cv);
+                if (first) {
+                    m = v;
+                    first = false;
+                } else {
+                    m.x = hmax2_u32(m.x, v.x);
+                    m.y = hmax2_u32(m.y, v.y);
+                    m.z = hmax2_u32(m.z, v.z);
+                    m.w = hmax2_u32(m.w, v.w);
+                }
+            }
+        }
+        reinterpret_cast<uint4*>(out)[i] = m;
+    }
+}
+
+int launch_maxpool3x3s2(const __half* in, int N, int H, int W, int C, __half* out, cudaStream_t s) {
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const size_t total = static_cast<size_t>(N) * Ho * Wo * (C / 8);
+    const int threads = 256;
+    size_t blocks = (total + threads - 1) / threads;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    maxpool_kernel<<<static_cast<int>(blocks), threads, 0, s>>>(in, N, H, W, C, Ho, Wo, out);
+    DAFNE_CHECK_LAUNCH("maxpool_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm + ReLU
+__global__ void gn_relu_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int HW, int C,
+                               int groups, const float* __restrict__ sums, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, float eps) {
+    const int c8 = C / 8;  // one uint4 = one group of 8 channels
+    const size_t per_img = static_cast<size_t>(HW) * c8;
+    const size_t total = per_img * N;
+    const float inv_cnt = 1.0f / (static_cast<float>(HW) * 8.0f);
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = i % c8;
+        const int n = i / per_img;
+        const float s1 = __ldg(sums + (static_cast<size_t>(n) * groups + g) * 2);
+        const float s2 = __ldg(sums + (static_cast<size_t>(n) * groups + g) * 2 + 1);
+        const float mean = s1 * inv_cnt;
+        const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + i);
+        const uint32_t vin[4] = {v.x, v.y, v.z, v.w};
+        uint32_t vo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&vin[j]));
+            const int c = g * 8 + 2 * j;
+            const float a0 = fmaxf((f.x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c), 0.f);
+            const float a1 = fmaxf((f.y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1), 0.f);
+            const __half2 h = __floats2half2_rn(a0, a1);
+            vo[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(vo[0], vo[1], vo[2], vo[3]);
+    }
+}
+
+int launch_gn_relu(const __half* in, __half* out, int N, int HW, int C, int groups, const float* sums,
+                   const float* gamma, const float* beta, float eps, cudaStream_t s) {
+    if (C != groups * 8) {
+        set_error("gn_relu: needs C == 8 * groups (C=%d groups=%d)", C, groups);
+        return -1;
+    }
+    const size_t total = static_cast<size_t>(N) * HW * (C / 8);
+    if (total == 0) return 0;
+    const int threads = 256;
+    size_t blocks = (total + threads - 1) / threads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gn_relu_kernel<<<static_cast<int>(blocks), threads, 0, s>>>(in, out, N, HW, C, groups, sums, gamma, beta, eps);
+    DAFNE_CHECK_LAUNCH("gn_relu_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ relu copy
+__global__ void relu_copy_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n8) {
+    const __half2 z = __floats2half2_rn(0.f, 0.f);
+    const uint32_t zu = *reinterpret_cast<const uint32_t*>(&z);
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        uint4 v = __ldg(in + i);
+        v.x = hmax2_u32(v.x, zu);
+        v.y = hmax2_u32(v.y, zu);
+        v.z = hmax2_u32(v.z, zu);
+        v.w = hmax2_u32(v.w, zu);
+        out[i] = v;
+    }
+}
+
+int launch_relu_copy(const __half* in, __half* out, size_t n8, cudaStream_t s) {
+    if (n8 == 0) return 0;
+    size_t blocks = (n8 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    relu_copy_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(reinterpret_cast<const uint4*>(in),
+                                                               reinterpret_cast<uint4*>(out), n8);
+    DAFNE_CHECK_LAUNCH("relu_copy_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int k, __half* __restrict__ o) {
+    const size_t total = static_cast<size_t>(Cout) * k * k * Cin;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ci = i % Cin;
+        const int tap = (i / Cin) % (k * k);
+        const int co = i / (static_cast<size_t>(Cin) * k * k);
+        o[i] = __float2half_rn(w[(static_cast<size_t>(co) * Cin + ci) * k * k + tap]);
+    }
+}
+int launch_pack_conv_weight(const float* w, int Cout, int Cin, int k, __half* out, cudaStream_t s) {
+    const size_t total = static_cast<size_t>(Cout) * k * k * Cin;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    pack_conv_weight_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(w, Cout, Cin, k, out);
+    DAFNE_CHECK_LAUNCH("pack_conv_weight_kernel");
+    return 0;
+}
+
+__global__ void pack_stem_weight_kernel(const float* __restrict__ w, float* __restrict__ o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [49][4][64]
+    if (i >= 49 * 4 * 64) return;
+    const int co = i % 64, ci = (i / 64) % 4, tap = i / 256;
+    o[i] = ci < 3 ? w[(co * 3 + ci) * 49 + tap] : 0.f;
+}
+int launch_pack_stem_weight(const float* w, float* out, cudaStream_t s) {
+    pack_stem_weight_kernel<<<(49 * 4 * 64 + 255) / 256, 256, 0, s>>>(w, out);
+    DAFNE_CHECK_LAUNCH("pack_stem_weight_kernel");
+    return 0;
+}
+
+__global__ void fold_bn_kernel(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                               int C, float* scale, float* shift) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C) return;
+    const float sc = gamma[i] * rsqrtf(var[i] + eps);
+    scale[i] = sc;
+    shift[i] = beta[i] - mean[i] * sc;
+}
+int launch_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int C,
+                   float* scale, float* shift, cudaStream_t s) {
+    fold_bn_kernel<<<(C + 255) / 256, 256, 0, s>>>(gamma, beta, mean, var, eps, C, scale, shift);
+    DAFNE_CHECK_LAUNCH("fold_bn_kernel");
+    return 0;
+}
+
+}  // namespace dafne

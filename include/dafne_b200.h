@@ -1,0 +1,161 @@
+/*
+ * dafne_b200 -- C ABI of the B200-native DAFNe inference hot path (libdafne_b200.so).
+ *
+ * Scope: batched inference only -- dense forward (ResNet-50/101 + FPN + P6/P7 + DAFNe head) and the rotated-box
+ * post-processing (threshold -> top-k -> decode -> corner sort -> polygon NMS -> top-1000 -> rescale/clip).
+ * Plain C: pointers and sizes only, no torch / C++ types. Every function returns 0 on success and a negative
+ * value on failure; dafne_last_error() then returns a thread-local message. No C++ exception crosses the ABI.
+ * All `dev` pointers are CUDA device pointers on the context's device; `stream` is a cudaStream_t passed as void*
+ * (NULL = legacy default stream). Unless stated otherwise no call synchronises the host with the device.
+ *
+ * Reference interfaces replaced (paths relative to the DAFNe reference tree):
+ *   dafne/modeling/one_stage_detector.py:45-107   OneStageDetector.forward / preprocess_image  -> dafne_detect*
+ *   dafne/modeling/backbone/fpn.py:16-91           ResNet + FPN + LastLevelP6P7                 -> dafne_forward_dense
+ *   dafne/modeling/dafne/dafne.py:350-494          DAFNeHead.forward                            -> dafne_forward_dense
+ *   dafne/modeling/dafne/dafne_outputs.py:733-925  predict_proposals / select_over_all_levels   -> dafne_postprocess
+ *   dafne/utils/sort_corners.py:26-92              sort_quadrilateral                           -> dafne_sort_quadrilateral
+ *   dafne/modeling/nms/nms.py:10-92                ml_nms / batched_nms_poly                    -> dafne_poly_nms
+ *   dafne/modeling/nms/nms.py:91                   poly_gpu_nms(dets[n,9] host, thr, device_id) -> dafne_poly_nms_host
+ *   tools/prepare_dota/polyiou.cpp:108-133         iou_poly                                     -> dafne_poly_iou
+ */
+#ifndef DAFNE_B200_H
+#define DAFNE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAFNE_ABI_VERSION 1
+#define DAFNE_MAX_LEVELS 5
+/* One detection row = DAFNE_DET_STRIDE floats:
+ *  [0..7] pred_corners x0,y0..x3,y3   [8..11] pred_boxes x1,y1,x2,y2   [12] score   [13] centerness
+ *  [14] pred_class   [15] fpn_level   [16,17] location x,y   [18] canonical candidate index within the image
+ *  (level-major, then location, then class)   [19] reserved (0) */
+#define DAFNE_DET_STRIDE 20
+
+typedef struct dafne_ctx dafne_ctx;
+
+/* Flat model description; field meanings follow dafne/config/defaults.py:40-108 and the detectron2 keys the
+ * pre-trained YAMLs dump (configs/pre-trained/dota-1.0_r101_ms.yaml:95-215). */
+typedef struct dafne_model_spec {
+    int32_t resnet_depth;      /* MODEL.RESNETS.DEPTH: 50 | 101 */
+    int32_t num_classes;       /* MODEL.DAFNE.NUM_CLASSES (<= 32) */
+    int32_t sort_corners;      /* MODEL.DAFNE.SORT_CORNERS */
+    int32_t thresh_with_ctr;   /* MODEL.DAFNE.THRESH_WITH_CTR */
+    int32_t pre_nms_topk;      /* MODEL.DAFNE.PRE_NMS_TOPK_TEST */
+    int32_t post_nms_topk;     /* MODEL.DAFNE.POST_NMS_TOPK_TEST */
+    float score_thresh;        /* MODEL.DAFNE.INFERENCE_TH_TEST */
+    float nms_thresh;          /* MODEL.DAFNE.NMS_TH */
+    int32_t num_levels;        /* len(MODEL.DAFNE.FPN_STRIDES) == 5 */
+    int32_t fpn_strides[DAFNE_MAX_LEVELS];
+    float pixel_mean[3];       /* MODEL.PIXEL_MEAN (applied in the input's channel order) */
+    float pixel_std[3];        /* MODEL.PIXEL_STD */
+    int32_t vehicle_merge;     /* 1 = reference behaviour: class 5 is treated as 4 inside NMS (nms.py:77-79) */
+    int32_t reserved[7];
+} dafne_model_spec;
+
+const char* dafne_last_error(void);
+int dafne_abi_version(void);
+
+/* ------------------------------------------------------------------ context, weights, workspace */
+int dafne_ctx_create(const dafne_model_spec* spec, int device, dafne_ctx** out);
+void dafne_ctx_destroy(dafne_ctx* ctx);
+
+/* Load weights by detectron2 state-dict name (e.g. "backbone.bottom_up.res2.0.conv1.weight",
+ * "backbone.bottom_up.res2.0.conv1.norm.running_var", "proposal_generator.dafne_head.cls_tower.0.weight").
+ * Tensors are fp32, contiguous, in the reference's native layouts (conv weights [Cout,Cin,kh,kw]) and live on the
+ * device; the library packs them into its own fp16 layouts with CUDA kernels on `stream`. shapes = 4 int64 per
+ * tensor (trailing dims 1). Unknown names are an error; names may arrive in any order and over several calls.
+ * dafne_weights_finalize() checks that every tensor the model needs was provided and folds FrozenBN. */
+int dafne_load_weights(dafne_ctx* ctx, int count, const char* const* names, const float* const* dev_ptrs,
+                       const int64_t* shapes, void* stream);
+int dafne_weights_finalize(dafne_ctx* ctx, void* stream);
+
+/* The library never allocates per call: activations live in a caller-owned workspace, sized for a padded batch
+ * N x 3 x H x W (H, W multiples of 32) and bound once per shape. Rebinding re-plans (tensor maps, launch table). */
+int dafne_workspace_bytes(dafne_ctx* ctx, int N, int H, int W, size_t* bytes);
+int dafne_bind_workspace(dafne_ctx* ctx, int N, int H, int W, void* dev_workspace, size_t bytes);
+
+/* ------------------------------------------------------------------ the hot path */
+/* images: NCHW, already padded to the bound N x 3 x H x W.  dtype 0 = uint8, 1 = float32 (un-normalised).
+ * image_sizes: N x (h, w) int32 on the HOST = un-padded size of each image inside the padded batch. Pixels outside
+ * (h, w) are replaced by 0 AFTER normalisation, as ImageList.from_tensors does.
+ * Runs normalise -> ResNet -> FPN -> head; leaves logits / ctrness / corner regression in the workspace. */
+int dafne_forward_dense(dafne_ctx* ctx, const void* dev_images, int dtype, const int32_t* image_sizes, void* stream);
+
+/* Head outputs of the last dafne_forward_dense for one level, fp32 NHWC with row pitch *ld floats:
+ * which 0 = class logits (num_classes valid), 1 = [ctrness logit, 8 corner deltas] (9 valid),
+ * 2 = center regression (2 valid). *hw receives H_l, W_l. */
+int dafne_head_output(dafne_ctx* ctx, int level, int which, const float** dev_ptr, int* ld, int* h, int* w);
+
+/* Post-processing of head outputs held in the workspace.
+ * image_sizes / output_sizes: N x (h, w) int32 on the host (output = the "height"/"width" the caller asked for).
+ * dev_dets: [N][capacity][DAFNE_DET_STRIDE] fp32, rows in descending score; dev_counts: [N] int32 = number of
+ * detections the reference would return (may exceed `capacity` only through exact score ties at the top-k cut; rows
+ * beyond capacity are dropped and the count still reports them). */
+int dafne_postprocess(dafne_ctx* ctx, const int32_t* image_sizes, const int32_t* output_sizes, int do_postprocess,
+                      float* dev_dets, int32_t* dev_counts, int capacity, void* stream);
+
+/* Same post-processing on caller-provided head outputs in the reference's own form (fp32, NHWC views of the
+ * reference's NCHW tensors): per level logits [N,H_l*W_l,C], reg [N,H_l*W_l,8] (= corners_reg_pred, i.e. already
+ * (center.repeat + delta) * scale), ctr [N,H_l*W_l]. This is the bit-exact parity gate. */
+int dafne_postprocess_external(dafne_ctx* ctx, int N, const int32_t* level_hw /* L x (H_l, W_l) */,
+                               const float* const* dev_logits, const float* const* dev_reg,
+                               const float* const* dev_ctr, const int32_t* image_sizes, const int32_t* output_sizes,
+                               int do_postprocess, float* dev_dets, int32_t* dev_counts, int capacity,
+                               void* dev_scratch, size_t scratch_bytes, void* stream);
+int dafne_postprocess_scratch_bytes(dafne_ctx* ctx, int N, const int32_t* level_hw, size_t* bytes);
+
+/* forward_dense + postprocess on device buffers. */
+int dafne_detect(dafne_ctx* ctx, const void* dev_images, int dtype, const int32_t* image_sizes,
+                 const int32_t* output_sizes, float* dev_dets, int32_t* dev_counts, int capacity, void* stream);
+
+/* The reference-facing call with HOST buffers: copies images H2D, runs dafne_detect, copies detections and counts
+ * D2H and synchronises `stream`. host_images should be pinned for full copy bandwidth. */
+int dafne_detect_host(dafne_ctx* ctx, const void* host_images, int dtype, const int32_t* image_sizes,
+                      const int32_t* output_sizes, float* host_dets, int32_t* host_counts, int capacity,
+                      void* stream);
+
+/* Counters for bench.py: kernels launched by this library since the last reset, and conv FLOPs (2*MACs). */
+int dafne_stats(dafne_ctx* ctx, int64_t* kernel_launches, double* conv_flops, int reset);
+
+/* ------------------------------------------------------------------ per-kernel hooks (tests, A/B) */
+/* One convolution through the tcgen05 kernel. NHWC fp16 in/out, weights [Cout][k*k][Cin] fp16.
+ * Exactly one of out_f16 / out_f32 is non-NULL (out_f32: Cout <= 32, row pitch out_ld). */
+int dafne_conv_nhwc(const void* dev_in_f16, int N, int H, int W, int Cin, const void* dev_w_f16, int Cout, int ksize,
+                    int stride, const float* dev_scale, const float* dev_shift, int relu,
+                    const void* dev_residual_f16, int res_H, int res_W, int res_shift, float* dev_gn_sums,
+                    void* dev_out_f16, float* dev_out_f32, int out_ld, void* stream);
+
+/* GroupNorm apply + ReLU on NHWC fp16 from per-(image, group) sums produced by dafne_conv_nhwc. */
+int dafne_gn_relu_nhwc(const void* dev_in_f16, void* dev_out_f16, int N, int HW, int C, int groups,
+                       const float* dev_gn_sums, const float* dev_gamma, const float* dev_beta, float eps,
+                       void* stream);
+
+/* sort_quadrilateral on device: quads [n,8] fp32 -> out [n,8] fp32 (sort_corners.py:26-92). */
+int dafne_sort_quadrilateral(const float* dev_quads, float* dev_out, int n, void* stream);
+
+/* Pairwise polygon IoU on device in the faithful fp32 arithmetic: iou[i] = IoU(p[i], q[i]). */
+int dafne_poly_iou(const float* dev_p, const float* dev_q, float* dev_iou, int n, void* stream);
+
+/* Class-aware polygon NMS of one image (ml_nms -> batched_nms_poly -> poly_gpu_nms semantics): polys [n,8], scores
+ * [n], classes [n] int32, all on device. dev_keep receives the kept input indices in descending score order
+ * (ties: ascending input index), dev_nkeep their number. Workspace via dafne_poly_nms_scratch_bytes. */
+int dafne_poly_nms(const float* dev_polys, const float* dev_scores, const int32_t* dev_classes, int n,
+                   float nms_thresh, int vehicle_merge, int32_t* dev_keep, int32_t* dev_nkeep, void* dev_scratch,
+                   size_t scratch_bytes, void* stream);
+int dafne_poly_nms_scratch_bytes(int n, size_t* bytes);
+
+/* Drop-in for the reference's native FFI  poly_gpu_nms(dets, thresh, device_id) / _poly_nms(keep_out, num_out,
+ * polys_host, polys_num, polys_dim, thresh, device_id):  host pointers in and out, dets = [n][9] fp32 (8 coords +
+ * score, class offsets already applied by the caller), synchronous. */
+int dafne_poly_nms_host(int* keep_out, int* num_out, const float* polys_host, int polys_num, int polys_dim,
+                        float nms_overlap_thresh, int device_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAFNE_B200_H */

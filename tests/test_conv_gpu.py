@@ -1,0 +1,138 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution against a plain PyTorch fp32 reference of the same op.
+
+The kernel computes fp16 x fp16 -> fp32 accumulate and stores fp16 (or fp32 for the small prediction convs), so the
+reference is torch conv2d in fp32 (TF32 off) on the SAME fp16-rounded inputs and weights; the tolerance is one fp16
+rounding of the output plus accumulation-order noise: |err| <= 2e-3 * max|ref| + 2e-3 * |ref|.
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+CASES = [
+    # name, N, H, W, Cin, Cout, k, stride, opts
+    ("1x1_64_64", 2, 32, 32, 64, 64, 1, 1, {}),
+    ("3x3_256_256_bias_gn", 1, 64, 64, 256, 256, 3, 1, {"shift": True, "gn": True}),
+    ("1x1s2_256_128_bn_relu", 2, 64, 64, 256, 128, 1, 2, {"scale": True, "shift": True, "relu": True}),
+    ("3x3s2_256_256_p6", 2, 32, 32, 256, 256, 3, 2, {"shift": True}),
+    ("3x3s2_odd25", 1, 25, 25, 256, 256, 3, 2, {"shift": True}),
+    ("1x1_64_256_residual_relu", 2, 32, 32, 64, 256, 1, 1, {"scale": True, "shift": True, "relu": True, "res": 0}),
+    ("1x1_512_256_fpn_upsample_add", 1, 32, 32, 512, 256, 1, 1, {"shift": True, "res": 1}),
+    ("3x3_256_15_pred_f32", 2, 32, 32, 256, 15, 3, 1, {"shift": True, "f32": 16}),
+    ("3x3_256_9_pred_f32", 1, 16, 16, 256, 9, 3, 1, {"shift": True, "f32": 16}),
+    ("3x3_odd50_gn", 1, 50, 50, 256, 256, 3, 1, {"shift": True, "gn": True}),
+    ("3x3_8x8_n3_gn", 3, 8, 8, 256, 256, 3, 1, {"shift": True, "gn": True}),
+    ("3x3_4x4_n5_gn", 5, 4, 4, 256, 256, 3, 1, {"shift": True, "gn": True}),
+    ("3x3_7x7_n2", 2, 7, 7, 256, 256, 3, 1, {"shift": True}),
+    ("3x3_128_128", 1, 64, 64, 128, 128, 3, 1, {"scale": True, "shift": True, "relu": True}),
+    ("3x3_512_512", 1, 32, 32, 512, 512, 3, 1, {"scale": True, "shift": True, "relu": True}),
+    ("1x1_1024_2048s2", 1, 16, 16, 1024, 2048, 1, 2, {"scale": True, "shift": True}),
+    ("3x3_256_256_multiwave", 2, 128, 128, 256, 256, 3, 1, {"shift": True, "gn": True}),
+]
+
+
+def run_conv_case(lib, name, N, H, W, Cin, Cout, k, stride, opts, seed=0):
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.randn(N, Cin, H, W, generator=g) * 1.0).half()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).half()
+    scale = (torch.rand(Cout, generator=g) + 0.5) if opts.get("scale") else None
+    shift = torch.randn(Cout, generator=g) if opts.get("shift") else None
+    pad = k // 2
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    res = None
+    rs = opts.get("res")
+    if rs is not None:
+        rH, rW = (Ho + (1 << rs) - 1) >> rs, (Wo + (1 << rs) - 1) >> rs
+        res = torch.randn(N, Cout, rH, rW, generator=g).half()
+
+    x_d = x.to(dev).permute(0, 2, 3, 1).contiguous()
+    w_d = w.to(dev).permute(0, 2, 3, 1).contiguous()  # [Cout][kh][kw][Cin]
+    scale_d = scale.to(dev) if scale is not None else None
+    shift_d = shift.to(dev) if shift is not None else None
+    res_d = res.to(dev).permute(0, 2, 3, 1).contiguous() if res is not None else None
+    f32_ld = opts.get("f32")
+    if f32_ld:
+        out_d = torch.full((N, Ho, Wo, f32_ld), float("nan"), device=dev, dtype=torch.float32)
+    else:
+        out_d = torch.full((N, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.float16)
+    sums_d = torch.zeros(N, Cout // 8, 2, device=dev, dtype=torch.float32) if opts.get("gn") else None
+
+    def p(t):
+        return C.c_void_p(0 if t is None else t.data_ptr())
+
+    st = lib.dafne_conv_nhwc(
+        p(x_d), N, H, W, Cin, p(w_d), Cout, k, stride, p(scale_d), p(shift_d), int(bool(opts.get("relu"))),
+        p(res_d), 0 if res is None else res.shape[2], 0 if res is None else res.shape[3], rs or 0, p(sums_d),
+        p(None if f32_ld else out_d), p(out_d if f32_ld else None), f32_ld or 0,
+        C.c_void_p(torch.cuda.current_stream().cuda_stream),
+    )
+    assert st == 0, lib.dafne_last_error()
+    torch.cuda.synchronize()
+
+    # plain PyTorch fp32 reference on the same fp16-rounded operands
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(x.to(dev).float(), w.to(dev).float(), None, stride, pad)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    if scale is not None:
+        ref = ref * scale.to(dev).view(1, -1, 1, 1)
+    if shift is not None:
+        ref = ref + shift.to(dev).view(1, -1, 1, 1)
+    if res is not None:
+        r = res.to(dev).float()
+        if rs:
+            r = F.interpolate(r, scale_factor=2, mode="nearest")[:, :, :Ho, :Wo]
+        ref = ref + r
+    if opts.get("relu"):
+        ref = ref.relu()
+    ref = ref.permute(0, 2, 3, 1)
+    got = out_d.float()[..., :Cout]
+    assert torch.isfinite(got).all(), f"{name}: non-finite / unwritten outputs"
+    err = (got - ref).abs()
+    tol = 2e-3 * ref.abs().max() + 2e-3 * ref.abs()
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{name}: {bad} of {err.numel()} outside tolerance, max err {err.max().item():.4g}"
+    if f32_ld and f32_ld > Cout:
+        assert (out_d[..., Cout:] == 0).all(), f"{name}: padded output channels must be exactly 0"
+    if sums_d is not None:
+        q = out_d.float().reshape(N, Ho * Wo, Cout // 8, 8)
+        s1 = q.sum(dim=(1, 3))
+        s2 = (q * q).sum(dim=(1, 3))
+        assert torch.allclose(sums_d[..., 0], s1, rtol=1e-3, atol=1e-2), f"{name}: GN sum mismatch"
+        assert torch.allclose(sums_d[..., 1], s2, rtol=1e-3, atol=1e-2), f"{name}: GN sumsq mismatch"
+    return err.max().item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_tc_matches_torch_fp32(case):
+    from dafne_b200 import _capi
+
+    run_conv_case(_capi.lib(), *case)
+
+
+@pytest.mark.gpu
+def test_gn_relu_matches_torch():
+    from dafne_b200 import _capi
+
+    lib = _capi.lib()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(1)
+    N, H, W, Cc = 3, 20, 12, 256
+    x = (torch.randn(N, Cc, H, W, generator=g) * 2 + 0.5).half().to(dev)
+    gamma = (torch.rand(Cc, generator=g) + 0.5).to(dev)
+    beta = torch.randn(Cc, generator=g).to(dev)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    q = x_nhwc.float().reshape(N, H * W, 32, 8)
+    sums = torch.stack([q.sum(dim=(1, 3)), (q * q).sum(dim=(1, 3))], dim=-1).contiguous()
+    out = torch.empty_like(x_nhwc)
+    st = lib.dafne_gn_relu_nhwc(x_nhwc.data_ptr(), out.data_ptr(), N, H * W, Cc, 32, sums.data_ptr(),
+                                gamma.data_ptr(), beta.data_ptr(), 1e-5, torch.cuda.current_stream().cuda_stream)
+    assert st == 0, lib.dafne_last_error()
+    ref = F.relu(F.group_norm(x.float(), 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+    assert torch.allclose(out.float(), ref, rtol=2e-3, atol=2e-3)
