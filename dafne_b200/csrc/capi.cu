@@ -6,6 +6,10 @@
 
 #include "conv_tc.cuh"
 #include "elementwise.cuh"
+#include "model.cuh"
+#include "postprocess.cuh"
+#include <string.h>
+#include <vector>
 
 using namespace dafne;
 
@@ -65,6 +69,252 @@ int dafne_gn_relu_nhwc(const void* in, void* out, int N, int HW, int C, int grou
                        const float* gamma, const float* beta, float eps, void* stream) {
     return launch_gn_relu(static_cast<const __half*>(in), static_cast<__half*>(out), N, HW, C, groups, sums, gamma,
                           beta, eps, static_cast<cudaStream_t>(stream));
+}
+
+
+#define NEED_CTX(ctx, fn)                          \
+    if (!(ctx)) {                                  \
+        set_error(fn ": ctx is NULL");             \
+        return -1;                                 \
+    }
+
+int dafne_ctx_create(const dafne_model_spec* spec, int device, dafne_ctx** out) { return ctx_create(spec, device, out); }
+void dafne_ctx_destroy(dafne_ctx* ctx) { ctx_destroy(ctx); }
+
+int dafne_load_weights(dafne_ctx* ctx, int count, const char* const* names, const float* const* dev_ptrs,
+                       const int64_t* shapes, void* stream) {
+    NEED_CTX(ctx, "dafne_load_weights");
+    return ctx_load_weights(ctx, count, names, dev_ptrs, shapes, static_cast<cudaStream_t>(stream));
+}
+int dafne_weights_finalize(dafne_ctx* ctx, void* stream) {
+    NEED_CTX(ctx, "dafne_weights_finalize");
+    return ctx_finalize(ctx, static_cast<cudaStream_t>(stream));
+}
+int dafne_workspace_bytes(dafne_ctx* ctx, int N, int H, int W, size_t* bytes) {
+    NEED_CTX(ctx, "dafne_workspace_bytes");
+    return ctx_plan(ctx, N, H, W, nullptr, 0, bytes);
+}
+int dafne_bind_workspace(dafne_ctx* ctx, int N, int H, int W, void* ws, size_t bytes) {
+    NEED_CTX(ctx, "dafne_bind_workspace");
+    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 1023u)) {
+        set_error("dafne_bind_workspace: workspace must be non-NULL and 1024-byte aligned");
+        return -1;
+    }
+    size_t need = 0;
+    return ctx_plan(ctx, N, H, W, static_cast<uint8_t*>(ws), bytes, &need);
+}
+int dafne_forward_dense(dafne_ctx* ctx, const void* images, int dtype, const int32_t* image_sizes, void* stream) {
+    NEED_CTX(ctx, "dafne_forward_dense");
+    return ctx_forward(ctx, images, dtype, image_sizes, static_cast<cudaStream_t>(stream));
+}
+int dafne_head_output(dafne_ctx* ctx, int level, int which, const float** ptr, int* ld, int* h, int* w) {
+    NEED_CTX(ctx, "dafne_head_output");
+    if (level < 0 || level >= 5 || which < 0 || which > 2 || !ctx->ws) {
+        set_error("dafne_head_output: bad level/which or no workspace bound");
+        return -1;
+    }
+    const HeadOut& o = ctx->head_out[level][which];
+    if (ptr) *ptr = o.p;
+    if (ld) *ld = o.ld;
+    if (h) *h = o.H;
+    if (w) *w = o.W;
+    return 0;
+}
+int dafne_postprocess(dafne_ctx* ctx, const int32_t* image_sizes, const int32_t* output_sizes, int do_postprocess,
+                      float* dets, int32_t* counts, int capacity, void* stream) {
+    NEED_CTX(ctx, "dafne_postprocess");
+    return ctx_postprocess(ctx, image_sizes, output_sizes, do_postprocess, dets, counts, capacity,
+                           static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+__global__ void set_sizes4_kernel(const int32_t* __restrict__ src, int32_t* dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+}  // namespace
+
+int dafne_postprocess_scratch_bytes(dafne_ctx* ctx, int N, const int32_t* level_hw, size_t* bytes) {
+    NEED_CTX(ctx, "dafne_postprocess_scratch_bytes");
+    int hw[10];
+    for (int i = 0; i < 10; ++i) hw[i] = level_hw[i];
+    // + room for the [N][4] size table
+    *bytes = postprocess_scratch_bytes(N, 5, hw, ctx->spec.num_classes, ctx->spec.pre_nms_topk) + 256 +
+             static_cast<size_t>(N) * 16;
+    return 0;
+}
+
+int dafne_postprocess_external(dafne_ctx* ctx, int N, const int32_t* level_hw, const float* const* logits,
+                               const float* const* reg, const float* const* ctr, const int32_t* image_sizes,
+                               const int32_t* output_sizes, int do_postprocess, float* dets, int32_t* counts,
+                               int capacity, void* scratch, size_t scratch_bytes, void* stream) {
+    NEED_CTX(ctx, "dafne_postprocess_external");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int hw[10];
+    for (int i = 0; i < 10; ++i) hw[i] = level_hw[i];
+    const size_t core = postprocess_scratch_bytes(N, 5, hw, ctx->spec.num_classes, ctx->spec.pre_nms_topk);
+    if (core + 256 + static_cast<size_t>(N) * 16 > scratch_bytes) {
+        set_error("dafne_postprocess_external: scratch too small (%zu < %zu)", scratch_bytes,
+                  core + 256 + static_cast<size_t>(N) * 16);
+        return -1;
+    }
+    int32_t* sizes_dev = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(scratch) + (core + 255) / 256 * 256);
+    std::vector<int32_t> sz(static_cast<size_t>(N) * 4);
+    for (int n = 0; n < N; ++n) {
+        sz[4 * n] = image_sizes[2 * n];
+        sz[4 * n + 1] = image_sizes[2 * n + 1];
+        sz[4 * n + 2] = output_sizes ? output_sizes[2 * n] : image_sizes[2 * n];
+        sz[4 * n + 3] = output_sizes ? output_sizes[2 * n + 1] : image_sizes[2 * n + 1];
+    }
+    // test / A-B entry point: a synchronous pageable copy is fine here
+    cudaError_t e = cudaMemcpyAsync(sizes_dev, sz.data(), sz.size() * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        set_error("dafne_postprocess_external: size upload: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    PostParams p;
+    memset(&p, 0, sizeof(p));
+    fill_post_spec(ctx, &p);
+    p.N = N;
+    for (int l = 0; l < 5; ++l) {
+        PostLevel& lv = p.lv[l];
+        lv.logits = logits[l];
+        lv.ld_logits = ctx->spec.num_classes;
+        lv.ctr = ctr[l];
+        lv.ld_ctr = 1;
+        lv.reg = reg[l];
+        lv.ld_reg = 8;
+        lv.center = nullptr;
+        lv.ld_center = 0;
+        lv.H = hw[2 * l];
+        lv.W = hw[2 * l + 1];
+    }
+    p.scales_dev = nullptr;
+    p.do_postprocess = do_postprocess;
+    p.sizes_dev = sizes_dev;
+    p.dets = dets;
+    p.counts = counts;
+    p.capacity = capacity;
+    p.scratch = scratch;
+    p.scratch_bytes = core;
+    return launch_postprocess(p, s, &ctx->stat_launches);
+}
+
+int dafne_detect(dafne_ctx* ctx, const void* images, int dtype, const int32_t* image_sizes,
+                 const int32_t* output_sizes, float* dets, int32_t* counts, int capacity, void* stream) {
+    NEED_CTX(ctx, "dafne_detect");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (ctx_forward(ctx, images, dtype, image_sizes, s)) return -1;
+    return ctx_postprocess(ctx, image_sizes, output_sizes, 1, dets, counts, capacity, s);
+}
+
+int dafne_detect_host(dafne_ctx* ctx, const void* host_images, int dtype, const int32_t* image_sizes,
+                      const int32_t* output_sizes, float* host_dets, int32_t* host_counts, int capacity,
+                      void* stream) {
+    NEED_CTX(ctx, "dafne_detect_host");
+    if (!ctx->ws) {
+        set_error("dafne_detect_host: no workspace bound");
+        return -1;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t esz = dtype == 0 ? 1 : 4;
+    const size_t bytes = static_cast<size_t>(ctx->N) * 3 * ctx->H * ctx->W * esz;
+    if (capacity > ctx->dets_capacity) capacity = ctx->dets_capacity;
+    cudaError_t e = cudaMemcpyAsync(ctx->images_dev, host_images, bytes, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) {
+        set_error("dafne_detect_host H2D: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    if (dafne_detect(ctx, ctx->images_dev, dtype, image_sizes, output_sizes, ctx->dets_dev, ctx->counts_dev, capacity,
+                     stream))
+        return -1;
+    e = cudaMemcpyAsync(host_dets, ctx->dets_dev, static_cast<size_t>(ctx->N) * capacity * DAFNE_DET_STRIDE * 4,
+                        cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(host_counts, ctx->counts_dev, static_cast<size_t>(ctx->N) * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        set_error("dafne_detect_host D2H: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
+int dafne_stats(dafne_ctx* ctx, int64_t* launches, double* flops, int reset) {
+    NEED_CTX(ctx, "dafne_stats");
+    if (launches) *launches = ctx->stat_launches;
+    if (flops) *flops = ctx->stat_flops;
+    if (reset) {
+        ctx->stat_launches = 0;
+        ctx->stat_flops = 0;
+    }
+    return 0;
+}
+
+int dafne_sort_quadrilateral(const float* quads, float* out, int n, void* stream) {
+    return launch_sort_quadrilateral(quads, out, n, static_cast<cudaStream_t>(stream));
+}
+int dafne_poly_iou(const float* p, const float* q, float* iou, int n, void* stream) {
+    return launch_poly_iou(p, q, iou, n, static_cast<cudaStream_t>(stream));
+}
+int dafne_poly_nms_scratch_bytes(int n, size_t* bytes) {
+    *bytes = poly_nms_scratch_bytes(n);
+    return 0;
+}
+int dafne_poly_nms(const float* polys, const float* scores, const int32_t* classes, int n, float thr,
+                   int vehicle_merge, int32_t* keep, int32_t* nkeep, void* scratch, size_t scratch_bytes,
+                   void* stream) {
+    return launch_poly_nms(polys, scores, classes, n, thr, vehicle_merge, keep, nkeep, scratch, scratch_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
+// Drop-in for the reference's native FFI (host pointers, own allocations, synchronous) -- nms.py:91.
+int dafne_poly_nms_host(int* keep_out, int* num_out, const float* polys_host, int n, int dim, float thr,
+                        int device_id) {
+    if (dim != 9 || !keep_out || !num_out || (n > 0 && !polys_host)) {
+        set_error("dafne_poly_nms_host: expects dets [n][9] = 8 coords + score");
+        return -1;
+    }
+    *num_out = 0;
+    if (n <= 0) return 0;
+    cudaError_t e = cudaSetDevice(device_id);
+    if (e != cudaSuccess) {
+        set_error("dafne_poly_nms_host: cudaSetDevice(%d): %s", device_id, cudaGetErrorString(e));
+        return -1;
+    }
+    std::vector<float> polys(static_cast<size_t>(n) * 8), scores(n);
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 8; ++k) polys[8 * i + k] = polys_host[9 * i + k];
+        scores[i] = polys_host[9 * i + 8];
+    }
+    const size_t sb = poly_nms_scratch_bytes(n);
+    uint8_t* dev = nullptr;
+    const size_t o_scores = static_cast<size_t>(n) * 32, o_keep = o_scores + static_cast<size_t>(n) * 4,
+                 o_nk = o_keep + static_cast<size_t>(n) * 4, o_scr = (o_nk + 4 + 1023) / 1024 * 1024;
+    e = cudaMalloc(&dev, o_scr + sb);
+    if (e != cudaSuccess) {
+        set_error("dafne_poly_nms_host: cudaMalloc: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    int rc = -1;
+    do {
+        if (cudaMemcpy(dev, polys.data(), polys.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) break;
+        if (cudaMemcpy(dev + o_scores, scores.data(), scores.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) break;
+        // offsets were applied by the caller (batched_nms_poly), so classes = NULL (all zero)
+        if (launch_poly_nms(reinterpret_cast<float*>(dev), reinterpret_cast<float*>(dev + o_scores), nullptr, n, thr, 0,
+                            reinterpret_cast<int32_t*>(dev + o_keep), reinterpret_cast<int32_t*>(dev + o_nk),
+                            dev + o_scr, sb, nullptr))
+            break;
+        if (cudaMemcpy(num_out, dev + o_nk, 4, cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        if (*num_out > 0 &&
+            cudaMemcpy(keep_out, dev + o_keep, static_cast<size_t>(*num_out) * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+            break;
+        rc = 0;
+    } while (0);
+    if (rc != 0 && get_error()[0] == 0) set_error("dafne_poly_nms_host: CUDA copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(dev);
+    return rc;
 }
 
 }  // extern "C"

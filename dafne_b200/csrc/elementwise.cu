@@ -212,7 +212,7 @@ int launch_maxpool3x3s2(const __half* in, int N, int H, int W, int C, __half* ou
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm + ReLU
-__global__ void gn_relu_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int HW, int C,
+__global__ void gn_relu_kernel(const __half* in, __half* out, int N, int HW, int C,
                                int groups, const float* __restrict__ sums, const float* __restrict__ gamma,
                                const float* __restrict__ beta, float eps) {
     const int c8 = C / 8;  // one uint4 = one group of 8 channels
@@ -228,7 +228,7 @@ __global__ void gn_relu_kernel(const __half* __restrict__ in, __half* __restrict
         const float mean = s1 * inv_cnt;
         const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + i);
+        const uint4 v = reinterpret_cast<const uint4*>(in)[i];  // may alias out (in-place)
         const uint32_t vin[4] = {v.x, v.y, v.z, v.w};
         uint32_t vo[4];
 #pragma unroll

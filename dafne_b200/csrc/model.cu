@@ -1,0 +1,683 @@
+// Dense forward of the DAFNe detector as a static launch plan over caller-owned memory.
+//
+// Graph restated (semantics, not code) from:
+//   detectron2 v0.5 ResNet (MSRA, STRIDE_IN_1X1, FrozenBN) + FPN(sum, no norm)   dafne/modeling/backbone/fpn.py:58-91
+//   LastLevelP6P7: p6 = conv3x3s2(p5), p7 = conv3x3s2(relu(p6))                  dafne/modeling/backbone/fpn.py:16-37
+//   DAFNeHead (center-to-corner, GN towers, CTR_ON_REG, corner tower on center)  dafne/modeling/dafne/dafne.py:287-348,388-414,462-471
+// Weights arrive under their detectron2 state-dict names and are packed on device (fp16 [Cout][tap][Cin]; FrozenBN
+// folded to per-channel scale/shift).
+#include "model.cuh"
+
+#include <stdio.h>
+#include <string.h>
+
+#include "elementwise.cuh"
+
+namespace dafne {
+
+#define CUDA_OK(expr)                                                                  \
+    do {                                                                               \
+        cudaError_t e__ = (expr);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            set_error("%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return -1;                                                                 \
+        }                                                                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ arena
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t Arena::alloc(size_t bytes) {
+    bytes = align_up(bytes ? bytes : 1, 1024);
+    // best fit among free blocks
+    auto best = free_.end();
+    for (auto it = free_.begin(); it != free_.end(); ++it)
+        if (it->second >= bytes && (best == free_.end() || it->second < best->second)) best = it;
+    if (best != free_.end()) {
+        size_t off = best->first, sz = best->second;
+        free_.erase(best);
+        if (sz > bytes) free_[off + bytes] = sz - bytes;
+        return off;
+    }
+    size_t off = top;
+    top += bytes;
+    if (top > peak) peak = top;
+    return off;
+}
+
+void Arena::release(size_t off, size_t bytes) {
+    bytes = align_up(bytes ? bytes : 1, 1024);
+    auto it = free_.emplace(off, bytes).first;
+    // coalesce with next
+    auto nx = std::next(it);
+    if (nx != free_.end() && it->first + it->second == nx->first) {
+        it->second += nx->second;
+        free_.erase(nx);
+    }
+    if (it != free_.begin()) {
+        auto pv = std::prev(it);
+        if (pv->first + pv->second == it->first) {
+            pv->second += it->second;
+            free_.erase(it);
+            it = pv;
+        }
+    }
+    if (it->first + it->second == top) {
+        top = it->first;
+        free_.erase(it);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ model description
+static int expect_param(dafne_ctx* c, const std::string& name, int64_t a, int64_t b = 1, int64_t d = 1, int64_t e = 1) {
+    ParamSlot s;
+    s.shape[0] = a;
+    s.shape[1] = b;
+    s.shape[2] = d;
+    s.shape[3] = e;
+    s.numel = a * b * d * e;
+    CUDA_OK(cudaMalloc(&s.raw, s.numel * sizeof(float)));
+    c->params.emplace(name, s);
+    c->param_order.push_back(name);
+    return 0;
+}
+
+static int add_conv(dafne_ctx* c, std::vector<ConvPart> parts, int Cin, int k, int stride, bool bn) {
+    ConvLayer L;
+    L.parts = parts;
+    L.Cin = Cin;
+    L.k = k;
+    L.stride = stride;
+    L.bn = bn;
+    L.Cout = 0;
+    for (auto& p : parts) {
+        L.Cout += p.cout;
+        if (expect_param(c, p.prefix + ".weight", p.cout, Cin, k, k)) return -1;
+        if (bn) {
+            for (const char* s : {".norm.weight", ".norm.bias", ".norm.running_mean", ".norm.running_var"})
+                if (expect_param(c, p.prefix + s, p.cout)) return -1;
+        } else {
+            if (expect_param(c, p.prefix + ".bias", p.cout)) return -1;
+        }
+    }
+    c->conv_index[parts[0].prefix] = static_cast<int>(c->convs.size());
+    c->convs.push_back(L);
+    return 0;
+}
+
+static const int* stage_blocks(int depth) {
+    static const int r50[4] = {3, 4, 6, 3};
+    static const int r101[4] = {3, 4, 23, 3};
+    return depth == 50 ? r50 : (depth == 101 ? r101 : nullptr);
+}
+
+static const char* kTowers[3] = {"cls_tower", "center_tower", "corners_tower"};
+static const std::string kBU = "backbone.bottom_up.";
+static const std::string kHead = "proposal_generator.dafne_head.";
+
+int ctx_create(const dafne_model_spec* spec, int device, dafne_ctx** out) {
+    if (!spec || !out) {
+        set_error("dafne_ctx_create: null argument");
+        return -1;
+    }
+    if (!stage_blocks(spec->resnet_depth)) {
+        set_error("dafne_ctx_create: resnet_depth %d unsupported (50 | 101)", spec->resnet_depth);
+        return -1;
+    }
+    if (spec->num_levels != 5 || spec->num_classes < 1 || spec->num_classes > 32) {
+        set_error("dafne_ctx_create: need num_levels == 5 and 1 <= num_classes <= 32 (got %d, %d)", spec->num_levels,
+                  spec->num_classes);
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(device));
+    dafne_ctx* c = new dafne_ctx();
+    c->spec = *spec;
+    c->device = device;
+    CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+
+    // stem
+    if (expect_param(c, kBU + "stem.conv1.weight", 64, 3, 7, 7)) return -1;
+    for (const char* s : {".norm.weight", ".norm.bias", ".norm.running_mean", ".norm.running_var"})
+        if (expect_param(c, kBU + "stem.conv1" + s, 64)) return -1;
+    // bottlenecks
+    const int* nb = stage_blocks(spec->resnet_depth);
+    int in_ch = 64, mid = 64, out_ch = 256;
+    for (int s = 2; s <= 5; ++s) {
+        for (int b = 0; b < nb[s - 2]; ++b) {
+            const std::string pre = kBU + "res" + std::to_string(s) + "." + std::to_string(b);
+            const int stride = (b == 0 && s > 2) ? 2 : 1;
+            if (b == 0 && add_conv(c, {{pre + ".shortcut", out_ch}}, in_ch, 1, stride, true)) return -1;
+            if (add_conv(c, {{pre + ".conv1", mid}}, in_ch, 1, stride, true)) return -1;  // STRIDE_IN_1X1
+            if (add_conv(c, {{pre + ".conv2", mid}}, mid, 3, 1, true)) return -1;
+            if (add_conv(c, {{pre + ".conv3", out_ch}}, mid, 1, 1, true)) return -1;
+            in_ch = out_ch;
+        }
+        mid *= 2;
+        out_ch *= 2;
+    }
+    // FPN
+    const int feat_ch[3] = {512, 1024, 2048};
+    for (int i = 0; i < 3; ++i) {
+        if (add_conv(c, {{"backbone.fpn_lateral" + std::to_string(3 + i), 256}}, feat_ch[i], 1, 1, false)) return -1;
+        if (add_conv(c, {{"backbone.fpn_output" + std::to_string(3 + i), 256}}, 256, 3, 1, false)) return -1;
+    }
+    if (add_conv(c, {{"backbone.top_block.p6", 256}}, 256, 3, 2, false)) return -1;
+    if (add_conv(c, {{"backbone.top_block.p7", 256}}, 256, 3, 2, false)) return -1;
+    // head
+    for (int t = 0; t < 3; ++t)
+        for (int i = 0; i < 4; ++i) {
+            const std::string tw = kHead + kTowers[t] + ".";
+            if (add_conv(c, {{tw + std::to_string(3 * i), 256}}, 256, 3, 1, false)) return -1;
+            if (expect_param(c, tw + std::to_string(3 * i + 1) + ".weight", 256)) return -1;
+            if (expect_param(c, tw + std::to_string(3 * i + 1) + ".bias", 256)) return -1;
+        }
+    if (add_conv(c, {{kHead + "cls_logits", spec->num_classes}}, 256, 3, 1, false)) return -1;
+    if (add_conv(c, {{kHead + "ctrness", 1}, {kHead + "corners_pred", 8}}, 256, 3, 1, false)) return -1;
+    if (add_conv(c, {{kHead + "center_pred", 2}}, 256, 3, 1, false)) return -1;
+    for (int l = 0; l < 5; ++l)
+        if (expect_param(c, kHead + "scales." + std::to_string(l) + ".scale", 1)) return -1;
+    *out = c;
+    return 0;
+}
+
+void ctx_destroy(dafne_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto& kv : c->params)
+        if (kv.second.raw) cudaFree(kv.second.raw);
+    for (auto& L : c->convs) {
+        if (L.w) cudaFree(L.w);
+        if (L.scale) cudaFree(L.scale);
+        if (L.shift) cudaFree(L.shift);
+    }
+    if (c->stem_w) cudaFree(c->stem_w);
+    if (c->stem_scale) cudaFree(c->stem_scale);
+    if (c->stem_shift) cudaFree(c->stem_shift);
+    if (c->scales_dev) cudaFree(c->scales_dev);
+    delete c;
+}
+
+int ctx_load_weights(dafne_ctx* c, int count, const char* const* names, const float* const* ptrs,
+                     const int64_t* shapes, cudaStream_t s) {
+    CUDA_OK(cudaSetDevice(c->device));
+    for (int i = 0; i < count; ++i) {
+        auto it = c->params.find(names[i]);
+        if (it == c->params.end()) {
+            set_error("dafne_load_weights: unknown tensor name '%s'", names[i]);
+            return -1;
+        }
+        ParamSlot& p = it->second;
+        const int64_t* sh = shapes + 4 * i;
+        const int64_t numel = sh[0] * sh[1] * sh[2] * sh[3];
+        bool same = numel == p.numel;
+        for (int d = 0; d < 4 && same; ++d) same = sh[d] == p.shape[d];
+        if (!same) {
+            set_error("dafne_load_weights: '%s' has shape [%lld,%lld,%lld,%lld], expected [%lld,%lld,%lld,%lld]",
+                      names[i], (long long)sh[0], (long long)sh[1], (long long)sh[2], (long long)sh[3],
+                      (long long)p.shape[0], (long long)p.shape[1], (long long)p.shape[2], (long long)p.shape[3]);
+            return -1;
+        }
+        CUDA_OK(cudaMemcpyAsync(p.raw, ptrs[i], numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        p.loaded = true;
+    }
+    c->finalized = false;
+    return 0;
+}
+
+static float* raw_of(dafne_ctx* c, const std::string& name) { return c->params.at(name).raw; }
+
+int ctx_finalize(dafne_ctx* c, cudaStream_t s) {
+    CUDA_OK(cudaSetDevice(c->device));
+    for (auto& name : c->param_order)
+        if (!c->params.at(name).loaded) {
+            set_error("dafne_weights_finalize: tensor '%s' was never loaded", name.c_str());
+            return -1;
+        }
+    const float bn_eps = 1e-5f;  // detectron2 FrozenBatchNorm2d default
+    if (!c->stem_w) {
+        CUDA_OK(cudaMalloc(&c->stem_w, 49 * 4 * 64 * sizeof(float)));
+        CUDA_OK(cudaMalloc(&c->stem_scale, 64 * sizeof(float)));
+        CUDA_OK(cudaMalloc(&c->stem_shift, 64 * sizeof(float)));
+        CUDA_OK(cudaMalloc(&c->scales_dev, 8 * sizeof(float)));
+    }
+    const std::string st = kBU + "stem.conv1";
+    if (launch_pack_stem_weight(raw_of(c, st + ".weight"), c->stem_w, s)) return -1;
+    if (launch_fold_bn(raw_of(c, st + ".norm.weight"), raw_of(c, st + ".norm.bias"),
+                       raw_of(c, st + ".norm.running_mean"), raw_of(c, st + ".norm.running_var"), bn_eps, 64,
+                       c->stem_scale, c->stem_shift, s))
+        return -1;
+    for (auto& L : c->convs) {
+        const size_t kk = static_cast<size_t>(L.k) * L.k;
+        if (!L.w) {
+            CUDA_OK(cudaMalloc(&L.w, L.Cout * kk * L.Cin * sizeof(__half)));
+            CUDA_OK(cudaMalloc(&L.shift, L.Cout * sizeof(float)));
+            if (L.bn) CUDA_OK(cudaMalloc(&L.scale, L.Cout * sizeof(float)));
+        }
+        int row = 0;
+        for (auto& p : L.parts) {
+            if (launch_pack_conv_weight(raw_of(c, p.prefix + ".weight"), p.cout, L.Cin, L.k, L.w + row * kk * L.Cin, s))
+                return -1;
+            if (L.bn) {
+                if (launch_fold_bn(raw_of(c, p.prefix + ".norm.weight"), raw_of(c, p.prefix + ".norm.bias"),
+                                   raw_of(c, p.prefix + ".norm.running_mean"),
+                                   raw_of(c, p.prefix + ".norm.running_var"), bn_eps, p.cout, L.scale + row,
+                                   L.shift + row, s))
+                    return -1;
+            } else {
+                CUDA_OK(cudaMemcpyAsync(L.shift + row, raw_of(c, p.prefix + ".bias"), p.cout * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, s));
+            }
+            row += p.cout;
+        }
+    }
+    for (int l = 0; l < 5; ++l)
+        CUDA_OK(cudaMemcpyAsync(c->scales_dev + l, raw_of(c, kHead + "scales." + std::to_string(l) + ".scale"),
+                                sizeof(float), cudaMemcpyDeviceToDevice, s));
+    c->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+namespace {
+struct Builder {
+    dafne_ctx* c;
+    uint8_t* base;  // nullptr = dry run (size query)
+    Arena arena;
+    int64_t launches = 0;
+    double flops = 0;
+    bool failed = false;
+
+    Act new_act(int N, int H, int W, int C) {
+        Act a;
+        a.N = N;
+        a.H = H;
+        a.W = W;
+        a.C = C;
+        a.bytes = static_cast<size_t>(N) * H * W * C * sizeof(__half);
+        a.off = arena.alloc(a.bytes);
+        a.p = base ? reinterpret_cast<__half*>(base + a.off) : nullptr;
+        return a;
+    }
+    void free_act(Act& a) {
+        if (a.bytes) arena.release(a.off, a.bytes);
+        a.bytes = 0;
+    }
+    template <typename T>
+    T* persistent(size_t bytes) {
+        size_t off = arena.alloc(bytes);
+        return base ? reinterpret_cast<T*>(base + off) : nullptr;
+    }
+    const ConvLayer& layer(const std::string& prefix) { return c->convs[c->conv_index.at(prefix)]; }
+
+    // out = epilogue(conv(in)); allocates the fp16 output unless out_f32 is given
+    Act conv(const ConvLayer& L, const Act& in, bool relu, const Act* residual = nullptr, int res_shift = 0,
+             float* gn_sums = nullptr, float* out_f32 = nullptr, int out_ld = 0) {
+        ConvDesc d;
+        d.in = in.p;
+        d.N = in.N;
+        d.Hin = in.H;
+        d.Win = in.W;
+        d.Cin = L.Cin;
+        d.w = L.w;
+        d.Cout = L.Cout;
+        d.ksize = L.k;
+        d.stride = L.stride;
+        conv_out_dims(d);
+        Act out;
+        if (out_f32) {
+            out.N = in.N;
+            out.H = d.Hout;
+            out.W = d.Wout;
+            out.C = L.Cout;
+        } else {
+            out = new_act(in.N, d.Hout, d.Wout, L.Cout);
+        }
+        d.out = out.p;
+        d.out_f32 = out_f32;
+        d.out_ld = out_ld;
+        d.scale = L.scale;
+        d.shift = L.shift;
+        d.relu = relu ? 1 : 0;
+        if (residual) {
+            d.residual = residual->p;
+            d.res_H = residual->H;
+            d.res_W = residual->W;
+            d.res_shift = res_shift;
+        }
+        d.gn_sums = gn_sums;
+        ++launches;
+        flops += 2.0 * in.N * d.Hout * d.Wout * (double)L.Cout * L.k * L.k * L.Cin;
+        if (base) {
+            if (in.C != L.Cin) {
+                set_error("plan: conv '%s' expects Cin=%d, got %d", L.parts[0].prefix.c_str(), L.Cin, in.C);
+                failed = true;
+                return out;
+            }
+            ConvPlan plan;
+            if (conv_plan_build(d, &plan, c->num_sms)) {
+                failed = true;
+                return out;
+            }
+            c->ops.push_back([plan](cudaStream_t s) { return conv_plan_launch(plan, s); });
+        }
+        return out;
+    }
+};
+}  // namespace
+
+int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, size_t* needed) {
+    if (N < 1 || H < 32 || W < 32 || H % 32 || W % 32) {
+        set_error("plan: need N >= 1 and H, W positive multiples of 32 (got N=%d H=%d W=%d)", N, H, W);
+        return -1;
+    }
+    if (base && !c->finalized) {
+        set_error("plan: call dafne_weights_finalize before dafne_bind_workspace");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(c->device));
+    Builder B;
+    B.c = c;
+    B.base = base;
+    if (base) c->ops.clear();
+    const dafne_model_spec& sp = c->spec;
+
+    // ---- persistent buffers
+    int lvH[5], lvW[5];
+    lvH[0] = H / 8;
+    lvW[0] = W / 8;
+    lvH[1] = H / 16;
+    lvW[1] = W / 16;
+    lvH[2] = H / 32;
+    lvW[2] = W / 32;
+    for (int l = 3; l < 5; ++l) {
+        lvH[l] = (lvH[l - 1] - 1) / 2 + 1;
+        lvW[l] = (lvW[l - 1] - 1) / 2 + 1;
+    }
+    int32_t* sizes_dev = B.persistent<int32_t>(static_cast<size_t>(N) * 4 * sizeof(int32_t));
+    const size_t sums_per = static_cast<size_t>(N) * 32 * 2 * sizeof(float);
+    const size_t sums_bytes = sums_per * 3 * 4 * 5;
+    float* sums_all = B.persistent<float>(sums_bytes);
+    HeadOut ho[5][3];
+    const int ld_logits = sp.num_classes <= 16 ? 16 : 32;
+    for (int l = 0; l < 5; ++l)
+        for (int k = 0; k < 3; ++k) {
+            ho[l][k].ld = k == 0 ? ld_logits : 16;
+            ho[l][k].H = lvH[l];
+            ho[l][k].W = lvW[l];
+            ho[l][k].p = B.persistent<float>(static_cast<size_t>(N) * lvH[l] * lvW[l] * ho[l][k].ld * sizeof(float));
+        }
+    int level_hw[10];
+    for (int l = 0; l < 5; ++l) {
+        level_hw[2 * l] = lvH[l];
+        level_hw[2 * l + 1] = lvW[l];
+    }
+    const size_t post_bytes = postprocess_scratch_bytes(N, 5, level_hw, sp.num_classes, sp.pre_nms_topk);
+    void* post_scratch = B.persistent<uint8_t>(post_bytes);
+    const size_t img_bytes = static_cast<size_t>(N) * 3 * H * W * sizeof(float);
+    void* images_dev = B.persistent<uint8_t>(img_bytes);
+    const int det_cap = 2048;
+    float* dets_dev = B.persistent<float>(static_cast<size_t>(N) * det_cap * DAFNE_DET_STRIDE * sizeof(float));
+    int32_t* counts_dev = B.persistent<int32_t>(static_cast<size_t>(N) * sizeof(int32_t));
+
+    // ---- stem
+    Act x0 = B.new_act(N, H, W, 4);
+    __half* x0p_saved = x0.p;
+    Act s1 = B.new_act(N, H / 2, W / 2, 64);
+    B.launches += 2;
+    B.flops += 2.0 * N * (H / 2) * (W / 2) * 64.0 * 49 * 3;
+    if (base) {
+        // op 0 (preprocess) is issued by ctx_forward because it takes the per-call image pointer
+        __half* x0p = x0.p;
+        __half* s1p = s1.p;
+        const float* sw = c->stem_w;
+        const float* ssc = c->stem_scale;
+        const float* ssh = c->stem_shift;
+        c->ops.push_back([=](cudaStream_t s) { return launch_stem(x0p, N, H, W, sw, ssc, ssh, s1p, s); });
+    }
+    Act x = B.new_act(N, H / 4, W / 4, 64);
+    B.launches += 1;
+    if (base) {
+        __half* s1p = s1.p;
+        __half* xp = x.p;
+        c->ops.push_back([=](cudaStream_t s) { return launch_maxpool3x3s2(s1p, N, H / 2, W / 2, 64, xp, s); });
+    }
+    // x0 is needed until the stem ran; releasing at plan time is safe because ops execute in plan order
+    B.free_act(x0);
+    B.free_act(s1);
+
+    // ---- bottlenecks
+    const int* nb = stage_blocks(sp.resnet_depth);
+    Act feats[3];
+    for (int s = 2; s <= 5; ++s) {
+        for (int b = 0; b < nb[s - 2]; ++b) {
+            const std::string pre = kBU + "res" + std::to_string(s) + "." + std::to_string(b);
+            Act sc = x;
+            bool own_sc = false;
+            if (b == 0) {
+                sc = B.conv(B.layer(pre + ".shortcut"), x, false);
+                own_sc = true;
+            }
+            Act a = B.conv(B.layer(pre + ".conv1"), x, true);
+            Act m = B.conv(B.layer(pre + ".conv2"), a, true);
+            B.free_act(a);
+            Act o = B.conv(B.layer(pre + ".conv3"), m, true, &sc, 0);
+            B.free_act(m);
+            if (own_sc) B.free_act(sc);
+            B.free_act(x);  // block input (== sc for b > 0)
+            x = o;
+            if (B.failed) return -1;
+        }
+        if (s >= 3) {
+            feats[s - 3] = x;
+            // keep the stage output alive for the FPN lateral: hand the next stage a non-owning alias
+            if (s < 5) x.bytes = 0;
+        }
+    }
+    feats[2] = x;
+
+    // ---- FPN (top-down), P6, P7
+    Act prev, P[5];
+    for (int i = 2; i >= 0; --i) {
+        const std::string lat = "backbone.fpn_lateral" + std::to_string(3 + i);
+        const std::string outn = "backbone.fpn_output" + std::to_string(3 + i);
+        Act inner = (i == 2) ? B.conv(B.layer(lat), feats[i], false) : B.conv(B.layer(lat), feats[i], false, &prev, 1);
+        B.free_act(feats[i]);
+        if (i != 2) B.free_act(prev);
+        P[i] = B.conv(B.layer(outn), inner, false);
+        prev = inner;
+        if (B.failed) return -1;
+    }
+    B.free_act(prev);
+    P[3] = B.conv(B.layer("backbone.top_block.p6"), P[2], false);
+    Act p6r = B.new_act(P[3].N, P[3].H, P[3].W, 256);
+    B.launches += 1;
+    if (base) {
+        const __half* src = P[3].p;
+        __half* dst = p6r.p;
+        const size_t n8 = static_cast<size_t>(P[3].N) * P[3].H * P[3].W * 256 / 8;
+        c->ops.push_back([=](cudaStream_t s) { return launch_relu_copy(src, dst, n8, s); });
+    }
+    P[4] = B.conv(B.layer("backbone.top_block.p7"), p6r, false);
+    B.free_act(p6r);
+    if (B.failed) return -1;
+
+    // ---- head: three 4-conv GN towers + prediction convs per level (weights shared across levels)
+    for (int l = 0; l < 5; ++l) {
+        if (P[l].H != lvH[l] || P[l].W != lvW[l]) {
+            set_error("plan: level %d is %dx%d, expected %dx%d", l, P[l].H, P[l].W, lvH[l], lvW[l]);
+            return -1;
+        }
+        Act tower_out[3];
+        for (int t = 0; t < 3; ++t) {
+            // cls_tower(f), center_tower(f), corners_tower(center_tower(f))   (dafne.py:362-404)
+            Act cur = (t == 2) ? tower_out[1] : P[l];
+            bool own = false;
+            for (int i = 0; i < 4; ++i) {
+                const std::string tw = kHead + kTowers[t] + ".";
+                float* sums = sums_all ? sums_all + ((static_cast<size_t>(t) * 4 + i) * 5 + l) * (sums_per / sizeof(float))
+                                       : nullptr;
+                Act raw = B.conv(B.layer(tw + std::to_string(3 * i)), cur, false, nullptr, 0,
+                                 base ? sums : reinterpret_cast<float*>(1));
+                if (own) B.free_act(cur);
+                // GroupNorm + ReLU in place
+                B.launches += 1;
+                if (base) {
+                    __half* rp = raw.p;
+                    const int HW = raw.H * raw.W;
+                    const float* gamma = raw_of(c, tw + std::to_string(3 * i + 1) + ".weight");
+                    const float* beta = raw_of(c, tw + std::to_string(3 * i + 1) + ".bias");
+                    c->ops.push_back(
+                        [=](cudaStream_t s) { return launch_gn_relu(rp, rp, N, HW, 256, 32, sums, gamma, beta, 1e-5f, s); });
+                }
+                cur = raw;
+                own = true;
+                if (B.failed) return -1;
+            }
+            tower_out[t] = cur;
+        }
+        B.conv(B.layer(kHead + "cls_logits"), tower_out[0], false, nullptr, 0, nullptr,
+               base ? ho[l][0].p : reinterpret_cast<float*>(1), ho[l][0].ld);
+        B.conv(B.layer(kHead + "ctrness"), tower_out[2], false, nullptr, 0, nullptr,
+               base ? ho[l][1].p : reinterpret_cast<float*>(1), ho[l][1].ld);
+        B.conv(B.layer(kHead + "center_pred"), tower_out[1], false, nullptr, 0, nullptr,
+               base ? ho[l][2].p : reinterpret_cast<float*>(1), ho[l][2].ld);
+        for (int t = 0; t < 3; ++t) B.free_act(tower_out[t]);
+        B.free_act(P[l]);
+        if (B.failed) return -1;
+    }
+
+    if (needed) *needed = B.arena.peak;
+    if (!base) return 0;
+    if (B.arena.peak > bytes) {
+        set_error("bind_workspace: workspace of %zu bytes is too small, need %zu", bytes, B.arena.peak);
+        c->ops.clear();
+        return -1;
+    }
+    c->N = N;
+    c->H = H;
+    c->W = W;
+    c->ws = base;
+    c->ws_bytes = bytes;
+    c->launches_per_forward = B.launches;  // preprocess + stem + pool + convs + GN applies + relu copy
+    c->x0 = x0p_saved;
+    c->flops_per_forward = B.flops;
+    c->gn_sums_all = sums_all;
+    c->gn_sums_bytes = sums_bytes;
+    c->sizes_dev = sizes_dev;
+    c->images_dev = images_dev;
+    c->images_dev_bytes = img_bytes;
+    c->dets_dev = dets_dev;
+    c->counts_dev = counts_dev;
+    c->dets_capacity = det_cap;
+    c->post_scratch = post_scratch;
+    c->post_scratch_bytes = post_bytes;
+    for (int l = 0; l < 5; ++l)
+        for (int k = 0; k < 3; ++k) c->head_out[l][k] = ho[l][k];
+    return 0;
+}
+
+// Host int32 values reach the device as kernel arguments (copied at launch, no pinned staging, no host sync).
+struct IntChunk {
+    int32_t v[256];
+};
+__global__ void set_ints_kernel(IntChunk a, int32_t* dst, int n) {
+    const int i = threadIdx.x;
+    if (i < n) dst[i] = a.v[i];
+}
+
+static int upload_sizes(dafne_ctx* c, const int32_t* image_sizes, const int32_t* output_sizes, cudaStream_t s) {
+    for (int n0 = 0; n0 < c->N; n0 += 64) {
+        IntChunk ch;
+        const int cnt = c->N - n0 < 64 ? c->N - n0 : 64;
+        for (int j = 0; j < cnt; ++j) {
+            const int n = n0 + j;
+            const int h = image_sizes ? image_sizes[2 * n] : c->H, w = image_sizes ? image_sizes[2 * n + 1] : c->W;
+            if (h < 1 || w < 1 || h > c->H || w > c->W) {
+                set_error("image %d size %dx%d outside the bound %dx%d batch", n, h, w, c->H, c->W);
+                return -1;
+            }
+            ch.v[4 * j] = h;
+            ch.v[4 * j + 1] = w;
+            ch.v[4 * j + 2] = output_sizes ? output_sizes[2 * n] : h;
+            ch.v[4 * j + 3] = output_sizes ? output_sizes[2 * n + 1] : w;
+        }
+        set_ints_kernel<<<1, 256, 0, s>>>(ch, c->sizes_dev + 4 * n0, 4 * cnt);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("set_ints_kernel launch: %s", cudaGetErrorString(e));
+            return -1;
+        }
+        c->stat_launches += 1;
+    }
+    return 0;
+}
+
+int ctx_forward(dafne_ctx* c, const void* images, int dtype, const int32_t* image_sizes, cudaStream_t s) {
+    if (!c->ws || c->ops.empty()) {
+        set_error("dafne_forward_dense: no workspace bound");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(c->device));
+    if (upload_sizes(c, image_sizes, nullptr, s)) return -1;
+    CUDA_OK(cudaMemsetAsync(c->gn_sums_all, 0, c->gn_sums_bytes, s));
+    if (launch_preprocess(images, dtype, c->sizes_dev, c->N, c->H, c->W, c->spec.pixel_mean, c->spec.pixel_std,
+                          c->x0, s))
+        return -1;
+    for (auto& op : c->ops)
+        if (op(s)) return -1;
+    c->stat_launches += c->launches_per_forward;
+    c->stat_flops += c->flops_per_forward;
+    return 0;
+}
+
+void fill_post_spec(const dafne_ctx* c, PostParams* p) {
+    const dafne_model_spec& sp = c->spec;
+    p->L = sp.num_levels;
+    p->num_classes = sp.num_classes;
+    p->sort_corners = sp.sort_corners;
+    p->thresh_with_ctr = sp.thresh_with_ctr;
+    p->pre_nms_topk = sp.pre_nms_topk;
+    p->post_nms_topk = sp.post_nms_topk;
+    p->vehicle_merge = sp.vehicle_merge;
+    p->score_thresh = sp.score_thresh;
+    p->nms_thresh = sp.nms_thresh;
+    for (int l = 0; l < sp.num_levels; ++l) p->lv[l].stride = sp.fpn_strides[l];
+}
+
+int ctx_postprocess(dafne_ctx* c, const int32_t* image_sizes, const int32_t* output_sizes, int do_postprocess,
+                    float* dets, int32_t* counts, int capacity, cudaStream_t s) {
+    if (!c->ws) {
+        set_error("dafne_postprocess: no workspace bound");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(c->device));
+    if (upload_sizes(c, image_sizes, output_sizes, s)) return -1;
+    PostParams p;
+    memset(&p, 0, sizeof(p));
+    fill_post_spec(c, &p);
+    p.N = c->N;
+    for (int l = 0; l < 5; ++l) {
+        PostLevel& lv = p.lv[l];
+        lv.logits = c->head_out[l][0].p;
+        lv.ld_logits = c->head_out[l][0].ld;
+        lv.ctr = c->head_out[l][1].p;  // column 0 = ctrness logit
+        lv.ld_ctr = c->head_out[l][1].ld;
+        lv.reg = c->head_out[l][1].p + 1;  // columns 1..8 = corner deltas
+        lv.ld_reg = c->head_out[l][1].ld;
+        lv.center = c->head_out[l][2].p;
+        lv.ld_center = c->head_out[l][2].ld;
+        lv.H = c->head_out[l][0].H;
+        lv.W = c->head_out[l][0].W;
+    }
+    p.scales_dev = c->scales_dev;
+    p.do_postprocess = do_postprocess;
+    p.sizes_dev = c->sizes_dev;
+    p.dets = dets;
+    p.counts = counts;
+    p.capacity = capacity;
+    p.scratch = c->post_scratch;
+    p.scratch_bytes = c->post_scratch_bytes;
+    return launch_postprocess(p, s, &c->stat_launches);
+}
+
+}  // namespace dafne

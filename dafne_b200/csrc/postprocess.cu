@@ -1,0 +1,1079 @@
+// Rotated-box post-processing of DAFNe on device, with no host round trip:
+//   score = sqrt(sigmoid(cls) * sigmoid(ctr)), threshold, per-level top-k     dafne/modeling/dafne/dafne_outputs.py:792-858
+//   center-to-corner decode, polygon = location + reg * stride                 dafne/modeling/dafne/dafne.py:405-411, dafne_outputs.py:771-772,860-872
+//   canonical corner order                                                     dafne/utils/sort_corners.py:26-92
+//   class-aware polygon NMS (class offset trick, 5->4 merge, IoU > thr)        dafne/modeling/nms/nms.py:37-92 -> external poly_gpu_nms
+//   polygon IoU arithmetic (fp32 transliteration of the in-tree algorithm)     tools/prepare_dota/polyiou.cpp:8-133
+//   post-NMS top-k with ties kept                                              dafne/modeling/dafne/dafne_outputs.py:907-925
+//   rescale / clip / drop empty                                                detectron2 detector_postprocess, one_stage_detector.py:78-98
+//
+// This translation unit is compiled with -fmad=false -prec-div=true -prec-sqrt=true -ftz=false: every fp32 operation
+// is rounded once, in source order, exactly like the CPU oracle (oracle/polyiou_oracle.c, oracle/postprocess.py).
+// Sigmoid is evaluated in double and rounded once to float (the correctly rounded value; torch's float sigmoid is
+// within 1-2 ulp of it and differs between its own CPU and CUDA builds).
+//
+// Ordering contract (the reference leaves ties unspecified): candidates are ordered by descending score, ties by
+// ascending canonical index (level, location, class).
+#include "postprocess.cuh"
+
+#include <math.h>
+#include <stdio.h>
+
+#include "conv_tc.cuh"  // set_error
+
+namespace dafne {
+
+#define POST_CHECK_LAUNCH(name)                                         \
+    do {                                                                \
+        cudaError_t e__ = cudaGetLastError();                           \
+        if (e__ != cudaSuccess) {                                       \
+            set_error("%s launch: %s", name, cudaGetErrorString(e__)); \
+            return -1;                                                  \
+        }                                                               \
+    } while (0)
+
+constexpr int kMaxSorted = 16384;  // candidates per image the in-smem sort handles
+constexpr int kDet = 20;
+
+// ================================================================================================ polygon IoU (fp32)
+struct P2 {
+    float x, y;
+};
+// sig(d) = (d > eps) - (d < -eps) with the reference's DOUBLE eps = 1e-8 applied to a float: for a float d,
+// (double)d > 1e-8  <=>  d > EPS_BELOW where EPS_BELOW is the largest float <= 1e-8 (there is no float in between).
+__device__ __forceinline__ int sigf(float d) {
+    const float eps_below = 9.99999993922529029e-09f;  // == (float)1e-8, which rounds down
+    return (d > eps_below) - (d < -eps_below);
+}
+__device__ __forceinline__ bool same_pt(P2 a, P2 b) { return sigf(a.x - b.x) == 0 && sigf(a.y - b.y) == 0; }
+__device__ __forceinline__ float cross3(P2 o, P2 a, P2 b) {
+    return (a.x - o.x) * (b.y - o.y) - (b.x - o.x) * (a.y - o.y);
+}
+__device__ __forceinline__ float signed_area(P2* ps, int n) {
+    float acc = 0.f;
+    ps[n] = ps[0];
+    for (int i = 0; i < n; i++) acc += ps[i].x * ps[i + 1].y - ps[i].y * ps[i + 1].x;
+    return acc / 2.0f;
+}
+__device__ __forceinline__ int line_cross(P2 a, P2 b, P2 c, P2 d, P2* out) {
+    const float s1 = cross3(a, b, c);
+    const float s2 = cross3(a, b, d);
+    if (sigf(s1) == 0 && sigf(s2) == 0) return 2;
+    if (sigf(s2 - s1) == 0) return 0;
+    out->x = (c.x * s2 - d.x * s1) / (s2 - s1);
+    out->y = (c.y * s2 - d.y * s1) / (s2 - s1);
+    return 1;
+}
+__device__ __forceinline__ void clip_left(P2* p, int* n_io, P2 a, P2 b) {
+    P2 tmp[24];
+    int n = *n_io, m = 0;
+    p[n] = p[0];
+    for (int i = 0; i < n; i++) {
+        const int si = sigf(cross3(a, b, p[i]));
+        const int sj = sigf(cross3(a, b, p[i + 1]));
+        if (si > 0) tmp[m++] = p[i];
+        if (si != sj) {
+            tmp[m].x = 0.f;  // defined where the reference reads an unwritten slot (see oracle header)
+            tmp[m].y = 0.f;
+            line_cross(a, b, p[i], p[i + 1], &tmp[m]);
+            m++;
+        }
+    }
+    n = 0;
+    for (int i = 0; i < m; i++)
+        if (i == 0 || !same_pt(tmp[i], tmp[i - 1])) p[n++] = tmp[i];
+    while (n > 1 && same_pt(p[n - 1], p[0])) n--;
+    *n_io = n;
+}
+__device__ __forceinline__ float tri_overlap(P2 a, P2 b, P2 c, P2 d) {
+    P2 o;
+    o.x = 0.f;
+    o.y = 0.f;
+    const int s1 = sigf(cross3(o, a, b));
+    const int s2 = sigf(cross3(o, c, d));
+    if (s1 == 0 || s2 == 0) return 0.f;
+    if (s1 == -1) {
+        P2 t = a;
+        a = b;
+        b = t;
+    }
+    if (s2 == -1) {
+        P2 t = c;
+        c = d;
+        d = t;
+    }
+    P2 p[12];
+    int n = 3;
+    p[0] = o;
+    p[1] = a;
+    p[2] = b;
+    clip_left(p, &n, o, c);
+    clip_left(p, &n, c, d);
+    clip_left(p, &n, d, o);
+    float res = fabsf(signed_area(p, n));
+    if (s1 * s2 == -1) res = -res;
+    return res;
+}
+__device__ float iou_poly_f32(const float* pa, const float* qa) {
+    P2 p[6], q[6];
+    for (int i = 0; i < 4; i++) {
+        p[i].x = pa[2 * i];
+        p[i].y = pa[2 * i + 1];
+        q[i].x = qa[2 * i];
+        q[i].y = qa[2 * i + 1];
+    }
+    if (signed_area(p, 4) < 0.f) {
+        P2 t = p[0];
+        p[0] = p[3];
+        p[3] = t;
+        t = p[1];
+        p[1] = p[2];
+        p[2] = t;
+    }
+    if (signed_area(q, 4) < 0.f) {
+        P2 t = q[0];
+        q[0] = q[3];
+        q[3] = t;
+        t = q[1];
+        q[1] = q[2];
+        q[2] = t;
+    }
+    p[4] = p[0];
+    q[4] = q[0];
+    float inter = 0.f;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) inter += tri_overlap(p[i], p[i + 1], q[j], q[j + 1]);
+    const float a1 = fabsf(signed_area(p, 4));
+    const float a2 = fabsf(signed_area(q, 4));
+    const float uni = a1 + a2 - inter;
+    if (uni == 0.f) return (inter + 1.f) / (uni + 1.f);
+    return inter / uni;
+}
+
+__global__ void poly_iou_kernel(const float* __restrict__ p, const float* __restrict__ q, float* __restrict__ out,
+                                int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = iou_poly_f32(p + 8 * i, q + 8 * i);
+}
+int launch_poly_iou(const float* p, const float* q, float* iou, int n, cudaStream_t s) {
+    if (n <= 0) return 0;
+    poly_iou_kernel<<<(n + 63) / 64, 64, 0, s>>>(p, q, iou, n);
+    POST_CHECK_LAUNCH("poly_iou_kernel");
+    return 0;
+}
+
+// ================================================================================================ corner sort
+__device__ __forceinline__ float cross2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
+
+// sort_corners.py:26-92, one quadrilateral per thread. Pure permutation of the inputs, or zeros for degenerate rows.
+__device__ __forceinline__ void sort_quad(const float* in, float* out) {
+    float px[4], py[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        px[i] = in[2 * i];
+        py[i] = in[2 * i + 1];
+    }
+    int lm = 0;  // leftmost vertex, first minimum wins (:46)
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (px[i] < px[lm]) lm = i;
+    const float p1x = px[lm], p1y = py[lm];
+    float sx[3], sy[3];
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i != lm) {
+                sx[k] = px[i];
+                sy[k] = py[i];
+                ++k;
+            }
+    }
+    float p3x = 0.f, p3y = 0.f, ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;  // (a, b) = S_new
+    bool done = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int j = i == 0 ? 1 : 0;
+        const int k = i == 2 ? 1 : 2;
+        const float l = cross2(sx[i] - p1x, sy[i] - p1y, sx[j] - p1x, sy[j] - p1y);
+        const float r = cross2(sx[i] - p1x, sy[i] - p1y, sx[k] - p1x, sy[k] - p1y);
+        if (!done && (l * r) < 0.0f) {
+            p3x = sx[i];
+            p3y = sy[i];
+            ax = sx[j];
+            ay = sy[j];
+            bx = sx[k];
+            by = sy[k];
+            done = true;
+        }
+    }
+    float p2x, p2y, p4x, p4y;
+    const float c0 = cross2(p3x - p1x, p3y - p1y, ax - p1x, ay - p1y);
+    const float c1 = cross2(p3x - p1x, p3y - p1y, bx - p1x, by - p1y);
+    if (c0 > 0.0f || !(c1 > 0.0f)) {
+        p2x = ax;
+        p2y = ay;
+        p4x = bx;
+        p4y = by;
+    } else {
+        p2x = bx;
+        p2y = by;
+        p4x = ax;
+        p4y = ay;
+    }
+    out[0] = p1x;
+    out[1] = p1y;
+    out[2] = p2x;
+    out[3] = p2y;
+    out[4] = p3x;
+    out[5] = p3y;
+    out[6] = p4x;
+    out[7] = p4y;
+}
+
+__global__ void sort_quad_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float q[8], o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = in[8 * i + k];
+    sort_quad(q, o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[8 * i + k] = o[k];
+}
+int launch_sort_quadrilateral(const float* quads, float* out, int n, cudaStream_t s) {
+    if (n <= 0) return 0;
+    sort_quad_kernel<<<(n + 127) / 128, 128, 0, s>>>(quads, out, n);
+    POST_CHECK_LAUNCH("sort_quad_kernel");
+    return 0;
+}
+
+// ================================================================================================ scratch layout
+struct Layout {
+    int N, L, C, ldc;
+    int hw[5], cap[5];
+    size_t cand_off[5];  // offsets (in keys) of each level's candidate list inside one image's block
+    size_t cand_per_img;  // keys per image
+    int level_base[6];    // canonical index base of each level (sum of HW*C of the lower levels)
+    int max_sel, nblk;
+    // byte offsets of the per-image arrays, each [N][...]
+    size_t o_cand, o_cand_cnt, o_sel, o_sel_cnt, o_poly, o_nmsbox, o_score, o_ctr, o_cls, o_level, o_loc, o_hbox,
+        o_canon, o_mask, o_keep, o_nkeep, total;
+};
+
+static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
+
+static Layout make_layout(int N, int L, const int* level_hw, int C, int topk) {
+    Layout y;
+    y.N = N;
+    y.L = L;
+    y.C = C;
+    y.ldc = C <= 16 ? 16 : 32;
+    size_t keys = 0;
+    int sel = 0, base = 0;
+    for (int l = 0; l < L; ++l) {
+        y.hw[l] = level_hw[2 * l] * level_hw[2 * l + 1];
+        y.cap[l] = y.hw[l] * C;
+        y.cand_off[l] = keys;
+        keys += y.cap[l];
+        y.level_base[l] = base;
+        base += y.cap[l];
+        sel += y.cap[l] < topk ? y.cap[l] : topk;
+    }
+    y.level_base[L] = base;
+    y.cand_per_img = keys;
+    y.max_sel = sel < 1 ? 1 : sel;
+    y.nblk = (y.max_sel + 63) / 64;
+    size_t o = 0;
+    const size_t n = N, ms = y.max_sel;
+    y.o_cand = o;
+    o = a256(o + n * keys * 8);
+    y.o_cand_cnt = o;
+    o = a256(o + n * 8 * 4);
+    y.o_sel = o;
+    o = a256(o + n * ms * 8);
+    y.o_sel_cnt = o;
+    o = a256(o + n * 4);
+    y.o_poly = o;
+    o = a256(o + n * ms * 32);
+    y.o_nmsbox = o;
+    o = a256(o + n * ms * 32);
+    y.o_score = o;
+    o = a256(o + n * ms * 4);
+    y.o_ctr = o;
+    o = a256(o + n * ms * 4);
+    y.o_cls = o;
+    o = a256(o + n * ms * 4);
+    y.o_level = o;
+    o = a256(o + n * ms * 4);
+    y.o_loc = o;
+    o = a256(o + n * ms * 8);
+    y.o_hbox = o;
+    o = a256(o + n * ms * 16);
+    y.o_canon = o;
+    o = a256(o + n * ms * 4);
+    y.o_mask = o;
+    o = a256(o + n * ms * y.nblk * 8);
+    y.o_keep = o;
+    o = a256(o + n * ms * 4);
+    y.o_nkeep = o;
+    o = a256(o + n * 4);
+    y.total = o;
+    return y;
+}
+
+size_t postprocess_scratch_bytes(int N, int L, const int* level_hw, int num_classes, int pre_nms_topk) {
+    return make_layout(N, L, level_hw, num_classes, pre_nms_topk).total;
+}
+
+// ================================================================================================ K1: scores + candidates
+__device__ __forceinline__ float sigmoid_cr(float x) { return static_cast<float>(1.0 / (1.0 + exp(-static_cast<double>(x)))); }
+
+struct ScoreArgs {
+    const float* logits;
+    const float* ctr;
+    int ldc, ld_logits, ld_ctr, C, HW;
+    float thr;
+    int thresh_with_ctr;
+    unsigned long long* cand;  // [N][cand_per_img] + level offset
+    size_t cand_per_img;
+    int* cand_cnt;  // [N][8] + level
+};
+
+// one thread per (image, location, padded class); ldc in {16, 32} so a location never straddles a warp
+__global__ void score_candidates_kernel(ScoreArgs a, int N) {
+    const size_t total = static_cast<size_t>(N) * a.HW * a.ldc;
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    bool cand = false;
+    unsigned long long key = 0;
+    int n = 0;
+    if (i < total) {
+        const int c = i % a.ldc;
+        const size_t pix = i / a.ldc;  // n * HW + loc
+        n = pix / a.HW;
+        const int loc = pix % a.HW;
+        if (c < a.C) {
+            const float cls = sigmoid_cr(a.logits[pix * a.ld_logits + c]);
+            const float ctr = sigmoid_cr(a.ctr[pix * a.ld_ctr]);
+            float s;
+            if (a.thresh_with_ctr) {
+                s = sqrtf(cls * ctr);
+                cand = s > a.thr;
+            } else {
+                cand = cls > a.thr;
+                s = sqrtf(cls * ctr);
+            }
+            const unsigned idx = static_cast<unsigned>(loc) * a.C + c;
+            key = (static_cast<unsigned long long>(__float_as_uint(s)) << 32) | (0xFFFFFFFFu - idx);
+        }
+    }
+    // warp-aggregated append; a warp can straddle two images only at an image boundary, handle both
+    const int n_first = __shfl_sync(0xffffffffu, n, 0);
+    for (int pass = 0; pass < 2; ++pass) {
+        const int img = n_first + pass;
+        const unsigned m = __ballot_sync(0xffffffffu, cand && n == img);
+        if (m == 0) continue;
+        const int leader = __ffs(m) - 1;
+        int basepos = 0;
+        if (lane == leader) basepos = atomicAdd(a.cand_cnt + img * 8, __popc(m));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (cand && n == img) {
+            const int pos = basepos + __popc(m & ((1u << lane) - 1));
+            a.cand[static_cast<size_t>(img) * a.cand_per_img + pos] = key;
+        }
+    }
+}
+
+// ================================================================================================ K2: per-level top-k
+struct SelectArgs {
+    const unsigned long long* cand;  // image 0, level 0
+    size_t cand_per_img;
+    size_t cand_off[5];
+    const int* cand_cnt;  // [N][8]
+    int level_base[5];
+    int topk;
+    unsigned long long* sel;  // [N][max_sel]
+    int* sel_cnt;             // [N]
+    int max_sel;
+};
+
+// one CTA per (level, image): exact radix select of the topk largest 64-bit keys (all keys are distinct)
+__global__ void __launch_bounds__(1024) select_topk_kernel(SelectArgs a) {
+    const int l = blockIdx.x, n = blockIdx.y;
+    const int cnt = a.cand_cnt[n * 8 + l];
+    const unsigned long long* keys = a.cand + static_cast<size_t>(n) * a.cand_per_img + a.cand_off[l];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_k, s_base;
+    unsigned long long thr_key = 0;  // keep keys >= thr_key
+    if (cnt > a.topk) {
+        if (threadIdx.x == 0) {
+            s_prefix = 0;
+            s_k = a.topk;
+        }
+        for (int byte = 7; byte >= 0; --byte) {
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            const int shift = 8 * (byte + 1);
+            for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+                const unsigned long long k = keys[i];
+                const bool match = byte == 7 ? true : ((k >> shift) == prefix);
+                if (match) atomicAdd(&hist[(k >> (8 * byte)) & 0xFF], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int k = s_k;
+                int b = 255;
+                for (; b > 0; --b) {
+                    if (static_cast<int>(hist[b]) >= k) break;
+                    k -= hist[b];
+                }
+                s_k = k;
+                s_prefix = (prefix << 8) | static_cast<unsigned>(b);
+            }
+            __syncthreads();
+        }
+        thr_key = s_prefix;
+    }
+    const int take = cnt > a.topk ? a.topk : cnt;
+    if (threadIdx.x == 0) s_base = atomicAdd(a.sel_cnt + n, take);
+    __syncthreads();
+    // append (order inside the image list is irrelevant: the list is sorted next)
+    __shared__ int s_pos;
+    if (threadIdx.x == 0) s_pos = 0;
+    __syncthreads();
+    unsigned long long* dst = a.sel + static_cast<size_t>(n) * a.max_sel + s_base;
+    const unsigned lb = a.level_base[l];
+    for (int i0 = 0; i0 < cnt; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        unsigned long long k = 0;
+        bool ok = false;
+        if (i < cnt) {
+            k = keys[i];
+            ok = k >= thr_key;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const unsigned lane = threadIdx.x & 31;
+        int basepos = 0;
+        if (m != 0) {
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) basepos = atomicAdd(&s_pos, __popc(m));
+            basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        }
+        if (ok) {
+            const unsigned idx = 0xFFFFFFFFu - static_cast<unsigned>(k & 0xFFFFFFFFu);  // index inside the level
+            const unsigned canon = lb + idx;
+            dst[basepos + __popc(m & ((1u << lane) - 1))] = (k & 0xFFFFFFFF00000000ull) | (0xFFFFFFFFu - canon);
+        }
+    }
+}
+
+// ================================================================================================ K3: sort + decode
+struct DecodeArgs {
+    PostLevel lv[5];
+    int L, C;
+    int level_base[6];
+    const float* scales;
+    int sort_corners, vehicle_merge;
+    const unsigned long long* sel;
+    const int* sel_cnt;
+    int max_sel;
+    float *poly, *nmsbox, *score, *ctr, *loc, *hbox;
+    int *cls, *level;
+    unsigned* canon;
+};
+
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* s, int n_pow2) {
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = s[i], b = s[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) {
+                        s[i] = b;
+                        s[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// one CTA per image: sort the selected keys, decode every candidate, find min/max coordinate, build NMS boxes
+__global__ void __launch_bounds__(1024) sort_decode_kernel(DecodeArgs a) {
+    extern __shared__ unsigned long long s_keys[];
+    __shared__ float s_min[32], s_max[32];
+    const int n = blockIdx.x;
+    const int m = a.sel_cnt[n];
+    int np2 = 1;
+    while (np2 < m) np2 <<= 1;
+    const unsigned long long* src = a.sel + static_cast<size_t>(n) * a.max_sel;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = i < m ? src[i] : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(s_keys, np2);
+
+    const size_t rowbase = static_cast<size_t>(n) * a.max_sel;
+    float vmin = INFINITY, vmax = -INFINITY;
+    for (int r = threadIdx.x; r < m; r += blockDim.x) {
+        const unsigned long long key = s_keys[r];
+        const float score = __uint_as_float(static_cast<unsigned>(key >> 32));
+        const unsigned canon = 0xFFFFFFFFu - static_cast<unsigned>(key & 0xFFFFFFFFu);
+        int l = 0;
+        while (l + 1 < a.L && canon >= static_cast<unsigned>(a.level_base[l + 1])) ++l;
+        const unsigned idx = canon - a.level_base[l];
+        const int loc = idx / a.C, c = idx % a.C;
+        const PostLevel& lv = a.lv[l];
+        const size_t pix = static_cast<size_t>(n) * lv.H * lv.W + loc;
+        const int gx = loc % lv.W, gy = loc / lv.W;
+        const float fs = static_cast<float>(lv.stride);
+        const float lx = static_cast<float>(gx * lv.stride) + static_cast<float>(lv.stride / 2);
+        const float ly = static_cast<float>(gy * lv.stride) + static_cast<float>(lv.stride / 2);
+        float q[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float reg = lv.reg[pix * lv.ld_reg + k];
+            if (lv.center != nullptr) {
+                // reg_corners = (center.repeat(1,4,1,1) + delta) * scale_l      (dafne.py:405-411)
+                reg = (lv.center[pix * lv.ld_center + (k & 1)] + reg) * a.scales[l];
+            }
+            const float rc = reg * fs;       // dafne_outputs.py:771-772
+            q[k] = ((k & 1) ? ly : lx) + rc;  // dafne_outputs.py:860-872
+        }
+        if (a.sort_corners) {
+            sort_quad(q, o);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = q[k];
+        }
+        float xmin = o[0], xmax = o[0], ymin = o[1], ymax = o[1];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            xmin = fminf(xmin, o[2 * k]);
+            xmax = fmaxf(xmax, o[2 * k]);
+            ymin = fminf(ymin, o[2 * k + 1]);
+            ymax = fmaxf(ymax, o[2 * k + 1]);
+        }
+        vmin = fminf(vmin, fminf(xmin, ymin));
+        vmax = fmaxf(vmax, fmaxf(xmax, ymax));
+        float* pp = a.poly + (rowbase + r) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pp[k] = o[k];
+        float* hb = a.hbox + (rowbase + r) * 4;
+        hb[0] = xmin;
+        hb[1] = ymin;
+        hb[2] = xmax;
+        hb[3] = ymax;
+        a.score[rowbase + r] = score;
+        a.ctr[rowbase + r] = sigmoid_cr(lv.ctr[pix * lv.ld_ctr]);
+        a.cls[rowbase + r] = c;
+        a.level[rowbase + r] = l;
+        a.loc[(rowbase + r) * 2] = lx;
+        a.loc[(rowbase + r) * 2 + 1] = ly;
+        a.canon[rowbase + r] = canon;
+    }
+    // block-wide min / max of all coordinates (nms.py:74-75)
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_min[threadIdx.x >> 5] = vmin;
+        s_max[threadIdx.x >> 5] = vmax;
+    }
+    __syncthreads();
+    vmin = s_min[0];
+    vmax = s_max[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) {
+        vmin = fminf(vmin, s_min[w]);
+        vmax = fmaxf(vmax, s_max[w]);
+    }
+    const float span = vmax - vmin + 1.0f;  // max_coordinate - min_coordinate + 1   (nms.py:81)
+    for (int r = threadIdx.x; r < m; r += blockDim.x) {
+        int c = a.cls[rowbase + r];
+        if (a.vehicle_merge && c == 5) c = 4;  // nms.py:77-79
+        const float off = static_cast<float>(c) * span;
+        const float* pp = a.poly + (rowbase + r) * 8;
+        float* nb = a.nmsbox + (rowbase + r) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nb[k] = pp[k] + off;
+    }
+}
+
+// ================================================================================================ K4: NMS mask + sweep
+// grid (col block, row block, image), 64 threads: thread t owns row box rb*64+t and tests it against the 64 column
+// boxes staged in shared memory; only the upper triangle is evaluated. Faithful mode: every pair that the serial
+// sweep may consult is evaluated with the full polygon arithmetic -- no bounding-box or class pre-reject, because in
+// fp32 with class-shifted coordinates even disjoint boxes can produce IoU > thr.
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ boxes, const int* __restrict__ counts,
+                                                      int max_sel, int nblk, float thr,
+                                                      unsigned long long* __restrict__ mask) {
+    const int cb = blockIdx.x, rb = blockIdx.y, n = blockIdx.z;
+    if (cb < rb) return;
+    const int m = counts[n];
+    if (rb * 64 >= m || cb * 64 >= m) return;
+    __shared__ float s_box[64 * 8];
+    const float* b = boxes + static_cast<size_t>(n) * max_sel * 8;
+    const int ncol = min(64, m - cb * 64);
+    for (int i = threadIdx.x; i < ncol * 8; i += 64) s_box[i] = b[static_cast<size_t>(cb) * 64 * 8 + i];
+    __syncthreads();
+    const int row = rb * 64 + threadIdx.x;
+    if (row >= m) return;
+    float rbx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rbx[k] = b[static_cast<size_t>(row) * 8 + k];
+    unsigned long long bits = 0;
+    const int start = (cb == rb) ? threadIdx.x + 1 : 0;
+    for (int j = start; j < ncol; ++j)
+        if (iou_poly_f32(rbx, s_box + 8 * j) > thr) bits |= 1ull << j;
+    mask[(static_cast<size_t>(n) * max_sel + row) * nblk + cb] = bits;
+}
+
+// one CTA per image: resolve 64 rows at a time from the diagonal words, then OR the survivors' rows into `removed`
+__global__ void __launch_bounds__(256) nms_sweep_kernel(const unsigned long long* __restrict__ mask,
+                                                        const int* __restrict__ counts, int max_sel, int nblk,
+                                                        int* __restrict__ keep, int* __restrict__ nkeep) {
+    extern __shared__ unsigned long long s_removed[];  // nblk words
+    __shared__ unsigned long long s_diag[64];
+    __shared__ unsigned long long s_alive;
+    __shared__ int s_nk;
+    const int n = blockIdx.x;
+    const int m = counts[n];
+    const unsigned long long* mk = mask + static_cast<size_t>(n) * max_sel * nblk;
+    int* kp = keep + static_cast<size_t>(n) * max_sel;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) s_removed[i] = 0;
+    if (threadIdx.x == 0) s_nk = 0;
+    __syncthreads();
+    const int blocks = (m + 63) / 64;
+    for (int b = 0; b < blocks; ++b) {
+        const int rows = min(64, m - b * 64);
+        if (threadIdx.x < rows) s_diag[threadIdx.x] = mk[(static_cast<size_t>(b) * 64 + threadIdx.x) * nblk + b];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long rem = s_removed[b];
+            unsigned long long alive = 0;
+            int nk = s_nk;
+            for (int t = 0; t < rows; ++t) {
+                if (!((rem >> t) & 1ull)) {
+                    alive |= 1ull << t;
+                    kp[nk++] = b * 64 + t;
+                    rem |= s_diag[t];
+                }
+            }
+            s_nk = nk;
+            s_alive = alive;
+        }
+        __syncthreads();
+        const unsigned long long alive = s_alive;
+        for (int w = b + 1 + threadIdx.x; w < blocks; w += blockDim.x) {
+            unsigned long long acc = 0;
+            unsigned long long am = alive;
+            while (am) {
+                const int t = __ffsll(static_cast<long long>(am)) - 1;
+                am &= am - 1;
+                acc |= mk[(static_cast<size_t>(b) * 64 + t) * nblk + w];
+            }
+            s_removed[w] |= acc;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) nkeep[n] = s_nk;
+}
+
+// ================================================================================================ K5: top-k cut, rescale, clip, pack
+struct FinalArgs {
+    const float *poly, *score, *ctr, *loc, *hbox;
+    const int *cls, *level;
+    const unsigned* canon;
+    const int *keep, *nkeep;
+    int max_sel, post_topk, do_postprocess;
+    const int32_t* sizes;  // [N][4] h, w, out_h, out_w
+    float* dets;
+    int32_t* counts;
+    int capacity;
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
+    const int n = blockIdx.x;
+    const size_t rowbase = static_cast<size_t>(n) * a.max_sel;
+    const int* kp = a.keep + rowbase;
+    int nk = a.nkeep[n];
+    __shared__ int s_cut, s_out;
+    if (threadIdx.x == 0) {
+        int cut = nk;
+        if (a.post_topk > 0 && nk > a.post_topk) {
+            // kthvalue(scores, nk - topk + 1) = the topk-th largest; keep scores >= it (ties kept)  (dafne_outputs.py:916-923)
+            const float thr = a.score[rowbase + kp[a.post_topk - 1]];
+            cut = a.post_topk;
+            while (cut < nk && a.score[rowbase + kp[cut]] >= thr) ++cut;
+        }
+        s_cut = cut;
+        s_out = 0;
+    }
+    __syncthreads();
+    nk = s_cut;
+    const float ih = static_cast<float>(a.sizes[4 * n]), iw = static_cast<float>(a.sizes[4 * n + 1]);
+    const int oh_i = a.sizes[4 * n + 2], ow_i = a.sizes[4 * n + 3];
+    const float sx = static_cast<float>(static_cast<double>(ow_i) / static_cast<double>(iw));
+    const float sy = static_cast<float>(static_cast<double>(oh_i) / static_cast<double>(ih));
+    const float ow = static_cast<float>(ow_i), oh = static_cast<float>(oh_i);
+    float* out = a.dets + static_cast<size_t>(n) * a.capacity * kDet;
+    // order-preserving compaction, 256 rows per round
+    for (int r0 = 0; r0 < nk; r0 += blockDim.x) {
+        const int r = r0 + threadIdx.x;
+        bool ok = false;
+        float hb[4] = {0, 0, 0, 0};
+        int src = 0;
+        if (r < nk) {
+            src = kp[r];
+            const float* h = a.hbox + (rowbase + src) * 4;
+            hb[0] = h[0];
+            hb[1] = h[1];
+            hb[2] = h[2];
+            hb[3] = h[3];
+            ok = true;
+            if (a.do_postprocess) {
+                // Boxes.scale, Boxes.clip(output size), Boxes.nonempty()   (detectron2 detector_postprocess)
+                hb[0] = fminf(fmaxf(hb[0] * sx, 0.f), ow);
+                hb[2] = fminf(fmaxf(hb[2] * sx, 0.f), ow);
+                hb[1] = fminf(fmaxf(hb[1] * sy, 0.f), oh);
+                hb[3] = fminf(fmaxf(hb[3] * sy, 0.f), oh);
+                ok = (hb[2] - hb[0]) > 0.f && (hb[3] - hb[1]) > 0.f;
+            }
+        }
+        // block-wide exclusive scan of ok
+        __shared__ int s_warp[8];
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) s_warp[w] = __popc(m);
+        __syncthreads();
+        int before = s_out;
+        for (unsigned i = 0; i < w; ++i) before += s_warp[i];
+        const int pos = before + __popc(m & ((1u << lane) - 1));
+        if (ok && pos < a.capacity) {
+            float* d = out + static_cast<size_t>(pos) * kDet;
+            const float* pp = a.poly + (rowbase + src) * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float v = pp[k];
+                if (a.do_postprocess) v = v * ((k & 1) ? sy : sx);  // one_stage_detector.py:92-93
+                d[k] = v;
+            }
+            d[8] = hb[0];
+            d[9] = hb[1];
+            d[10] = hb[2];
+            d[11] = hb[3];
+            d[12] = a.score[rowbase + src];
+            d[13] = a.ctr[rowbase + src];
+            d[14] = static_cast<float>(a.cls[rowbase + src]);
+            d[15] = static_cast<float>(a.level[rowbase + src]);
+            float lx = a.loc[(rowbase + src) * 2], ly = a.loc[(rowbase + src) * 2 + 1];
+            if (a.do_postprocess) {
+                lx = lx * sx;  // one_stage_detector.py:94-95
+                ly = ly * sy;
+            }
+            d[16] = lx;
+            d[17] = ly;
+            d[18] = __uint_as_float(a.canon[rowbase + src]);  // raw bits of the canonical index
+            d[19] = 0.f;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int i = 0; i < 8; ++i) tot += s_warp[i];
+            s_out += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.counts[n] = s_out;
+}
+
+// ================================================================================================ host orchestration
+static int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, int nblk, float thr,
+                   unsigned long long* mask, int* keep, int* nkeep, cudaStream_t s, int64_t* launches) {
+    dim3 grid(nblk, nblk, N);
+    nms_mask_kernel<<<grid, 64, 0, s>>>(nmsbox, counts, max_sel, nblk, thr, mask);
+    POST_CHECK_LAUNCH("nms_mask_kernel");
+    nms_sweep_kernel<<<N, 256, nblk * sizeof(unsigned long long), s>>>(mask, counts, max_sel, nblk, keep, nkeep);
+    POST_CHECK_LAUNCH("nms_sweep_kernel");
+    if (launches) *launches += 2;
+    return 0;
+}
+
+int launch_postprocess(const PostParams& p, cudaStream_t s, int64_t* launches) {
+    int level_hw[10];
+    for (int l = 0; l < p.L; ++l) {
+        level_hw[2 * l] = p.lv[l].H;
+        level_hw[2 * l + 1] = p.lv[l].W;
+    }
+    const Layout y = make_layout(p.N, p.L, level_hw, p.num_classes, p.pre_nms_topk);
+    if (y.total > p.scratch_bytes) {
+        set_error("postprocess: scratch of %zu bytes is too small, need %zu", p.scratch_bytes, y.total);
+        return -1;
+    }
+    if (y.max_sel > kMaxSorted) {
+        set_error("postprocess: %d candidates per image exceed the supported %d", y.max_sel, kMaxSorted);
+        return -1;
+    }
+    uint8_t* base = static_cast<uint8_t*>(p.scratch);
+    auto* cand = reinterpret_cast<unsigned long long*>(base + y.o_cand);
+    int* cand_cnt = reinterpret_cast<int*>(base + y.o_cand_cnt);
+    auto* sel = reinterpret_cast<unsigned long long*>(base + y.o_sel);
+    int* sel_cnt = reinterpret_cast<int*>(base + y.o_sel_cnt);
+    // cand_cnt and sel_cnt are adjacent enough to clear separately
+    cudaError_t e = cudaMemsetAsync(cand_cnt, 0, static_cast<size_t>(p.N) * 8 * 4, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sel_cnt, 0, static_cast<size_t>(p.N) * 4, s);
+    if (e != cudaSuccess) {
+        set_error("postprocess memset: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    for (int l = 0; l < p.L; ++l) {
+        if (p.lv[l].ld_logits < p.num_classes) {
+            set_error("postprocess: level %d logits pitch %d < num_classes %d", l, p.lv[l].ld_logits, p.num_classes);
+            return -1;
+        }
+        ScoreArgs a;
+        a.logits = p.lv[l].logits;
+        a.ctr = p.lv[l].ctr;
+        a.ldc = y.ldc;
+        a.ld_logits = p.lv[l].ld_logits;
+        a.ld_ctr = p.lv[l].ld_ctr;
+        a.C = p.num_classes;
+        a.HW = y.hw[l];
+        a.thr = p.score_thresh;
+        a.thresh_with_ctr = p.thresh_with_ctr;
+        a.cand = cand + y.cand_off[l];
+        a.cand_per_img = y.cand_per_img;
+        a.cand_cnt = cand_cnt + l;
+        const size_t total = static_cast<size_t>(p.N) * y.hw[l] * y.ldc;
+        if (total == 0) continue;
+        score_candidates_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(a, p.N);
+        POST_CHECK_LAUNCH("score_candidates_kernel");
+        if (launches) *launches += 1;
+    }
+    {
+        SelectArgs a;
+        a.cand = cand;
+        a.cand_per_img = y.cand_per_img;
+        for (int l = 0; l < 5; ++l) {
+            a.cand_off[l] = l < p.L ? y.cand_off[l] : 0;
+            a.level_base[l] = l < p.L ? y.level_base[l] : 0;
+        }
+        a.cand_cnt = cand_cnt;
+        a.topk = p.pre_nms_topk;
+        a.sel = sel;
+        a.sel_cnt = sel_cnt;
+        a.max_sel = y.max_sel;
+        select_topk_kernel<<<dim3(p.L, p.N), 1024, 0, s>>>(a);
+        POST_CHECK_LAUNCH("select_topk_kernel");
+        if (launches) *launches += 1;
+    }
+    float* poly = reinterpret_cast<float*>(base + y.o_poly);
+    float* nmsbox = reinterpret_cast<float*>(base + y.o_nmsbox);
+    float* score = reinterpret_cast<float*>(base + y.o_score);
+    float* ctr = reinterpret_cast<float*>(base + y.o_ctr);
+    int* cls = reinterpret_cast<int*>(base + y.o_cls);
+    int* level = reinterpret_cast<int*>(base + y.o_level);
+    float* loc = reinterpret_cast<float*>(base + y.o_loc);
+    float* hbox = reinterpret_cast<float*>(base + y.o_hbox);
+    unsigned* canon = reinterpret_cast<unsigned*>(base + y.o_canon);
+    auto* mask = reinterpret_cast<unsigned long long*>(base + y.o_mask);
+    int* keep = reinterpret_cast<int*>(base + y.o_keep);
+    int* nkeep = reinterpret_cast<int*>(base + y.o_nkeep);
+    {
+        DecodeArgs a;
+        for (int l = 0; l < 5; ++l) a.lv[l] = p.lv[l < p.L ? l : 0];
+        a.L = p.L;
+        a.C = p.num_classes;
+        for (int l = 0; l <= p.L; ++l) a.level_base[l] = y.level_base[l];
+        a.scales = p.scales_dev;
+        a.sort_corners = p.sort_corners;
+        a.vehicle_merge = p.vehicle_merge;
+        a.sel = sel;
+        a.sel_cnt = sel_cnt;
+        a.max_sel = y.max_sel;
+        a.poly = poly;
+        a.nmsbox = nmsbox;
+        a.score = score;
+        a.ctr = ctr;
+        a.loc = loc;
+        a.hbox = hbox;
+        a.cls = cls;
+        a.level = level;
+        a.canon = canon;
+        int np2 = 1;
+        while (np2 < y.max_sel) np2 <<= 1;
+        const size_t smem = static_cast<size_t>(np2) * 8;
+        static size_t configured = 0;
+        if (smem > configured) {
+            e = cudaFuncSetAttribute(sort_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem));
+            if (e != cudaSuccess) {
+                set_error("sort_decode_kernel smem attribute (%zu): %s", smem, cudaGetErrorString(e));
+                return -1;
+            }
+            configured = smem;
+        }
+        sort_decode_kernel<<<p.N, 1024, smem, s>>>(a);
+        POST_CHECK_LAUNCH("sort_decode_kernel");
+        if (launches) *launches += 1;
+    }
+    if (p.nms_thresh > 0.f) {
+        if (run_nms(nmsbox, sel_cnt, p.N, y.max_sel, y.nblk, p.nms_thresh, mask, keep, nkeep, s, launches)) return -1;
+    } else {
+        set_error("postprocess: nms_thresh <= 0 (NMS disabled) is not supported by the fused path");
+        return -1;
+    }
+    {
+        FinalArgs a;
+        a.poly = poly;
+        a.score = score;
+        a.ctr = ctr;
+        a.loc = loc;
+        a.hbox = hbox;
+        a.cls = cls;
+        a.level = level;
+        a.canon = canon;
+        a.keep = keep;
+        a.nkeep = nkeep;
+        a.max_sel = y.max_sel;
+        a.post_topk = p.post_nms_topk;
+        a.do_postprocess = p.do_postprocess;
+        a.sizes = p.sizes_dev;
+        a.dets = p.dets;
+        a.counts = p.counts;
+        a.capacity = p.capacity;
+        finalize_kernel<<<p.N, 256, 0, s>>>(a);
+        POST_CHECK_LAUNCH("finalize_kernel");
+        if (launches) *launches += 1;
+    }
+    return 0;
+}
+
+// ================================================================================================ stand-alone NMS hook
+// ml_nms semantics for one image given boxes / scores / classes in arbitrary order.
+__global__ void __launch_bounds__(1024) nms_prepare_kernel(const float* __restrict__ polys,
+                                                           const float* __restrict__ scores,
+                                                           const int* __restrict__ classes, int n, int vehicle_merge,
+                                                           float* __restrict__ nmsbox, int* __restrict__ order,
+                                                           int* __restrict__ count) {
+    extern __shared__ unsigned long long s_keys[];
+    __shared__ float s_min[32], s_max[32];
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x)
+        s_keys[i] = i < n ? ((static_cast<unsigned long long>(__float_as_uint(scores[i])) << 32) |
+                             (0xFFFFFFFFu - static_cast<unsigned>(i)))
+                          : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(s_keys, np2);
+    float vmin = INFINITY, vmax = -INFINITY;
+    for (int i = threadIdx.x; i < n * 8; i += blockDim.x) {
+        vmin = fminf(vmin, polys[i]);
+        vmax = fmaxf(vmax, polys[i]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_min[threadIdx.x >> 5] = vmin;
+        s_max[threadIdx.x >> 5] = vmax;
+    }
+    __syncthreads();
+    vmin = s_min[0];
+    vmax = s_max[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) {
+        vmin = fminf(vmin, s_min[w]);
+        vmax = fmaxf(vmax, s_max[w]);
+    }
+    const float span = vmax - vmin + 1.0f;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const int src = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(s_keys[r] & 0xFFFFFFFFu));
+        order[r] = src;
+        int c = classes ? classes[src] : 0;
+        if (vehicle_merge && c == 5) c = 4;
+        const float off = static_cast<float>(c) * span;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nmsbox[r * 8 + k] = polys[src * 8 + k] + off;
+    }
+    if (threadIdx.x == 0) *count = n;
+}
+
+__global__ void nms_gather_kernel(const int* __restrict__ order, const int* __restrict__ keep_pos,
+                                  const int* __restrict__ nkeep, int* __restrict__ keep_out,
+                                  int* __restrict__ nkeep_out) {
+    const int nk = *nkeep;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nk; i += gridDim.x * blockDim.x)
+        keep_out[i] = order[keep_pos[i]];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *nkeep_out = nk;
+}
+
+size_t poly_nms_scratch_bytes(int n) {
+    const size_t ms = n < 1 ? 1 : n, nblk = (ms + 63) / 64;
+    return a256(ms * 32) + a256(ms * 4) + a256(4) + a256(ms * nblk * 8) + a256(ms * 4) + a256(4);
+}
+
+int launch_poly_nms(const float* polys, const float* scores, const int32_t* classes, int n, float thresh,
+                    int vehicle_merge, int32_t* keep_out, int32_t* nkeep_out, void* scratch, size_t scratch_bytes,
+                    cudaStream_t s) {
+    if (n <= 0 || thresh <= 0.f) {
+        // nms.py:22-25,63-64: nothing to suppress -> the reference returns the input unchanged / an empty index list
+        cudaError_t e = cudaMemsetAsync(nkeep_out, 0, sizeof(int32_t), s);
+        if (e != cudaSuccess) {
+            set_error("poly_nms memset: %s", cudaGetErrorString(e));
+            return -1;
+        }
+        if (n > 0) {
+            set_error("poly_nms: nms_thresh <= 0 means 'no NMS' in the reference (ml_nms returns its input)");
+            return -1;
+        }
+        return 0;
+    }
+    if (n > kMaxSorted) {
+        set_error("poly_nms: n=%d exceeds the supported %d boxes per image", n, kMaxSorted);
+        return -1;
+    }
+    if (poly_nms_scratch_bytes(n) > scratch_bytes) {
+        set_error("poly_nms: scratch of %zu bytes is too small, need %zu", scratch_bytes, poly_nms_scratch_bytes(n));
+        return -1;
+    }
+    const size_t ms = n, nblk = (ms + 63) / 64;
+    uint8_t* b = static_cast<uint8_t*>(scratch);
+    float* nmsbox = reinterpret_cast<float*>(b);
+    b += a256(ms * 32);
+    int* order = reinterpret_cast<int*>(b);
+    b += a256(ms * 4);
+    int* count = reinterpret_cast<int*>(b);
+    b += a256(4);
+    auto* mask = reinterpret_cast<unsigned long long*>(b);
+    b += a256(ms * nblk * 8);
+    int* keep_pos = reinterpret_cast<int*>(b);
+    b += a256(ms * 4);
+    int* nk = reinterpret_cast<int*>(b);
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    const size_t smem = static_cast<size_t>(np2) * 8;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(nms_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem));
+        if (e != cudaSuccess) {
+            set_error("nms_prepare_kernel smem attribute: %s", cudaGetErrorString(e));
+            return -1;
+        }
+        configured = smem;
+    }
+    nms_prepare_kernel<<<1, 1024, smem, s>>>(polys, scores, classes, n, vehicle_merge, nmsbox, order, count);
+    POST_CHECK_LAUNCH("nms_prepare_kernel");
+    if (run_nms(nmsbox, count, 1, n, static_cast<int>(nblk), thresh, mask, keep_pos, nk, s, nullptr)) return -1;
+    nms_gather_kernel<<<8, 256, 0, s>>>(order, keep_pos, nk, keep_out, nkeep_out);
+    POST_CHECK_LAUNCH("nms_gather_kernel");
+    return 0;
+}
+
+}  // namespace dafne

@@ -1,0 +1,47 @@
+// Rotated-box post-processing on device (see postprocess.cu): score/threshold/top-k, decode, corner sort,
+// class-aware polygon NMS, post-NMS top-k, rescale/clip/filter. No host round trip anywhere.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace dafne {
+
+struct PostLevel {
+    const float* logits;  // [N, H*W, ld_logits], num_classes valid
+    int ld_logits;
+    const float* ctr;  // ctrness logit of (n, loc) at ctr[(n*HW + loc) * ld_ctr]
+    int ld_ctr;
+    const float* reg;  // 8 corner values of (n, loc) at reg[(n*HW + loc) * ld_reg + k]
+    int ld_reg;
+    const float* center;  // nullptr: `reg` already is corners_reg_pred. Else reg = (center[k%2] + reg[k]) * scale
+    int ld_center;
+    int H, W, stride;
+};
+
+struct PostParams {
+    int N, L, num_classes;
+    PostLevel lv[5];
+    const float* scales_dev;  // [L] Scale parameters (dafne.py:47-53,409-411) or nullptr (= 1, only with center == nullptr)
+    int sort_corners, thresh_with_ctr, pre_nms_topk, post_nms_topk, vehicle_merge, do_postprocess;
+    float score_thresh, nms_thresh;
+    const int32_t* sizes_dev;  // [N][4] = image h, w, output h, w
+    float* dets;               // [N][capacity][20]
+    int32_t* counts;           // [N]
+    int capacity;
+    void* scratch;
+    size_t scratch_bytes;
+};
+
+size_t postprocess_scratch_bytes(int N, int L, const int* level_hw, int num_classes, int pre_nms_topk);
+int launch_postprocess(const PostParams& p, cudaStream_t stream, int64_t* launches);
+
+int launch_sort_quadrilateral(const float* quads, float* out, int n, cudaStream_t stream);
+int launch_poly_iou(const float* p, const float* q, float* iou, int n, cudaStream_t stream);
+
+size_t poly_nms_scratch_bytes(int n);
+int launch_poly_nms(const float* polys, const float* scores, const int32_t* classes, int n, float thresh,
+                    int vehicle_merge, int32_t* keep, int32_t* nkeep, void* scratch, size_t scratch_bytes,
+                    cudaStream_t stream);
+
+}  // namespace dafne

@@ -1,0 +1,201 @@
+"""Host-side owner of one `dafne_ctx`: weights, workspace, and the calls into the C ABI.
+
+One engine per (process, GPU). torch is used for device memory and streams only; every arithmetic step of the hot
+path happens inside libdafne_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _capi
+from .spec import ModelSpec
+
+DET = _capi.DET_STRIDE
+
+
+def _i32_array(values: Sequence[int]):
+    arr = (C.c_int32 * len(values))(*[int(v) for v in values])
+    return arr
+
+
+class DafneEngine:
+    def __init__(self, spec: ModelSpec, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise _capi.DafneError("dafne_b200 needs a CUDA device: the CUDA kernels are the only execution path")
+        self.spec = spec
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.lib = _capi.lib()
+        handle = C.c_void_p()
+        cspec = spec.to_c()
+        _capi.check(self.lib.dafne_ctx_create(C.byref(cspec), self.device.index or 0, C.byref(handle)),
+                    "dafne_ctx_create")
+        self._ctx = handle
+        self._ws: Optional[torch.Tensor] = None
+        self._shape: Optional[Tuple[int, int, int]] = None
+        self._weights_ready = False
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self.lib.dafne_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------------------------------- weights
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        """Upload tensors by detectron2 name (reference layouts, fp32); extra keys are ignored with a record."""
+        from .weights import state_dict_shapes
+
+        shapes = state_dict_shapes(self.spec)
+        missing = [k for k in shapes if k not in state_dict]
+        if missing:
+            raise KeyError(f"state dict lacks {len(missing)} tensors, e.g. {missing[:3]}")
+        names, ptrs, shp, keep = [], [], [], []
+        with torch.cuda.device(self.device):
+            for k, shape in shapes.items():
+                t = state_dict[k]
+                if tuple(t.shape) != tuple(shape):
+                    raise ValueError(f"{k}: shape {tuple(t.shape)} != expected {tuple(shape)}")
+                t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+                keep.append(t)
+                names.append(k.encode())
+                ptrs.append(t.data_ptr())
+                s4 = list(shape) + [1] * (4 - len(shape))
+                shp.extend(s4)
+            n = len(names)
+            c_names = (C.c_char_p * n)(*names)
+            c_ptrs = (C.c_void_p * n)(*ptrs)
+            c_shp = (C.c_int64 * (4 * n))(*shp)
+            stream = _capi.stream_ptr()
+            _capi.check(self.lib.dafne_load_weights(self._ctx, n, c_names, c_ptrs, c_shp, stream), "dafne_load_weights")
+            _capi.check(self.lib.dafne_weights_finalize(self._ctx, stream), "dafne_weights_finalize")
+            torch.cuda.current_stream().synchronize()  # the staging tensors in `keep` may now be released
+        self._weights_ready = True
+
+    # ---------------------------------------------------------------------------------------- workspace
+    def bind(self, N: int, H: int, W: int) -> None:
+        if self._shape == (N, H, W):
+            return
+        if not self._weights_ready:
+            raise _capi.DafneError("load_state_dict() must be called before running the model")
+        need = C.c_size_t()
+        _capi.check(self.lib.dafne_workspace_bytes(self._ctx, N, H, W, C.byref(need)), "dafne_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need.value + 1024:
+            self._ws = None
+            self._ws = torch.empty(need.value + 1024, dtype=torch.uint8, device=self.device)
+        base = (self._ws.data_ptr() + 1023) // 1024 * 1024
+        _capi.check(self.lib.dafne_bind_workspace(self._ctx, N, H, W, base, need.value), "dafne_bind_workspace")
+        self._shape = (N, H, W)
+        self.workspace_bytes = need.value
+
+    # ---------------------------------------------------------------------------------------- hot path
+    def forward_dense(self, images: torch.Tensor, image_sizes: Sequence[Tuple[int, int]]) -> None:
+        N, _, H, W = images.shape
+        self.bind(N, H, W)
+        dtype = {torch.uint8: 0, torch.float32: 1}[images.dtype]
+        sizes = _i32_array([v for hw in image_sizes for v in hw])
+        _capi.check(self.lib.dafne_forward_dense(self._ctx, images.data_ptr(), dtype, sizes, _capi.stream_ptr()),
+                    "dafne_forward_dense")
+
+    def head_outputs(self, level: int) -> Dict[str, torch.Tensor]:
+        """Copies of the head outputs of the last forward_dense for one level, in the reference's NCHW form."""
+        N = self._shape[0]
+        out = {}
+        for which, (name, nvalid) in enumerate((("logits", self.spec.num_classes), ("ctr_delta", 9), ("center", 2))):
+            p, ld, h, w = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+            _capi.check(self.lib.dafne_head_output(self._ctx, level, which, C.byref(p), C.byref(ld), C.byref(h),
+                                                   C.byref(w)), "dafne_head_output")
+            n_el = N * h.value * w.value * ld.value
+            t = torch.as_tensor(_DeviceFloats(p.value, n_el), device=self.device)  # zero-copy view of the workspace
+            t = t.view(N, h.value, w.value, ld.value)[..., :nvalid].permute(0, 3, 1, 2).contiguous()
+            out[name] = t
+        return out
+
+    def postprocess(self, image_sizes, output_sizes=None, do_postprocess=True, capacity: Optional[int] = None):
+        N = self._shape[0]
+        cap = capacity or (self.spec.post_nms_topk + 64)
+        dets = torch.zeros(N, cap, DET, dtype=torch.float32, device=self.device)
+        counts = torch.zeros(N, dtype=torch.int32, device=self.device)
+        sizes = _i32_array([v for hw in image_sizes for v in hw])
+        osz = _i32_array([v for hw in (output_sizes or image_sizes) for v in hw])
+        _capi.check(self.lib.dafne_postprocess(self._ctx, sizes, osz, int(do_postprocess), dets.data_ptr(),
+                                               counts.data_ptr(), cap, _capi.stream_ptr()), "dafne_postprocess")
+        return dets, counts
+
+    def detect(self, images: torch.Tensor, image_sizes, output_sizes=None, do_postprocess=True,
+               capacity: Optional[int] = None):
+        """Device tensors in, device tensors out: dets [N, cap, 20] fp32, counts [N] int32. No host sync."""
+        self.forward_dense(images, image_sizes)
+        return self.postprocess(image_sizes, output_sizes, do_postprocess, capacity)
+
+    def detect_host(self, host_images: torch.Tensor, image_sizes, output_sizes=None, host_dets=None,
+                    host_counts=None, capacity: Optional[int] = None):
+        """The reference-facing call with HOST buffers (pinned for full bandwidth): H2D + detect + D2H + sync."""
+        N, _, H, W = host_images.shape
+        self.bind(N, H, W)
+        cap = min(capacity or (self.spec.post_nms_topk + 64), 2048)
+        if host_dets is None:
+            host_dets = torch.empty(N, cap, DET, dtype=torch.float32).pin_memory()
+        if host_counts is None:
+            host_counts = torch.empty(N, dtype=torch.int32).pin_memory()
+        dtype = {torch.uint8: 0, torch.float32: 1}[host_images.dtype]
+        sizes = _i32_array([v for hw in image_sizes for v in hw])
+        osz = _i32_array([v for hw in (output_sizes or image_sizes) for v in hw])
+        _capi.check(self.lib.dafne_detect_host(self._ctx, host_images.data_ptr(), dtype, sizes, osz,
+                                               host_dets.data_ptr(), host_counts.data_ptr(), cap,
+                                               _capi.stream_ptr()), "dafne_detect_host")
+        return host_dets, host_counts
+
+    def postprocess_external(self, logits: List[torch.Tensor], reg: List[torch.Tensor], ctr: List[torch.Tensor],
+                             image_sizes, output_sizes=None, do_postprocess=True, capacity: Optional[int] = None):
+        """Post-process head outputs given in the reference's own NCHW fp32 form (the bit-exact parity gate)."""
+        N = logits[0].shape[0]
+        level_hw = [v for t in logits for v in t.shape[2:]]
+        keep = []
+        lp, rp, cp = [], [], []
+        for lg, rg, ct in zip(logits, reg, ctr):
+            # NCHW -> NHWC views materialised: pure data movement, no arithmetic
+            a = lg.to(self.device, torch.float32).permute(0, 2, 3, 1).contiguous()
+            b = rg.to(self.device, torch.float32).permute(0, 2, 3, 1).contiguous()
+            c = ct.to(self.device, torch.float32).permute(0, 2, 3, 1).contiguous()
+            keep += [a, b, c]
+            lp.append(a.data_ptr())
+            rp.append(b.data_ptr())
+            cp.append(c.data_ptr())
+        hw = _i32_array(level_hw)
+        need = C.c_size_t()
+        _capi.check(self.lib.dafne_postprocess_scratch_bytes(self._ctx, N, hw, C.byref(need)), "scratch_bytes")
+        scratch = torch.empty(need.value + 1024, dtype=torch.uint8, device=self.device)
+        sbase = (scratch.data_ptr() + 1023) // 1024 * 1024
+        cap = capacity or (self.spec.post_nms_topk + 64)
+        dets = torch.zeros(N, cap, DET, dtype=torch.float32, device=self.device)
+        counts = torch.zeros(N, dtype=torch.int32, device=self.device)
+        sizes = _i32_array([v for s in image_sizes for v in s])
+        osz = _i32_array([v for s in (output_sizes or image_sizes) for v in s])
+        L = len(logits)
+        _capi.check(
+            self.lib.dafne_postprocess_external(
+                self._ctx, N, hw, (C.c_void_p * L)(*lp), (C.c_void_p * L)(*rp), (C.c_void_p * L)(*cp), sizes, osz,
+                int(do_postprocess), dets.data_ptr(), counts.data_ptr(), cap, sbase, need.value, _capi.stream_ptr()),
+            "dafne_postprocess_external")
+        torch.cuda.current_stream().synchronize()
+        return dets, counts
+
+    def stats(self, reset: bool = False) -> Tuple[int, float]:
+        launches, flops = C.c_int64(), C.c_double()
+        _capi.check(self.lib.dafne_stats(self._ctx, C.byref(launches), C.byref(flops), int(reset)), "dafne_stats")
+        return launches.value, flops.value
+
+
+class _DeviceFloats:
+    """`__cuda_array_interface__` holder: lets torch view caller-owned device memory without copying."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
