@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the DAFNe inference hot path on B200 (contract: see the task description / DESIGN.md section 6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload r50_b8|r101_b32|...]
+
+A "step" = one pass of the hot path (normalise -> ResNet+FPN -> head -> threshold/top-k/decode/rotated NMS) over one
+batch of synthetic 1024x1024x3 uint8 images. `value` = images/s with the inputs already resident in HBM; `e2e` = the
+same through the reference-facing C-ABI call `dafne_detect_host` with HOST buffers (H2D of the images and D2H of the
+detections inside the timed region). Under torchrun every rank runs its own shard of the batch (weak scaling) and a
+step ends with ONE all-gather of the fixed-shape detections.
+
+`--impl reference` times the reference's CPU implementation of the same path on the host cores. detectron2 / poly_nms
+cannot be installed here (no network), so that arm is the restated oracle (kind "port"): torch CPU fp32 ops +
+the C polygon NMS, all host threads, one image per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (config file, per-GPU batch, H, W, BASELINE.json config it restates)
+    "r50_b8": ("configs/dota10_r50_1024.yaml", 8, 1024, 1024, "configs[1]: ResNet-50 + FPN DAFNe, batch 8x1024x1024"),
+    "r101_b32": ("configs/dota10_r101_ms.yaml", 32, 1024, 1024, "configs[2]: ResNet-101 DAFNe dota-1.0_r101_ms, batch 32"),
+    "r101_b16": ("configs/dota10_r101_ms.yaml", 16, 1024, 1024, "configs[3]: ResNet-101 DAFNe, 16 images per GPU"),
+    "hrsc_r50_b8": ("configs/hrsc_r50_ms.yaml", 8, 1024, 1024, "configs[4] (single size): HRSC r50_ms, batch 8"),
+}
+GFLOP_PER_IMAGE = {"r50": 505.97, "r101": 661.13}  # BASELINE.md section 2 (C = 15, 1024^2)
+
+
+def load_spec(workload):
+    from dafne_b200.config import get_cfg
+    from dafne_b200.spec import ModelSpec
+
+    cfg_file, batch, H, W, what = WORKLOADS[workload]
+    cfg = get_cfg()
+    cfg.merge_from_file(os.path.join(ROOT, cfg_file))
+    return cfg, ModelSpec.from_cfg(cfg), batch, H, W, what
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get("bf16_tflops_sustained", 1383.4), p.get("hbm_gbs", 6555.5), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step(sd, spec, images_u8, num_threads):
+    """One image through the restated reference on the host cores (oracle = the checker, timed as the CPU baseline)."""
+    import torch
+
+    from oracle import model as omodel
+    from oracle import postprocess as opost
+
+    torch.set_num_threads(num_threads)
+    batch, sizes = omodel.preprocess(list(images_u8), spec.pixel_mean, spec.pixel_std)
+    out = omodel.forward_dense(sd, spec.resnet_depth, batch, "fp32")
+    res = opost.postprocess([t.numpy() for t in out["logits"]], [t.numpy() for t in out["reg"]],
+                            [t.numpy() for t in out["ctr"]], spec.fpn_strides, sizes, None,
+                            score_thresh=spec.score_thresh, pre_nms_topk=spec.pre_nms_topk,
+                            nms_thresh=spec.nms_thresh, post_nms_topk=spec.post_nms_topk,
+                            sort_corners=spec.sort_corners, thresh_with_ctr=spec.thresh_with_ctr,
+                            vehicle_merge=spec.vehicle_merge)
+    return sum(len(r["scores"]) for r in res)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+
+    from dafne_b200.weights import synthetic_state_dict
+
+    cfg, spec, batch, H, W, what = load_spec(args.workload)
+    cores = os.cpu_count() or 1
+    sd = synthetic_state_dict(spec, 0)
+    g = torch.Generator().manual_seed(1234)
+    imgs = torch.randint(0, 256, (1, 3, H, W), dtype=torch.uint8, generator=g)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(sd, spec, imgs, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(sd, spec, imgs, cores)
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "images_per_sec_1024x1024", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "what": what, "per_step": "1 image (bounded sample of the batch)"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} x 1 image 1024x1024, restated reference (torch CPU fp32 + C polygon NMS)"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from dafne_b200.engine import DET, DafneEngine
+    from dafne_b200.weights import synthetic_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg, spec, batch, H, W, what = load_spec(args.workload)
+    if args.batch:
+        batch = args.batch
+    eng = DafneEngine(spec, dev)
+    eng.load_state_dict(synthetic_state_dict(spec, 0))
+    sizes = [(H, W)] * batch
+    cap = spec.post_nms_topk + 24
+
+    # inputs: several distinct batches so the input stream (not only the ~GB of activations) exceeds the 126 MB L2
+    n_sets = max(2, (160 * 2**20) // (batch * 3 * H * W) + 1)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_sets = [torch.randint(0, 256, (batch, 3, H, W), dtype=torch.uint8, generator=g).pin_memory()
+                 for _ in range(n_sets)]
+    dev_sets = [h.to(dev) for h in host_sets]
+    host_dets = torch.empty(batch, cap, DET, dtype=torch.float32).pin_memory()
+    host_counts = torch.empty(batch, dtype=torch.int32).pin_memory()
+    gathered = gathered_counts = None
+    if world > 1:
+        gathered = torch.empty(world * batch, cap, DET, dtype=torch.float32, device=dev)
+        gathered_counts = torch.empty(world * batch, dtype=torch.int32, device=dev)
+
+    def step_device(i):
+        dets, counts = eng.detect(dev_sets[i % n_sets], sizes, None, True, cap)
+        if world > 1:  # the path's one exchange: fixed-shape detections of every rank
+            dist.all_gather_into_tensor(gathered, dets)
+            dist.all_gather_into_tensor(gathered_counts, counts)
+        return dets, counts
+
+    def step_host(i):
+        eng.detect_host(host_sets[i % n_sets], sizes, None, host_dets, host_counts, cap)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, host_dets.to(dev, non_blocking=True))
+            dist.all_gather_into_tensor(gathered_counts, host_counts.to(dev, non_blocking=True))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(max(args.warmup, 3)):
+        step_device(i)
+    barrier()
+    eng.stats(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_device, args.steps)
+    launches, flops = eng.stats(reset=True)
+    for i in range(2):
+        step_host(i)
+    ms_host = timed(step_host, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    dets, counts = step_device(0)
+    torch.cuda.synchronize()
+    det_counts = counts.cpu().tolist()
+
+    # per-launch timing of one forward (CUDA events on the launching stream) for the roofline of the dominant kernel
+    prof = eng.profile_forward(dev_sets[0], sizes)
+    dom = [o for o in prof if o["kind"] == 1 and o["block_n"] == 256 and o["ksize"] == 3 and o["cin"] == 256
+           and o["cout"] == 256 and o["stride"] == 1 and "tower" in o["name"]]
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    dom_ms = sum(o["ms"] for o in dom)
+    dom_fl = sum(o["flops"] for o in dom)
+    total_ms = sum(o["ms"] for o in prof)
+    conv_ms = sum(o["ms"] for o in prof if o["kind"] == 1)
+    conv_fl = sum(o["flops"] for o in prof if o["kind"] == 1)
+    achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+
+    line = None
+    if rank == 0:
+        images = world * batch * args.steps
+        value = images / (ms * 1e-3)
+        e2e = images / (ms_host * 1e-3)
+        depth_key = "r101" if spec.resnet_depth == 101 else "r50"
+        gflop_img = flops / (args.steps * batch) / 1e9 if flops else GFLOP_PER_IMAGE[depth_key]
+        line = {
+            "metric": "images_per_sec_1024x1024", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {
+                "workload": args.workload, "what": what, "per_gpu_batch": batch, "global_batch": world * batch,
+                "image": [3, H, W], "resnet_depth": spec.resnet_depth, "num_classes": spec.num_classes,
+                "weights": "seeded random init (dafne_b200.weights.synthetic_state_dict)",
+                "parallelism": f"batch-sharded x{world}, one all-gather of detections" if world > 1 else "single GPU",
+                "l2": f"{n_sets} distinct input batches ({n_sets * batch * 3 * H * W / 2**20:.0f} MiB) rotate; "
+                      f"activation workspace {eng.workspace_bytes / 2**20:.0f} MiB >> 126 MiB L2",
+                "detections_per_image": det_counts[:8],
+                "gflop_per_image": gflop_img,
+                "conv_roofline_frac_whole_step": value / world * gflop_img * 1e9 / (peak_tf * 1e12),
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": batch * 3 * H * W,
+                    "d2h_bytes_per_step": batch * cap * DET * 4 + batch * 4, "ms_per_step": ms_host / args.steps},
+            "gpu_launches": launches,
+            "roofline": {
+                "kernel": "conv_tc_kernel<256> (head tower 3x3 256->256 convs, all levels)", "bound": "tensor",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "peak_source": peak_src, "launches": len(dom), "ms_in_step": dom_ms,
+                "share_of_forward": dom_ms / total_ms if total_ms else None,
+                "all_convs": {"achieved": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0,
+                              "ms": conv_ms, "forward_ms_sum_of_launches": total_ms},
+            },
+        }
+        if args.profile_json:
+            with open(args.profile_json, "w") as f:
+                json.dump(prof, f, indent=1)
+    # CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sd = synthetic_state_dict(spec, 0)
+        n_img = args.cpu_images
+        t0 = time.perf_counter()
+        for k in range(n_img):
+            cpu_reference_step(sd, spec, host_sets[0][k:k + 1], cores)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n_img / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"{n_img} image(s) of the first batch, restated reference on the host "
+                                          f"(torch CPU fp32 + C polygon NMS), {dt:.1f} s"}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="r50_b8", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--cpu-images", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-json", default="")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -40,6 +40,16 @@ class ModelSpecC(C.Structure):
     ]
 
 
+class OpProfileC(C.Structure):
+    _fields_ = [
+        ("ms", C.c_float),
+        ("kind", C.c_int32), ("block_n", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
+        ("cin", C.c_int32), ("cout", C.c_int32), ("hout", C.c_int32), ("wout", C.c_int32),
+        ("flops", C.c_double), ("bytes", C.c_double),
+        ("name", C.c_char * 48),
+    ]
+
+
 def build_library(verbose: bool = False) -> str:
     """Compile the CUDA sources for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     res = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
@@ -75,6 +85,10 @@ _SIGNATURES = {
     "dafne_postprocess_scratch_bytes": (_i, [_vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]),
     "dafne_detect": (_i, [_vp, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _i, _vp]),
     "dafne_detect_host": (_i, [_vp, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _i, _vp]),
+    "dafne_debug_keep_activations": (_i, [_vp, _i]),
+    "dafne_debug_activation": (_i, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "dafne_set_profiling": (_i, [_vp, _i]),
+    "dafne_get_profile": (_i, [_vp, C.c_void_p, _i, C.POINTER(_i)]),
     "dafne_stats": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_double), _i]),
     "dafne_conv_nhwc": (
         _i,

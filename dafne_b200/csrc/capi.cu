@@ -241,6 +241,65 @@ int dafne_detect_host(dafne_ctx* ctx, const void* host_images, int dtype, const 
     return 0;
 }
 
+int dafne_debug_keep_activations(dafne_ctx* ctx, int keep) {
+    NEED_CTX(ctx, "dafne_debug_keep_activations");
+    ctx->keep_activations = keep != 0;
+    return 0;
+}
+int dafne_debug_activation(dafne_ctx* ctx, const char* name, const void** ptr, int* N, int* H, int* W, int* Cc) {
+    NEED_CTX(ctx, "dafne_debug_activation");
+    auto it = ctx->named.find(name ? name : "");
+    if (it == ctx->named.end()) {
+        set_error("dafne_debug_activation: no activation named '%s' (was keep_activations set before bind?)",
+                  name ? name : "(null)");
+        return -1;
+    }
+    if (ptr) *ptr = it->second.p;
+    if (N) *N = it->second.N;
+    if (H) *H = it->second.H;
+    if (W) *W = it->second.W;
+    if (Cc) *Cc = it->second.C;
+    return 0;
+}
+
+int dafne_set_profiling(dafne_ctx* ctx, int enable) {
+    NEED_CTX(ctx, "dafne_set_profiling");
+    ctx->profiling = enable != 0;
+    return 0;
+}
+int dafne_get_profile(dafne_ctx* ctx, dafne_op_profile* ops, int capacity, int* count) {
+    NEED_CTX(ctx, "dafne_get_profile");
+    const int n = static_cast<int>(ctx->op_info.size());
+    if (count) *count = n;
+    if (!ops) return 0;
+    if (ctx->prof_events.size() < static_cast<size_t>(n) + 1) {
+        set_error("dafne_get_profile: no profiled forward has run");
+        return -1;
+    }
+    for (int i = 0; i < n && i < capacity; ++i) {
+        const OpInfo& o = ctx->op_info[i];
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]);
+        if (e != cudaSuccess) {
+            set_error("dafne_get_profile: cudaEventElapsedTime: %s", cudaGetErrorString(e));
+            return -1;
+        }
+        ops[i].ms = ms;
+        ops[i].kind = o.kind;
+        ops[i].block_n = o.block_n;
+        ops[i].ksize = o.ksize;
+        ops[i].stride = o.stride;
+        ops[i].cin = o.Cin;
+        ops[i].cout = o.Cout;
+        ops[i].hout = o.Hout;
+        ops[i].wout = o.Wout;
+        ops[i].flops = o.flops;
+        ops[i].bytes = o.bytes;
+        memcpy(ops[i].name, o.name, sizeof(ops[i].name));
+    }
+    return 0;
+}
+
 int dafne_stats(dafne_ctx* ctx, int64_t* launches, double* flops, int reset) {
     NEED_CTX(ctx, "dafne_stats");
     if (launches) *launches = ctx->stat_launches;

@@ -28,7 +28,7 @@ __global__ void preprocess_kernel(const T* __restrict__ img, const int32_t* __re
         const int x = i % W;
         const int y = (i / W) % H;
         const int n = i / (static_cast<size_t>(W) * H);
-        const int h = sizes[2 * n], w = sizes[2 * n + 1];
+        const int h = sizes[4 * n], w = sizes[4 * n + 1];  // rows of [h, w, out_h, out_w]
         float v0 = 0.f, v1 = 0.f, v2 = 0.f;
         if (y < h && x < w) {
             const size_t plane = static_cast<size_t>(H) * W;

@@ -7,7 +7,7 @@
 namespace dafne {
 
 // NCHW uint8 / fp32 image batch -> (x - mean) / std, zero outside each image's (h, w), fp16 NHWC with 4 channels
-// (channel 3 = 0). sizes_dev: N x (h, w) int32 on the device.
+// (channel 3 = 0). sizes_dev: N rows of (h, w, out_h, out_w) int32 on the device.
 int launch_preprocess(const void* images, int dtype, const int32_t* sizes_dev, int N, int H, int W, const float* mean3,
                       const float* std3, __half* out_nhwc4, cudaStream_t s);
 

@@ -299,8 +299,28 @@ struct Builder {
         return a;
     }
     void free_act(Act& a) {
-        if (a.bytes) arena.release(a.off, a.bytes);
+        if (a.bytes && !c->keep_activations) arena.release(a.off, a.bytes);
         a.bytes = 0;
+    }
+    void info(const char* nm, int kind, double fl, double by, int bn = 0, int k = 0, int st = 0, int ci = 0,
+              int co = 0, int ho = 0, int wo = 0) {
+        if (!base) return;
+        OpInfo o;
+        snprintf(o.name, sizeof(o.name), "%s", nm);
+        o.kind = kind;
+        o.flops = fl;
+        o.bytes = by;
+        o.block_n = bn;
+        o.ksize = k;
+        o.stride = st;
+        o.Cin = ci;
+        o.Cout = co;
+        o.Hout = ho;
+        o.Wout = wo;
+        c->op_info.push_back(o);
+    }
+    void name(const std::string& n, const Act& a) {
+        if (base && c->keep_activations) c->named[n] = a;
     }
     template <typename T>
     T* persistent(size_t bytes) {
@@ -359,6 +379,13 @@ struct Builder {
                 return out;
             }
             c->ops.push_back([plan](cudaStream_t s) { return conv_plan_launch(plan, s); });
+            const double px_in = (double)in.N * in.H * in.W, px_out = (double)in.N * d.Hout * d.Wout;
+            const double by = px_in * L.Cin * 2 + (double)L.Cout * L.k * L.k * L.Cin * 2 +
+                              px_out * (out_f32 ? out_ld * 4.0 : L.Cout * 2.0) +
+                              (residual ? (double)residual->N * residual->H * residual->W * L.Cout * 2 : 0.0);
+            std::string nm = L.parts[0].prefix;
+            if (nm.size() > 40) nm = nm.substr(nm.size() - 40);
+            info(nm.c_str(), 1, plan.flops, by, plan.block_n, L.k, L.stride, L.Cin, L.Cout, d.Hout, d.Wout);
         }
         return out;
     }
@@ -378,7 +405,12 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     Builder B;
     B.c = c;
     B.base = base;
-    if (base) c->ops.clear();
+    if (base) {
+        c->ops.clear();
+        c->named.clear();
+        c->op_info.clear();
+        B.info("preprocess", 0, 0, (double)N * H * W * (3 + 8));
+    }
     const dafne_model_spec& sp = c->spec;
 
     // ---- persistent buffers
@@ -433,6 +465,7 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
         const float* ssc = c->stem_scale;
         const float* ssh = c->stem_shift;
         c->ops.push_back([=](cudaStream_t s) { return launch_stem(x0p, N, H, W, sw, ssc, ssh, s1p, s); });
+        B.info("stem", 0, 2.0 * N * (H / 2) * (W / 2) * 64.0 * 147, (double)N * H * W * 8 + (double)N * (H / 2) * (W / 2) * 128);
     }
     Act x = B.new_act(N, H / 4, W / 4, 64);
     B.launches += 1;
@@ -440,8 +473,11 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
         __half* s1p = s1.p;
         __half* xp = x.p;
         c->ops.push_back([=](cudaStream_t s) { return launch_maxpool3x3s2(s1p, N, H / 2, W / 2, 64, xp, s); });
+        B.info("maxpool", 0, 0, (double)N * (H / 2) * (W / 2) * 128 * 1.25);
     }
     // x0 is needed until the stem ran; releasing at plan time is safe because ops execute in plan order
+    B.name("stem", s1);
+    B.name("pool", x);
     B.free_act(x0);
     B.free_act(s1);
 
@@ -465,6 +501,7 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
             if (own_sc) B.free_act(sc);
             B.free_act(x);  // block input (== sc for b > 0)
             x = o;
+            B.name("res" + std::to_string(s) + "." + std::to_string(b), o);
             if (B.failed) return -1;
         }
         if (s >= 3) {
@@ -488,6 +525,7 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
         if (B.failed) return -1;
     }
     B.free_act(prev);
+    for (int i = 0; i < 3; ++i) B.name("p" + std::to_string(3 + i), P[i]);
     P[3] = B.conv(B.layer("backbone.top_block.p6"), P[2], false);
     Act p6r = B.new_act(P[3].N, P[3].H, P[3].W, 256);
     B.launches += 1;
@@ -496,9 +534,12 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
         __half* dst = p6r.p;
         const size_t n8 = static_cast<size_t>(P[3].N) * P[3].H * P[3].W * 256 / 8;
         c->ops.push_back([=](cudaStream_t s) { return launch_relu_copy(src, dst, n8, s); });
+        B.info("relu_p6", 0, 0, (double)n8 * 32);
     }
     P[4] = B.conv(B.layer("backbone.top_block.p7"), p6r, false);
     B.free_act(p6r);
+    B.name("p6", P[3]);
+    B.name("p7", P[4]);
     if (B.failed) return -1;
 
     // ---- head: three 4-conv GN towers + prediction convs per level (weights shared across levels)
@@ -528,12 +569,14 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
                     const float* beta = raw_of(c, tw + std::to_string(3 * i + 1) + ".bias");
                     c->ops.push_back(
                         [=](cudaStream_t s) { return launch_gn_relu(rp, rp, N, HW, 256, 32, sums, gamma, beta, 1e-5f, s); });
+                    B.info("gn_relu", 0, 0, (double)N * HW * 256 * 4);
                 }
                 cur = raw;
                 own = true;
                 if (B.failed) return -1;
             }
             tower_out[t] = cur;
+            B.name(std::string(kTowers[t]) + ".l" + std::to_string(l), cur);
         }
         B.conv(B.layer(kHead + "cls_logits"), tower_out[0], false, nullptr, 0, nullptr,
                base ? ho[l][0].p : reinterpret_cast<float*>(1), ho[l][0].ld);
@@ -620,11 +663,23 @@ int ctx_forward(dafne_ctx* c, const void* images, int dtype, const int32_t* imag
     CUDA_OK(cudaSetDevice(c->device));
     if (upload_sizes(c, image_sizes, nullptr, s)) return -1;
     CUDA_OK(cudaMemsetAsync(c->gn_sums_all, 0, c->gn_sums_bytes, s));
+    const bool prof = c->profiling;
+    if (prof) {
+        while (c->prof_events.size() < c->ops.size() + 2) {
+            cudaEvent_t e;
+            CUDA_OK(cudaEventCreate(&e));
+            c->prof_events.push_back(e);
+        }
+        CUDA_OK(cudaEventRecord(c->prof_events[0], s));
+    }
     if (launch_preprocess(images, dtype, c->sizes_dev, c->N, c->H, c->W, c->spec.pixel_mean, c->spec.pixel_std,
                           c->x0, s))
         return -1;
-    for (auto& op : c->ops)
-        if (op(s)) return -1;
+    if (prof) CUDA_OK(cudaEventRecord(c->prof_events[1], s));
+    for (size_t i = 0; i < c->ops.size(); ++i) {
+        if (c->ops[i](s)) return -1;
+        if (prof) CUDA_OK(cudaEventRecord(c->prof_events[i + 2], s));
+    }
     c->stat_launches += c->launches_per_forward;
     c->stat_flops += c->flops_per_forward;
     return 0;

@@ -49,6 +49,15 @@ struct Arena {
     void release(size_t off, size_t bytes);
 };
 
+// What one planned launch is, for per-op timing: kind 0 = elementwise/other, 1 = tcgen05 conv.
+struct OpInfo {
+    int kind = 0;
+    int block_n = 0, ksize = 0, stride = 0, Cin = 0, Cout = 0, Hout = 0, Wout = 0;
+    double flops = 0;
+    double bytes = 0;  // algorithmic HBM bytes (inputs + weights + outputs, each once)
+    char name[48] = {0};
+};
+
 struct HeadOut {
     float* p = nullptr;
     int ld = 16;
@@ -77,6 +86,9 @@ struct dafne_ctx {
     __half* x0 = nullptr;  // preprocess output (NHWC4 fp16)
     size_t ws_bytes = 0;
     std::vector<std::function<int(cudaStream_t)>> ops;
+    std::vector<dafne::OpInfo> op_info;  // parallel to ops (+ entry 0 = preprocess)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;  // ops.size() + 2
     int64_t launches_per_forward = 0;
     double flops_per_forward = 0;
     float* gn_sums_all = nullptr;
@@ -90,6 +102,9 @@ struct dafne_ctx {
     dafne::HeadOut head_out[DAFNE_MAX_LEVELS][3];
     void* post_scratch = nullptr;
     size_t post_scratch_bytes = 0;
+    // debugging / per-layer parity: keep every activation alive and addressable by name
+    bool keep_activations = false;
+    std::unordered_map<std::string, dafne::Act> named;
     // counters
     int64_t stat_launches = 0;
     double stat_flops = 0;

@@ -1,0 +1,79 @@
+"""Multi-GPU inference: images shard by batch across ranks (one process per GPU), no data-path collective during the
+forward or the NMS (every image is independent), then ONE all-gather of the fixed-shape detections.
+
+Replaces the reference's pickled `comm.gather(self._predictions, dst=0)` (dafne/evaluation/dafne_evaluator.py:61-64)
+and detectron2's InferenceSampler sharding (tools/plain_train_net.py:280-313).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> range:
+    """Contiguous shard of `n_items` for `rank` (detectron2 InferenceSampler semantics: ceil-sized leading shards)."""
+    per = (n_items + world - 1) // world
+    begin = min(rank * per, n_items)
+    return range(begin, min(begin + per, n_items))
+
+
+def gather_detections(dets: torch.Tensor, counts: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather [B_local, cap, 20] detections and [B_local] counts -> ([world*B_local, cap, 20], [world*B_local]),
+    rank-major. One collective per tensor, issued on the current stream (NCCL) right after the NMS kernel."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return dets, counts
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        out_d = torch.empty((world * dets.shape[0],) + tuple(dets.shape[1:]), dtype=dets.dtype, device=dets.device)
+        out_c = torch.empty(world * counts.shape[0], dtype=counts.dtype, device=counts.device)
+        dist.all_gather_into_tensor(out_d, dets.contiguous(), group=group)
+        dist.all_gather_into_tensor(out_c, counts.contiguous(), group=group)
+        return out_d, out_c
+    ld = [torch.empty_like(dets) for _ in range(world)]
+    lc = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(ld, dets.contiguous(), group=group)
+    dist.all_gather(lc, counts.contiguous(), group=group)
+    return torch.cat(ld, 0), torch.cat(lc, 0)
+
+
+def pad_shard(items: Sequence, per_rank: int, filler):
+    """Every rank must contribute the same shape: pad a short (last) shard with `filler` items."""
+    items = list(items)
+    return items + [filler] * (per_rank - len(items)), len(items)
+
+
+def detect_sharded(engine, images: torch.Tensor, image_sizes: Sequence[Tuple[int, int]], output_sizes=None,
+                   capacity=None, group=None):
+    """`images` is the GLOBAL batch (same on every rank, or only this rank's slice is ever touched); each rank runs its
+    contiguous shard and all ranks receive every image's detections. Returns (dets, counts) for the global batch."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = images.shape[0]
+    per = (n + world - 1) // world
+    r = shard_range(n, rank, world)
+    local = images[r.start:r.stop]
+    sizes = list(image_sizes[r.start:r.stop])
+    osz = list(output_sizes[r.start:r.stop]) if output_sizes is not None else None
+    if len(r) < per:  # pad the last shard with copies of a valid image; its rows are dropped after the gather
+        pad = per - len(r)
+        filler = images[:1] if len(r) == 0 else local[-1:]
+        local = torch.cat([local] + [filler] * pad, 0)
+        fs = image_sizes[0] if len(r) == 0 else sizes[-1]
+        sizes = sizes + [fs] * pad
+        if osz is not None:
+            osz = osz + [(output_sizes[0] if len(r) == 0 else osz[-1])] * pad
+    dets, counts = engine.detect(local.contiguous(), sizes, osz, True, capacity)
+    dets, counts = gather_detections(dets, counts, group)
+    return dets[:n] if world * per == n else _drop_padding(dets, counts, n, per, world)[0], \
+        counts[:n] if world * per == n else _drop_padding(dets, counts, n, per, world)[1]
+
+
+def _drop_padding(dets, counts, n, per, world):
+    keep = []
+    for rk in range(world):
+        r = shard_range(n, rk, world)
+        keep.extend(range(rk * per, rk * per + len(r)))
+    idx = torch.tensor(keep, device=dets.device, dtype=torch.long)
+    return dets[idx], counts[idx]

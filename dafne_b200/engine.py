@@ -118,6 +118,20 @@ class DafneEngine:
             out[name] = t
         return out
 
+    def keep_activations(self, keep: bool = True) -> None:
+        """Per-layer parity support: disable activation-memory reuse (call before the first forward)."""
+        _capi.check(self.lib.dafne_debug_keep_activations(self._ctx, int(keep)), "dafne_debug_keep_activations")
+        self._shape = None
+
+    def activation(self, name: str) -> torch.Tensor:
+        """NCHW float32 copy of a named intermediate of the last forward (needs keep_activations)."""
+        p, n, h, w, c = C.c_void_p(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _capi.check(self.lib.dafne_debug_activation(self._ctx, name.encode(), C.byref(p), C.byref(n), C.byref(h),
+                                                    C.byref(w), C.byref(c)), "dafne_debug_activation")
+        n_el = n.value * h.value * w.value * c.value
+        t = torch.as_tensor(_DeviceHalfs(p.value, n_el), device=self.device)
+        return t.view(n.value, h.value, w.value, c.value).permute(0, 3, 1, 2).float().contiguous()
+
     def postprocess(self, image_sizes, output_sizes=None, do_postprocess=True, capacity: Optional[int] = None):
         N = self._shape[0]
         cap = capacity or (self.spec.post_nms_topk + 64)
@@ -188,6 +202,25 @@ class DafneEngine:
         torch.cuda.current_stream().synchronize()
         return dets, counts
 
+    def profile_forward(self, images: torch.Tensor, image_sizes) -> List[dict]:
+        """One dense forward with a CUDA event after every launch; returns per-launch records (ms, flops, ...)."""
+        _capi.check(self.lib.dafne_set_profiling(self._ctx, 1), "dafne_set_profiling")
+        try:
+            self.forward_dense(images, image_sizes)
+            torch.cuda.current_stream().synchronize()
+        finally:
+            _capi.check(self.lib.dafne_set_profiling(self._ctx, 0), "dafne_set_profiling")
+        cnt = C.c_int()
+        _capi.check(self.lib.dafne_get_profile(self._ctx, None, 0, C.byref(cnt)), "dafne_get_profile")
+        arr = (_capi.OpProfileC * cnt.value)()
+        _capi.check(self.lib.dafne_get_profile(self._ctx, C.cast(arr, C.c_void_p), cnt.value, C.byref(cnt)),
+                    "dafne_get_profile")
+        return [
+            dict(name=o.name.decode(), ms=o.ms, kind=o.kind, block_n=o.block_n, ksize=o.ksize, stride=o.stride,
+                 cin=o.cin, cout=o.cout, hout=o.hout, wout=o.wout, flops=o.flops, bytes=o.bytes)
+            for o in arr
+        ]
+
     def stats(self, reset: bool = False) -> Tuple[int, float]:
         launches, flops = C.c_int64(), C.c_double()
         _capi.check(self.lib.dafne_stats(self._ctx, C.byref(launches), C.byref(flops), int(reset)), "dafne_stats")
@@ -199,3 +232,8 @@ class _DeviceFloats:
 
     def __init__(self, ptr: int, n: int):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class _DeviceHalfs:
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f2", "data": (ptr, False), "version": 2}

@@ -1,0 +1,344 @@
+"""The reference's Python surface for the inference path, backed by the sm_100a kernels.
+
+Mirrors (names, argument meaning, return types, error behaviour):
+  OneStageDetector(cfg).forward / .inference / ._postprocess      dafne/modeling/one_stage_detector.py:34-107
+  model.proposal_generator.dafne_outputs.select_over_all_levels     dafne/modeling/dafne/dafne_outputs.py:907-925 (used by TTA, tta.py:265-267)
+  ml_nms, batched_nms_poly                                          dafne/modeling/nms/nms.py:10-92
+  poly_gpu_nms(dets, thresh, device_id)                             external poly_nms module (nms.py:6,91)
+  sort_quadrilateral                                                dafne/utils/sort_corners.py:26-92
+  META_ARCH_REGISTRY / PROPOSAL_GENERATOR_REGISTRY / BACKBONE_REGISTRY + build_model(cfg)   detectron2 registries
+
+Everything numeric goes through libdafne_b200.so; torch is device memory, streams and the nn.Module shell that
+gives the model a detectron2-compatible state dict.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _capi
+from .engine import DET, DafneEngine
+from .spec import ModelSpec
+from .structures import Boxes, Instances
+from .weights import state_dict_shapes, synthetic_state_dict
+
+
+class Registry(dict):
+    def __init__(self, name: str):
+        super().__init__()
+        self._name = name
+
+    def register(self, obj=None):
+        def deco(o):
+            self[o.__name__] = o
+            return o
+
+        return deco if obj is None else deco(obj)
+
+    def get(self, name):  # type: ignore[override]
+        if name not in self:
+            raise KeyError(f"No object named '{name}' found in '{self._name}' registry!")
+        return self[name]
+
+
+META_ARCH_REGISTRY = Registry("META_ARCH")
+PROPOSAL_GENERATOR_REGISTRY = Registry("PROPOSAL_GENERATOR")
+BACKBONE_REGISTRY = Registry("BACKBONE")
+
+
+class _ParamTree(nn.Module):
+    """Nested module whose state-dict keys are exactly the dotted names given (e.g. backbone.bottom_up.res2.0...)."""
+
+    def add(self, dotted: str, tensor: torch.Tensor) -> None:
+        head, _, rest = dotted.partition(".")
+        if not rest:
+            self.register_buffer(head, tensor)
+            return
+        if head not in self._modules:
+            self.add_module(head, _ParamTree())
+        self._modules[head].add(rest, tensor)
+
+
+# ------------------------------------------------------------------------------------------------ functional ops
+def _scratch(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+
+
+def _aligned(t: torch.Tensor) -> int:
+    return (t.data_ptr() + 1023) // 1024 * 1024
+
+
+def sort_quadrilateral(bboxes: torch.Tensor) -> torch.Tensor:
+    """Canonical corner order of quadrilaterals [n, 8] (sort_corners.py:26-92) on the GPU."""
+    assert bboxes.dim() == 2
+    if bboxes.shape[0] == 0:
+        return bboxes
+    if not bboxes.is_cuda:
+        raise _capi.DafneError("sort_quadrilateral: CUDA tensor required (no CPU fallback in this package)")
+    x = bboxes.contiguous().float()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib().dafne_sort_quadrilateral(x.data_ptr(), out.data_ptr(), x.shape[0], _capi.stream_ptr()),
+                    "dafne_sort_quadrilateral")
+    return out
+
+
+def poly_iou(p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+    """Row-wise polygon IoU of quadrilaterals [n, 8] in the faithful fp32 arithmetic (polyiou.cpp:108-133)."""
+    p = p.contiguous().float()
+    q = q.contiguous().float()
+    out = torch.empty(p.shape[0], dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        _capi.check(_capi.lib().dafne_poly_iou(p.data_ptr(), q.data_ptr(), out.data_ptr(), p.shape[0],
+                                               _capi.stream_ptr()), "dafne_poly_iou")
+    return out
+
+
+def batched_nms_poly(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float,
+                     vehicle_merge: bool = True) -> torch.Tensor:
+    """Class-aware polygon NMS (nms.py:37-92): int64 indices of kept boxes, in decreasing score order."""
+    assert boxes.shape[-1] == 8
+    if boxes.numel() == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    if not boxes.is_cuda:
+        raise _capi.DafneError("batched_nms_poly: CUDA tensors required (no CPU fallback in this package)")
+    n = boxes.shape[0]
+    lib = _capi.lib()
+    b = boxes.contiguous().float()
+    s = scores.contiguous().float()
+    c = idxs.to(torch.int32).contiguous()
+    need = C.c_size_t()
+    _capi.check(lib.dafne_poly_nms_scratch_bytes(n, C.byref(need)), "dafne_poly_nms_scratch_bytes")
+    scratch = _scratch(need.value, boxes.device)
+    keep = torch.empty(n, dtype=torch.int32, device=boxes.device)
+    nkeep = torch.zeros(1, dtype=torch.int32, device=boxes.device)
+    with torch.cuda.device(boxes.device):
+        _capi.check(lib.dafne_poly_nms(b.data_ptr(), s.data_ptr(), c.data_ptr(), n, float(iou_threshold),
+                                       int(vehicle_merge), keep.data_ptr(), nkeep.data_ptr(), _aligned(scratch),
+                                       need.value, _capi.stream_ptr()), "dafne_poly_nms")
+    return keep[: int(nkeep.item())].to(torch.int64)
+
+
+def ml_nms(boxlist: Instances, nms_thresh: float, max_proposals: int = -1) -> Instances:
+    """nms.py:10-33."""
+    if nms_thresh <= 0:
+        return boxlist
+    if boxlist.scores.shape[0] == 0:
+        return boxlist
+    keep = batched_nms_poly(boxlist.pred_corners, boxlist.scores, boxlist.pred_classes, nms_thresh)
+    if max_proposals > 0:
+        keep = keep[:max_proposals]
+    return boxlist[keep]
+
+
+def poly_gpu_nms(dets: np.ndarray, thresh: float, device_id: int = 0) -> List[int]:
+    """Drop-in for the external `poly_nms.poly_gpu_nms` the reference calls at nms.py:91: host numpy [n, 9] in
+    (8 coordinates with class offsets already applied + score), list of kept indices out, descending score."""
+    dets = np.ascontiguousarray(dets, dtype=np.float32)
+    n = dets.shape[0]
+    if n == 0:
+        return []
+    keep = (C.c_int * n)()
+    num = C.c_int(0)
+    _capi.check(_capi.lib().dafne_poly_nms_host(keep, C.byref(num), dets.ctypes.data_as(C.POINTER(C.c_float)), n,
+                                                dets.shape[1], float(thresh), int(device_id)), "dafne_poly_nms_host")
+    return list(keep[: num.value])
+
+
+# ------------------------------------------------------------------------------------------------ module surface
+class DAFNeOutputs:
+    """The slice of dafne_outputs.DAFNeOutputs the inference callers touch."""
+
+    def __init__(self, spec: ModelSpec):
+        self.nms_thresh = spec.nms_thresh
+        self.post_nms_topk = spec.post_nms_topk
+        self.pre_nms_thresh = spec.score_thresh
+        self.pre_nms_topk = spec.pre_nms_topk
+
+    def select_over_all_levels(self, boxlists: List[Instances]) -> List[Instances]:
+        """dafne_outputs.py:907-925: polygon NMS per image, then keep the post_nms_topk best (ties kept)."""
+        results = []
+        for boxlist in boxlists:
+            result = ml_nms(boxlist, self.nms_thresh)
+            n = len(result)
+            if n > self.post_nms_topk > 0:
+                scores = result.scores
+                thr = scores[self.post_nms_topk - 1]  # rows are in descending score: the topk-th largest
+                result = result[torch.nonzero(scores >= thr).squeeze(1)]
+            results.append(result)
+        return results
+
+
+@PROPOSAL_GENERATOR_REGISTRY.register()
+class DAFNe:
+    def __init__(self, spec: ModelSpec):
+        self.in_features = ["p3", "p4", "p5", "p6", "p7"]
+        self.fpn_strides = list(spec.fpn_strides)
+        self.dafne_outputs = DAFNeOutputs(spec)
+
+
+@BACKBONE_REGISTRY.register()
+def build_dafne_resnet_fpn_backbone(cfg, input_shape=None):
+    """The backbone is part of the fused launch plan; this entry exists so the registry name in the configs resolves."""
+    return {"name": "resnet_fpn_p6p7", "depth": int(cfg.MODEL.RESNETS.DEPTH), "size_divisibility": 32}
+
+
+@META_ARCH_REGISTRY.register()
+class OneStageDetector(nn.Module):
+    """`OneStageDetector(cfg)(batched_inputs) -> [{"instances": Instances}]`, inference only.
+
+    batched_inputs: list of dicts with "image" (CHW uint8 or float tensor, the channel order MODEL.PIXEL_MEAN is
+    given in), and optionally "height" / "width" = the resolution the outputs are rescaled to.
+    """
+
+    def __init__(self, cfg, init: str = "synthetic", seed: int = 0):
+        super().__init__()
+        self.cfg = cfg
+        self.spec = ModelSpec.from_cfg(cfg)
+        self.size_divisibility = self.spec.size_divisibility
+        self.params = _ParamTree()
+        if init == "synthetic":
+            sd = synthetic_state_dict(self.spec, seed)
+        else:
+            sd = {k: torch.zeros(s) for k, s in state_dict_shapes(self.spec).items()}
+        for k, v in sd.items():
+            self.params.add(k, v)
+        self.register_buffer("pixel_mean", torch.tensor(self.spec.pixel_mean).view(-1, 1, 1), persistent=False)
+        self.register_buffer("pixel_std", torch.tensor(self.spec.pixel_std).view(-1, 1, 1), persistent=False)
+        self.proposal_generator = DAFNe(self.spec)
+        self.backbone = build_dafne_resnet_fpn_backbone(cfg)
+        self.top_module = None  # MODEL.TOP_MODULE.NAME == "" in every shipped config (defaults.py:34)
+        self._engine: Optional[DafneEngine] = None
+        self._weights_dirty = True
+        self.eval()
+
+    # -- state dict with detectron2 names -------------------------------------------------------------
+    def _mark_dirty(self):
+        self._weights_dirty = True
+
+    def state_dict(self, *args, **kwargs):  # type: ignore[override]
+        return self.params.state_dict(*args, **kwargs)
+
+    def load_state_dict(self, state_dict, strict: bool = True):  # type: ignore[override]
+        if "model" in state_dict and isinstance(state_dict["model"], dict):  # detectron2 checkpoint wrapper
+            state_dict = state_dict["model"]
+        state_dict = {k: torch.as_tensor(v) for k, v in state_dict.items()}
+        res = self.params.load_state_dict(state_dict, strict=strict)
+        self._weights_dirty = True
+        return res
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("dafne_b200 implements the inference path only (SURVEY.md section 8)")
+        return super().train(False)
+
+    @property
+    def device(self) -> torch.device:
+        return self.pixel_mean.device
+
+    def _get_engine(self) -> DafneEngine:
+        if not self.device.type == "cuda":
+            raise _capi.DafneError("OneStageDetector must live on a CUDA device: call model.to('cuda') first")
+        if self._engine is None or self._engine.device != self.device:
+            self._engine = DafneEngine(self.spec, self.device)
+            self._weights_dirty = True
+        if self._weights_dirty:
+            self._engine.load_state_dict(self.params.state_dict())
+            self._weights_dirty = False
+        return self._engine
+
+    # -- the reference's methods -----------------------------------------------------------------------
+    def preprocess_image(self, batched_inputs: Sequence[dict]):
+        """Batch the images (zero canvas, size divisibility 32); normalisation happens in the first kernel.
+        Returns (N x 3 x H x W tensor on the device, [(h, w)])."""
+        images = [x["image"] for x in batched_inputs]
+        sizes = [(int(im.shape[1]), int(im.shape[2])) for im in images]
+        d = self.size_divisibility
+        H = (max(s[0] for s in sizes) + d - 1) // d * d
+        W = (max(s[1] for s in sizes) + d - 1) // d * d
+        dtype = torch.uint8 if all(im.dtype == torch.uint8 for im in images) else torch.float32
+        batch = torch.zeros(len(images), 3, H, W, dtype=dtype, device=self.device)
+        for i, im in enumerate(images):
+            batch[i, :, : sizes[i][0], : sizes[i][1]] = im.to(device=self.device, dtype=dtype, non_blocking=True)
+        return batch, sizes
+
+    @torch.no_grad()
+    def forward(self, batched_inputs: Sequence[dict], do_postprocess: bool = True):
+        if self.training:
+            raise NotImplementedError("training is outside the hot-path scope")
+        eng = self._get_engine()
+        batch, sizes = self.preprocess_image(batched_inputs)
+        out_sizes = [
+            (int(inp.get("height", s[0])), int(inp.get("width", s[1]))) for inp, s in zip(batched_inputs, sizes)
+        ]
+        with torch.cuda.device(self.device):
+            dets, counts = eng.detect(batch, sizes, out_sizes, do_postprocess=do_postprocess)
+            counts_h = counts.cpu().tolist()  # the one host sync of the call: result sizes
+        cap = dets.shape[1]
+        results = []
+        for i, n in enumerate(counts_h):
+            if n > cap:
+                raise _capi.DafneError(f"{n} detections exceed the output capacity {cap} (score ties at the cut)")
+            d = dets[i, :n]
+            image_size = out_sizes[i] if do_postprocess else sizes[i]
+            inst = Instances(image_size)
+            inst.pred_boxes = Boxes(d[:, 8:12].clone())
+            inst.pred_corners = d[:, 0:8].clone()
+            inst.scores = d[:, 12].clone()
+            inst.centerness = d[:, 13].clone()
+            inst.pred_classes = d[:, 14].to(torch.int64)
+            inst.locations = d[:, 16:18].clone()
+            inst.fpn_levels = d[:, 15].to(torch.int64)
+            results.append({"instances": inst})
+        return results
+
+    def inference(self, batched_inputs, detected_instances=None, do_postprocess: bool = True):
+        assert not self.training
+        return self.forward(batched_inputs, do_postprocess)
+
+    @staticmethod
+    def _postprocess(processed_results, batched_inputs):
+        """Rescale corners / locations to the requested output size (one_stage_detector.py:78-98), for callers that
+        ran `forward(..., do_postprocess=False)` and rescale later (TTA)."""
+        for res, inp in zip(processed_results, batched_inputs):
+            key = "proposals" if "proposals" in res else "instances"
+            oh, ow = inp["height"], inp["width"]
+            ih, iw = inp["image"].shape[1:3]
+            sx, sy = ow / iw, oh / ih
+            r = res[key]
+            r.pred_corners[:, 0::2] *= sx
+            r.pred_corners[:, 1::2] *= sy
+            r.locations[:, 0] *= sx
+            r.locations[:, 1] *= sy
+        return processed_results
+
+
+def build_model(cfg) -> nn.Module:
+    """detectron2.modeling.build_model: look the meta-architecture up by name and move it to cfg.MODEL.DEVICE."""
+    model = META_ARCH_REGISTRY.get(cfg.MODEL.META_ARCHITECTURE)(cfg)
+    model.to(torch.device(cfg.MODEL.DEVICE))
+    return model
+
+
+class DefaultPredictor:
+    """detectron2.engine.DefaultPredictor for this model (call shape of tools/vis/feature_maps.py:171-194):
+    predictor(bgr_hwc_uint8) -> {"instances": Instances}. Resizing (ResizeShortestEdge) is not part of the hot path;
+    the image is used at its own resolution."""
+
+    def __init__(self, cfg, state_dict: Optional[Dict[str, torch.Tensor]] = None):
+        self.cfg = cfg
+        self.model = build_model(cfg)
+        if state_dict is not None:
+            self.model.load_state_dict(state_dict)
+        self.input_format = cfg.INPUT.FORMAT
+
+    def __call__(self, original_image: np.ndarray):
+        if self.input_format == "RGB":
+            original_image = original_image[:, :, ::-1]
+        h, w = original_image.shape[:2]
+        image = torch.as_tensor(np.ascontiguousarray(original_image.transpose(2, 0, 1)))
+        return self.model([{"image": image, "height": h, "width": w}])[0]

@@ -71,7 +71,10 @@ def state_dict_shapes(spec: ModelSpec) -> "OrderedDict[str, Tuple[int, ...]]":
 # Frozen constants of the synthetic recipe (calibrated once on 1024^2 uniform-noise images):
 # the class bias puts roughly 1 % of the (location, class) scores of a level above the 0.05 threshold.
 SYNTH_CLS_STD = 0.02
-SYNTH_CLS_BIAS = -4.6
+SYNTH_CLS_BIAS = -4.6  # reference default: -log((1 - 0.01) / 0.01) (dafne.py:283-285) -> no candidates at all
+# (depth, THRESH_WITH_CTR) -> class bias giving roughly 0.5-2 % of (location, class) scores above the threshold on
+# uniform-noise 1024^2 images (scripts/dev_calibrate.py, gpurun_out/calib.log of round 1).
+SYNTH_CLS_BIAS_TABLE = {(50, False): -4.25, (50, True): -6.5, (101, False): -4.4, (101, True): -6.75}
 SYNTH_BASE_QUAD = (-3.0, -1.0, 3.0, -1.0, 3.0, 1.0, -3.0, 1.0)  # stride units: 48x16 px at p3, 96x32 at p4, ...
 
 
@@ -109,7 +112,8 @@ def synthetic_state_dict(spec: ModelSpec, seed: int = 0, cls_bias: float | None 
             else:
                 sd[name] = kaiming(shape)
         elif name == HEAD + "cls_logits.bias":
-            sd[name] = torch.full(shape, SYNTH_CLS_BIAS if cls_bias is None else cls_bias)
+            auto = SYNTH_CLS_BIAS_TABLE[(spec.resnet_depth, bool(spec.thresh_with_ctr))]
+            sd[name] = torch.full(shape, auto if cls_bias is None else cls_bias)
         elif name == HEAD + "corners_pred.bias":
             sd[name] = torch.tensor(base_quad, dtype=torch.float32)
         elif any(f"{t}." in name for t in TOWERS) and name.endswith(".weight"):

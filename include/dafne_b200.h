@@ -119,6 +119,26 @@ int dafne_detect_host(dafne_ctx* ctx, const void* host_images, int dtype, const 
                       const int32_t* output_sizes, float* host_dets, int32_t* host_counts, int capacity,
                       void* stream);
 
+/* Per-layer parity support. keep != 0 (set BEFORE dafne_bind_workspace) disables activation-memory reuse so that
+ * every intermediate survives the forward; dafne_debug_activation then returns the NHWC fp16 tensor called `name`:
+ * "stem", "pool", "res2.0" ... "res5.2", "p3" ... "p7", "cls_tower.l0" ... "corners_tower.l4". */
+int dafne_debug_keep_activations(dafne_ctx* ctx, int keep);
+int dafne_debug_activation(dafne_ctx* ctx, const char* name, const void** dev_ptr, int* N, int* H, int* W, int* C);
+
+/* Per-launch timing of the dense forward with CUDA events on the launching stream (bench.py's roofline numbers).
+ * dafne_set_profiling(ctx, 1) makes every following dafne_forward_dense record an event after each launch;
+ * dafne_get_profile (after the stream has been synchronised) returns, for launch i < *count: its duration in ms,
+ * its algorithmic FLOPs (2*MACs) and HBM bytes, kind (0 = other, 1 = tcgen05 conv), the conv tile width block_n
+ * and a label. Arrays may be NULL to query *count. */
+typedef struct dafne_op_profile {
+    float ms;
+    int32_t kind, block_n, ksize, stride, cin, cout, hout, wout;
+    double flops, bytes;
+    char name[48];
+} dafne_op_profile;
+int dafne_set_profiling(dafne_ctx* ctx, int enable);
+int dafne_get_profile(dafne_ctx* ctx, dafne_op_profile* ops, int capacity, int* count);
+
 /* Counters for bench.py: kernels launched by this library since the last reset, and conv FLOPs (2*MACs). */
 int dafne_stats(dafne_ctx* ctx, int64_t* kernel_launches, double* conv_flops, int reset);
 

@@ -88,8 +88,11 @@ def forward_dense(sd: Dict[str, torch.Tensor], depth: int, batch: torch.Tensor, 
         torch.set_num_threads(num_threads)
     net = _Net(sd, mode)
     x = net.rnd(batch)
+    named = {}
     x = net.conv_bn(x, BU + "stem.conv1", 2, 3, relu=True)
+    named["stem"] = x
     x = F.max_pool2d(x, 3, 2, 1)
+    named["pool"] = x
     feats = {}
     for s, nblocks in zip(range(2, 6), STAGE_BLOCKS[depth]):
         for b in range(nblocks):
@@ -99,6 +102,7 @@ def forward_dense(sd: Dict[str, torch.Tensor], depth: int, batch: torch.Tensor, 
             y = net.conv_bn(x, pre + ".conv1", stride, relu=True)
             y = net.conv_bn(y, pre + ".conv2", 1, 1, relu=True)
             x = net.conv_bn(y, pre + ".conv3", relu=True, residual=sc)
+            named[f"res{s}.{b}"] = x
         feats[s] = x
     # FPN top-down (detectron2 FPN.forward): prev = lateral(c5); p5 = output(prev); then lateral + nearest 2x
     prev = net.conv_bias(feats[5], "backbone.fpn_lateral5")
@@ -110,6 +114,8 @@ def forward_dense(sd: Dict[str, torch.Tensor], depth: int, batch: torch.Tensor, 
     p6 = net.conv_bias(P[5], "backbone.top_block.p6", 2, 1)
     p7 = net.conv_bias(F.relu(p6), "backbone.top_block.p7", 2, 1)
     levels = [P[3], P[4], P[5], p6, p7]
+    for i, f in enumerate(levels):
+        named[f"p{3 + i}"] = f
 
     def tower(f, name):
         for i in range(4):
@@ -119,11 +125,12 @@ def forward_dense(sd: Dict[str, torch.Tensor], depth: int, batch: torch.Tensor, 
             f = net.rnd(f)
         return f
 
-    out = {"features": levels, "logits": [], "reg": [], "ctr": [], "center": []}
+    out = {"features": levels, "logits": [], "reg": [], "ctr": [], "center": [], "named": named}
     for l, f in enumerate(levels):
         cls_t = tower(f, "cls_tower")
         ctr_t = tower(f, "center_tower")
         cor_t = tower(ctr_t, "corners_tower")  # CORNER_TOWER_ON_CENTER_TOWER
+        named[f"cls_tower.l{l}"], named[f"center_tower.l{l}"], named[f"corners_tower.l{l}"] = cls_t, ctr_t, cor_t
         center = net.conv_bias(ctr_t, HEAD + "center_pred", 1, 1, store=False)
         delta = net.conv_bias(cor_t, HEAD + "corners_pred", 1, 1, store=False)
         scale = sd[f"{HEAD}scales.{l}.scale"].float()

@@ -64,6 +64,7 @@ def main():
     N, H, W = 2, 256, 320
     imgs = torch.randint(0, 256, (N, 3, H, W), dtype=torch.uint8, generator=g)
     sizes = [(H, W), (H - 40, W - 24)]
+    eng.keep_activations(True)
     eng.forward_dense(imgs.to(dev), sizes)
     torch.cuda.synchronize()
     heads = [eng.head_outputs(l) for l in range(5)]
@@ -74,6 +75,11 @@ def main():
         t0 = time.time()
         ref = omodel.forward_dense(sd, depth, batch, mode)
         print(f"oracle {mode} forward {time.time()-t0:.1f}s")
+        for name, r in ref["named"].items():
+            a = eng.activation(name).cpu()
+            rel = ((a - r).norm() / (r.norm() + 1e-12)).item()
+            if rel > 2e-3 or name in ("stem", "pool", "res2.0", "res5.2", "p3", "p7"):
+                print(f"  [{mode}] {name:18s} rel_l2={rel:.3g} max|d|={(a - r).abs().max().item():.3g} absmax={r.abs().max().item():.3g}")
         for l in range(5):
             lg = heads[l]["logits"].cpu()
             cd = heads[l]["ctr_delta"].cpu()
@@ -92,6 +98,7 @@ def main():
         compare_post(spec, eng, heads, sizes, osz, dets, counts)
 
     # ---- timing at the benchmark shape
+    eng.keep_activations(False)
     N, H, W = int(os.environ.get("BN", "8")), 1024, 1024
     imgs = torch.randint(0, 256, (N, 3, H, W), dtype=torch.uint8, generator=g).to(dev)
     sizes = [(H, W)] * N

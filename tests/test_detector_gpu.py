@@ -1,0 +1,112 @@
+"""GPU tests of the reference-facing surface: OneStageDetector(cfg)(batched_inputs), DefaultPredictor, detect_host."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def model():
+    from dafne_b200.config import get_cfg
+    from dafne_b200.modeling import build_model
+
+    cfg = get_cfg()
+    cfg.merge_from_file(os.path.join(ROOT, "configs", "dota10_r50_1024.yaml"))
+    cfg.MODEL.DEVICE = "cuda:0"
+    return build_model(cfg)
+
+
+def _inputs(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return [{"image": torch.randint(0, 256, (3, 256, 320), dtype=torch.uint8, generator=g), "height": 512, "width": 640},
+            {"image": torch.randint(0, 256, (3, 200, 300), dtype=torch.uint8, generator=g)}]
+
+
+def test_forward_returns_instances_with_reference_fields(model):
+    out = model(_inputs())
+    assert len(out) == 2
+    for o, size in zip(out, [(512, 640), (200, 300)]):
+        inst = o["instances"]
+        assert inst.image_size == size
+        n = len(inst)
+        assert inst.pred_boxes.tensor.shape == (n, 4) and inst.pred_corners.shape == (n, 8)
+        assert inst.scores.shape == (n,) and inst.centerness.shape == (n,) and inst.locations.shape == (n, 2)
+        assert inst.pred_classes.dtype == torch.int64 and inst.fpn_levels.dtype == torch.int64
+        s = inst.scores
+        assert bool((s[:-1] >= s[1:]).all()) and n > 0 and n <= 1000
+
+
+def test_batch_result_equals_padded_single_semantics(model):
+    """Reference semantics for mixed sizes: zero-pad to the batch maximum; GN statistics see the padding. Running the
+    small image alone therefore differs slightly from running it in the batch, but a batch of one reproduces itself."""
+    a = model(_inputs(3)[:1])[0]["instances"]
+    b = model(_inputs(3)[:1])[0]["instances"]
+    assert torch.equal(a.pred_classes, b.pred_classes) and torch.equal(a.pred_corners, b.pred_corners)
+
+
+def test_float_images_and_uint8_images_agree(model):
+    inp = _inputs(5)[:1]
+    a = model(inp)[0]["instances"]
+    inp_f = [{**inp[0], "image": inp[0]["image"].float()}]
+    b = model(inp_f)[0]["instances"]
+    assert torch.equal(a.pred_classes, b.pred_classes) and torch.equal(a.scores, b.scores)
+
+
+def test_do_postprocess_false_then_manual_rescale(model):
+    inp = _inputs(7)[:1]
+    raw = model.inference(inp, do_postprocess=False)
+    inst = raw[0]["instances"]
+    assert inst.image_size == (256, 320)
+    full = model(inp)[0]["instances"]
+    model._postprocess(raw, inp)
+    # the rescaled corners of the unfiltered result contain every post-processed row
+    assert len(inst) >= len(full)
+    assert torch.allclose(inst.pred_corners[: 5], full.pred_corners[: 5]) or len(inst) != len(full)
+
+
+def test_select_over_all_levels_like_tta(model):
+    """tta.py:264-268: concatenate instances of several runs, then NMS + top-k over the union."""
+    from dafne_b200.structures import Instances
+
+    inp = _inputs(9)[:1]
+    a = model.inference(inp, do_postprocess=False)[0]["instances"]
+    merged = Instances.cat([a, a])  # duplicates must collapse back to the original set
+    out = model.proposal_generator.dafne_outputs.select_over_all_levels([merged])[0]
+    assert len(out) == len(a)
+    assert torch.equal(out.scores, a.scores)
+
+
+def test_default_predictor_call_shape(model):
+    from dafne_b200.modeling import DefaultPredictor
+
+    pred = DefaultPredictor(model.cfg)
+    img = np.random.default_rng(0).integers(0, 256, (128, 160, 3), dtype=np.uint8)
+    out = pred(img)
+    assert "instances" in out and out["instances"].image_size == (128, 160)
+
+
+def test_detect_host_equals_device_path(model):
+    eng = model._get_engine()
+    g = torch.Generator().manual_seed(13)
+    batch = torch.randint(0, 256, (2, 3, 256, 256), dtype=torch.uint8, generator=g)
+    sizes = [(256, 256), (256, 256)]
+    dets_d, counts_d = eng.detect(batch.cuda(), sizes)
+    hd, hc = eng.detect_host(batch.pin_memory(), sizes)
+    torch.cuda.synchronize()
+    assert torch.equal(hc, counts_d.cpu())
+    n = int(hc[0])
+    assert torch.equal(hd[0, :n], dets_d[0, :n].cpu())
+
+
+def test_unsupported_config_fails_loudly():
+    from dafne_b200.config import get_cfg
+    from dafne_b200.modeling import build_model
+
+    cfg = get_cfg()
+    cfg.MODEL.DAFNE.CORNER_PREDICTION = "direct"
+    with pytest.raises(NotImplementedError):
+        build_model(cfg)

@@ -1,0 +1,213 @@
+"""GPU parity of the post-processing kernels against the oracle: bit-exact (integer / index work and the faithful fp32
+arithmetic), through the C ABI, on the committed golden fixtures and on seeded random inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import postprocess as opost
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def test_sort_quadrilateral_matches_reference_golden_on_gpu():
+    from dafne_b200.modeling import sort_quadrilateral
+
+    g = np.load(os.path.join(GOLD, "sort_corners.npz"))
+    got = sort_quadrilateral(torch.from_numpy(g["quads"]).to(_dev())).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), g["sorted"].view(np.uint32))
+
+
+def test_sort_quadrilateral_empty():
+    from dafne_b200.modeling import sort_quadrilateral
+
+    assert sort_quadrilateral(torch.zeros(0, 8, device=_dev())).shape == (0, 8)
+
+
+@pytest.mark.parametrize("offset", [0.0, 4400.0, 15400.0])
+def test_poly_iou_bit_exact_vs_oracle_f32(offset):
+    """Including the class-offset regimes where fp32 cancels catastrophically: the kernel must
+    reproduce the oracle's fp32 result bit for bit, whatever its distance from the true IoU."""
+    from dafne_b200.modeling import poly_iou
+
+    g = np.load(os.path.join(GOLD, "polyiou_ref.npz"))
+    p = (g["p"] + offset).astype(np.float32)
+    q = (g["q"] + offset).astype(np.float32)
+    want = opost.iou_poly_batch(p, q)
+    got = poly_iou(torch.from_numpy(p).to(_dev()), torch.from_numpy(q).to(_dev())).cpu().numpy()
+    same = got.view(np.uint32) == want.view(np.uint32)
+    assert same.all(), f"{(~same).sum()} of {len(same)} differ, first at {np.nonzero(~same)[0][:5]}"
+    if offset == 0.0:
+        assert np.abs(got.astype(np.float64) - g["iou"]).max() < 5e-3  # and close to the reference's double result
+
+
+def _random_boxes(rng, n, span=400, ncls=15, small=False):
+    from tests.golden.make_golden import rot_rects
+
+    w, h = (12, 4) if small else (48, 16)
+    boxes = rot_rects(rng, n, w, h, center=(0, span), jitter=1.0)
+    scores = rng.uniform(0.05, 1.0, n).astype(np.float32)
+    classes = rng.integers(0, ncls, n).astype(np.int64)
+    return boxes, scores, classes
+
+
+def _oracle_nms(boxes, scores, classes, thr, merge=True):
+    order = np.lexsort((np.arange(len(scores)), -scores.astype(np.float64)))
+    idx = classes.copy()
+    if merge:
+        idx[idx == 5] = 4
+    span = (boxes.max() - boxes.min()) + np.float32(1.0)
+    shifted = boxes + (idx.astype(np.float32) * span)[:, None]
+    keep = opost.greedy_nms(shifted[order], thr)
+    return order[keep]
+
+
+@pytest.mark.parametrize("n,span,ncls,small", [(1, 100, 1, False), (63, 200, 3, False), (64, 200, 15, False),
+                                              (65, 100, 1, False), (700, 300, 15, False), (2000, 500, 15, True),
+                                              (3000, 1024, 1, False)])
+def test_poly_nms_matches_oracle(n, span, ncls, small):
+    from dafne_b200.modeling import batched_nms_poly
+
+    rng = np.random.default_rng(n)
+    boxes, scores, classes = _random_boxes(rng, n, span, ncls, small)
+    want = _oracle_nms(boxes, scores, classes, 0.1)
+    got = batched_nms_poly(torch.from_numpy(boxes).to(_dev()), torch.from_numpy(scores).to(_dev()),
+                           torch.from_numpy(classes).to(_dev()), 0.1).cpu().numpy()
+    assert np.array_equal(got, want), f"kept {len(got)} vs {len(want)}"
+
+
+def test_poly_nms_score_ties_and_duplicates():
+    """Exact score ties: order is defined as ascending input index; duplicates of a box are suppressed by the first."""
+    from dafne_b200.modeling import batched_nms_poly
+
+    rng = np.random.default_rng(0)
+    boxes, scores, classes = _random_boxes(rng, 300, 150, 2)
+    boxes[100:200] = boxes[0:100]
+    scores[:] = np.repeat(rng.uniform(0.1, 0.9, 30).astype(np.float32), 10)
+    classes[100:200] = classes[0:100]
+    want = _oracle_nms(boxes, scores, classes, 0.1)
+    got = batched_nms_poly(torch.from_numpy(boxes).to(_dev()), torch.from_numpy(scores).to(_dev()),
+                           torch.from_numpy(classes).to(_dev()), 0.1).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_poly_gpu_nms_host_dropin():
+    """The reference's FFI shape: dets [n, 9] host numpy (offsets applied by the caller) -> list of kept indices."""
+    from dafne_b200.modeling import poly_gpu_nms
+
+    rng = np.random.default_rng(11)
+    boxes, scores, _ = _random_boxes(rng, 500, 200, 1)
+    dets = np.hstack([boxes, scores[:, None]]).astype(np.float32)
+    order = np.lexsort((np.arange(500), -scores.astype(np.float64)))
+    want = order[opost.greedy_nms(boxes[order], 0.1)]
+    assert poly_gpu_nms(dets, 0.1, 0) == want.tolist()
+    assert poly_gpu_nms(dets[:0], 0.1, 0) == []
+
+
+def test_vehicle_merge_hack():
+    from dafne_b200.modeling import batched_nms_poly
+
+    b = np.array([[0, 0, 10, 0, 10, 10, 0, 10], [1, 1, 11, 1, 11, 11, 1, 11]], np.float32)
+    s = torch.tensor([0.9, 0.8], device=_dev())
+    bt = torch.from_numpy(b).to(_dev())
+    assert batched_nms_poly(bt, s, torch.tensor([4, 5], device=_dev()), 0.1).tolist() == [0]  # 5 is treated as 4
+    assert batched_nms_poly(bt, s, torch.tensor([3, 5], device=_dev()), 0.1).tolist() == [0, 1]
+    assert batched_nms_poly(bt, s, torch.tensor([4, 5], device=_dev()), 0.1, vehicle_merge=False).tolist() == [0, 1]
+
+
+def _engine(C_, sort_c, twc, pre, post):
+    from dafne_b200.engine import DafneEngine
+    from dafne_b200.spec import ModelSpec
+
+    spec = ModelSpec(resnet_depth=50, num_classes=C_, sort_corners=sort_c, thresh_with_ctr=twc, pre_nms_topk=pre,
+                     post_nms_topk=post)
+    return DafneEngine(spec, _dev()), spec
+
+
+def _compare(res, dets, counts, exact=True):
+    dets = dets.cpu().numpy()
+    counts = counts.cpu().numpy()
+    for i, r in enumerate(res):
+        n = len(r["scores"])
+        assert counts[i] == n, (i, counts[i], n)
+        g = dets[i, :n]
+        assert np.array_equal(g[:, 18].view(np.uint32).astype(np.int64), r["canon"])  # candidate indices: bit-exact
+        assert np.array_equal(g[:, 14].astype(np.int64), r["pred_classes"])
+        assert np.array_equal(g[:, 15].astype(np.int64), r["fpn_levels"])
+        assert np.array_equal(g[:, 0:8], r["pred_corners"])
+        assert np.array_equal(g[:, 8:12], r["pred_boxes"])
+        assert np.array_equal(g[:, 12], r["scores"])
+        assert np.array_equal(g[:, 13], r["centerness"])
+        assert np.array_equal(g[:, 16:18], r["locations"])
+
+
+@pytest.mark.parametrize("tag", ["c15_sort", "c15_ctr", "c1_nosort"])
+def test_postprocess_external_matches_golden(tag):
+    g = np.load(os.path.join(GOLD, f"postprocess_{tag}.npz"))
+    C_, sort_c, twc, pre, post = g["meta"].tolist()
+    eng, spec = _engine(C_, bool(sort_c), bool(twc), pre, post)
+    logits = [torch.from_numpy(g[f"logits{l}"]) for l in range(5)]
+    reg = [torch.from_numpy(g[f"reg{l}"]) for l in range(5)]
+    ctr = [torch.from_numpy(g[f"ctr{l}"]) for l in range(5)]
+    sizes = [tuple(r) for r in g["sizes"].tolist()]
+    osz = [tuple(r) for r in g["osz"].tolist()]
+    dets, counts = eng.postprocess_external(logits, reg, ctr, sizes, osz, True)
+    res = [{k[len(f"out{i}_"):]: g[k] for k in g.files if k.startswith(f"out{i}_")} for i in range(2)]
+    _compare(res, dets, counts)
+    eng.close()
+
+
+@pytest.mark.parametrize("C_,sort_c,twc,seed,scale", [(15, True, False, 21, 1.0), (15, True, True, 22, 1.0),
+                                                      (1, True, False, 23, 2.0), (16, False, False, 24, 1.0),
+                                                      (2, False, True, 25, 0.5)])
+def test_postprocess_random_heads_match_oracle(C_, sort_c, twc, seed, scale):
+    """Per-level top-k cap active at P3, ragged image sizes, rescaling to a different output size, odd level sizes."""
+    rng = np.random.default_rng(seed)
+    N = 3
+    hw = [(50, 38), (25, 19), (13, 10), (7, 5), (4, 3)]
+    strides = [8, 16, 32, 64, 128]
+    bias = -5.6 if twc else -2.6
+    logits = [rng.normal(bias, 1.3, (N, C_, h, w)).astype(np.float32) for h, w in hw]
+    base = np.array([-3, -1, 3, -1, 3, 1, -3, 1], np.float32).reshape(1, 8, 1, 1) * scale
+    reg = [(base + rng.normal(0, 0.8, (N, 8, h, w))).astype(np.float32) for h, w in hw]
+    ctr = [rng.normal(0, 1, (N, 1, h, w)).astype(np.float32) for h, w in hw]
+    sizes = [(400, 304), (380, 290), (333, 257)]
+    osz = [(800, 608), (380, 290), (100, 80)]
+    eng, spec = _engine(C_, sort_c, twc, 300, 200)
+    res = opost.postprocess(logits, reg, ctr, strides, sizes, osz, pre_nms_topk=300, post_nms_topk=200,
+                            sort_corners=sort_c, thresh_with_ctr=twc)
+    dets, counts = eng.postprocess_external([torch.from_numpy(t) for t in logits], [torch.from_numpy(t) for t in reg],
+                                            [torch.from_numpy(t) for t in ctr], sizes, osz, True)
+    assert max(len(r["scores"]) for r in res) > 50
+    _compare(res, dets, counts)
+    # do_postprocess=False (the TTA call shape, tta.py:190-194): no rescale / clip / filter
+    res2 = opost.postprocess(logits, reg, ctr, strides, sizes, osz, pre_nms_topk=300, post_nms_topk=200,
+                             sort_corners=sort_c, thresh_with_ctr=twc, do_postprocess=False)
+    dets2, counts2 = eng.postprocess_external([torch.from_numpy(t) for t in logits], [torch.from_numpy(t) for t in reg],
+                                              [torch.from_numpy(t) for t in ctr], sizes, osz, False)
+    _compare(res2, dets2, counts2)
+    eng.close()
+
+
+def test_postprocess_empty_and_all_pass():
+    eng, spec = _engine(3, True, False, 50, 20)
+    hw = [(8, 8), (4, 4), (2, 2), (1, 1), (1, 1)]
+    strides = [8, 16, 32, 64, 128]
+    rng = np.random.default_rng(9)
+    # image 0: nothing above threshold; image 1: every (location, class) passes -> top-k everywhere
+    logits = [np.stack([np.full((3, h, w), -20.0), rng.normal(3.0, 1.0, (3, h, w))]).astype(np.float32) for h, w in hw]
+    reg = [rng.normal(0, 2, (2, 8, h, w)).astype(np.float32) for h, w in hw]
+    ctr = [rng.normal(0, 1, (2, 1, h, w)).astype(np.float32) for h, w in hw]
+    sizes = [(64, 64), (64, 64)]
+    res = opost.postprocess(logits, reg, ctr, strides, sizes, None, pre_nms_topk=50, post_nms_topk=20)
+    dets, counts = eng.postprocess_external([torch.from_numpy(t) for t in logits], [torch.from_numpy(t) for t in reg],
+                                            [torch.from_numpy(t) for t in ctr], sizes, None, True)
+    assert counts.tolist()[0] == 0 and len(res[0]["scores"]) == 0
+    _compare(res, dets, counts)
+    eng.close()
