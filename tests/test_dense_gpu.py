@@ -109,7 +109,16 @@ def test_end_to_end_detections_vs_fp32_oracle(setup):
             a = np.array([k for k, _ in common])
             b = np.array([k for _, k in common])
             assert np.abs(dets[i, b, 12] - w["scores"][a]).max() <= 1e-3  # scores within 1e-3
-            assert np.abs(dets[i, b, 0:8] - w["pred_corners"][a]).max() <= 1.0  # coordinates within a pixel (p7 stride 128)
+            # Coordinates within a pixel (p7 stride 128). sort_quadrilateral picks its start vertex / direction by
+            # strict comparisons (sort_corners.py:46,65-69), so a quad whose two leftmost x sit within the fp16 drift
+            # may come out as another vertex order of the SAME polygon: compare modulo the 8 orders and bound how
+            # many rows needed one.
+            g4 = dets[i, b, 0:8].reshape(-1, 4, 2)
+            w4 = w["pred_corners"][a].reshape(-1, 4, 2)
+            orders = [np.roll(np.arange(4), s) for s in range(4)] + [np.roll(np.arange(4)[::-1], s) for s in range(4)]
+            d = np.stack([np.abs(g4[:, o] - w4).reshape(len(a), -1).max(1) for o in orders], 1)
+            assert d.min(1).max() <= 1.0
+            assert (d[:, 0] > 1.0).mean() <= 0.02, "more than 2% of the matched quads changed vertex order"
 
 
 def test_r101_plan_runs_and_matches_oracle_heads():
