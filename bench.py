@@ -244,6 +244,7 @@ def run_ours(args):
     dets, counts = step_device(0)
     torch.cuda.synchronize()
     det_counts = counts.cpu().tolist()
+    post_counts = eng.post_counts()
 
     # per-launch timing of one forward (CUDA events on the launching stream) for the roofline of the dominant kernel
     prof = eng.profile_forward(dev_sets[0], sizes)
@@ -282,6 +283,9 @@ def run_ours(args):
                 "l2": f"{n_sets} distinct input batches ({n_sets * batch * 3 * H * W / 2**20:.0f} MiB) rotate; "
                       f"activation workspace {eng.workspace_bytes / 2**20:.0f} MiB >> 126 MiB L2",
                 "detections_per_image": det_counts[:8],
+                "nms_boxes_in_per_image": [c["nms_in"] for c in post_counts[:8]],
+                "nms_boxes_kept_per_image": [c["nms_kept"] for c in post_counts[:8]],
+                "candidates_per_level_image0": post_counts[0]["candidates"],
                 "gflop_per_image": gflop_img,
                 "conv_roofline_frac_whole_step": value / world * gflop_img * 1e9 / (peak_tf * 1e12),
             },

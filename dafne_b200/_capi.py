@@ -87,6 +87,7 @@ _SIGNATURES = {
     "dafne_detect_host": (_i, [_vp, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _i, _vp]),
     "dafne_debug_keep_activations": (_i, [_vp, _i]),
     "dafne_debug_activation": (_i, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "dafne_debug_post_counts": (_i, [_vp, C.POINTER(C.c_int32), _vp]),
     "dafne_set_profiling": (_i, [_vp, _i]),
     "dafne_get_profile": (_i, [_vp, C.c_void_p, _i, C.POINTER(_i)]),
     "dafne_stats": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_double), _i]),
@@ -97,6 +98,7 @@ _SIGNATURES = {
     "dafne_gn_relu_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "dafne_sort_quadrilateral": (_i, [_vp, _vp, _i, _vp]),
     "dafne_poly_iou": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "dafne_poly_pair_filter": (_i, [_vp, _vp, _vp, _i, _vp]),
     "dafne_poly_nms": (_i, [_vp, _vp, _vp, _i, _f, _i, _vp, _vp, _vp, C.c_size_t, _vp]),
     "dafne_poly_nms_scratch_bytes": (_i, [_i, C.POINTER(C.c_size_t)]),
     "dafne_poly_nms_host": (_i, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), _i, _i, _f, _i]),

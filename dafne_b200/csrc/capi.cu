@@ -33,7 +33,7 @@ int dafne_abi_version(void) { return DAFNE_ABI_VERSION; }
 
 int dafne_conv_nhwc(const void* in, int N, int H, int W, int Cin, const void* w, int Cout, int ksize, int stride,
                     const float* scale, const float* shift, int relu, const void* residual, int res_H, int res_W,
-                    int res_shift, float* gn_sums, void* out_f16, float* out_f32, int out_ld, void* stream) {
+                    int res_shift, int64_t* gn_sums, void* out_f16, float* out_f32, int out_ld, void* stream) {
     if (!in || !w || ((out_f16 == nullptr) == (out_f32 == nullptr))) {
         set_error("dafne_conv_nhwc: need in, w and exactly one of out_f16 / out_f32");
         return -1;
@@ -59,15 +59,16 @@ int dafne_conv_nhwc(const void* in, int N, int H, int W, int Cin, const void* w,
     d.res_H = res_H;
     d.res_W = res_W;
     d.res_shift = res_shift;
-    d.gn_sums = gn_sums;
+    d.gn_sums = reinterpret_cast<long long*>(gn_sums);
     ConvPlan plan;
     if (conv_plan_build(d, &plan, num_sms_cached())) return -1;
     return conv_plan_launch(plan, static_cast<cudaStream_t>(stream));
 }
 
-int dafne_gn_relu_nhwc(const void* in, void* out, int N, int HW, int C, int groups, const float* sums,
+int dafne_gn_relu_nhwc(const void* in, void* out, int N, int HW, int C, int groups, const int64_t* sums,
                        const float* gamma, const float* beta, float eps, void* stream) {
-    return launch_gn_relu(static_cast<const __half*>(in), static_cast<__half*>(out), N, HW, C, groups, sums, gamma,
+    return launch_gn_relu(static_cast<const __half*>(in), static_cast<__half*>(out), N, HW, C, groups,
+                          reinterpret_cast<const long long*>(sums), gamma,
                           beta, eps, static_cast<cudaStream_t>(stream));
 }
 
@@ -262,6 +263,21 @@ int dafne_debug_activation(dafne_ctx* ctx, const char* name, const void** ptr, i
     return 0;
 }
 
+int dafne_debug_post_counts(dafne_ctx* ctx, int32_t* host_out, void* stream) {
+    NEED_CTX(ctx, "dafne_debug_post_counts");
+    if (!ctx->ws) {
+        set_error("dafne_debug_post_counts: no workspace bound");
+        return -1;
+    }
+    int hw[10];
+    for (int l = 0; l < 5; ++l) {
+        hw[2 * l] = ctx->head_out[l][0].H;
+        hw[2 * l + 1] = ctx->head_out[l][0].W;
+    }
+    return postprocess_debug_counts(ctx->post_scratch, ctx->N, 5, hw, ctx->spec.num_classes, ctx->spec.pre_nms_topk,
+                                    host_out, static_cast<cudaStream_t>(stream));
+}
+
 int dafne_set_profiling(dafne_ctx* ctx, int enable) {
     NEED_CTX(ctx, "dafne_set_profiling");
     ctx->profiling = enable != 0;
@@ -316,6 +332,9 @@ int dafne_sort_quadrilateral(const float* quads, float* out, int n, void* stream
 }
 int dafne_poly_iou(const float* p, const float* q, float* iou, int n, void* stream) {
     return launch_poly_iou(p, q, iou, n, static_cast<cudaStream_t>(stream));
+}
+int dafne_poly_pair_filter(const float* p, const float* q, uint8_t* fired, int n, void* stream) {
+    return launch_pair_filter(p, q, fired, n, static_cast<cudaStream_t>(stream));
 }
 int dafne_poly_nms_scratch_bytes(int n, size_t* bytes) {
     *bytes = poly_nms_scratch_bytes(n);

@@ -45,34 +45,35 @@ struct ConvCfg {
 
 // Sum 16 per-lane values across the warp; lane l returns the total of value index
 // 8*b4 + 4*b3 + 2*b2 + b1 (b_i = bit i of l). 16 shuffles instead of 80.
-__device__ __forceinline__ float warp_reduce16_scatter(const float (&v)[16], uint32_t lane) {
+template <typename T>
+__device__ __forceinline__ T warp_reduce16_scatter(const T (&v)[16], uint32_t lane) {
     const uint32_t full = 0xffffffffu;
-    float a[8], b[4], c[2];
+    T a[8], b[4], c[2];
     bool hi = lane & 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        float send = hi ? v[i] : v[i + 8];
-        float keep = hi ? v[i + 8] : v[i];
+        T send = hi ? v[i] : v[i + 8];
+        T keep = hi ? v[i + 8] : v[i];
         a[i] = keep + __shfl_xor_sync(full, send, 16);
     }
     hi = lane & 8;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float send = hi ? a[i] : a[i + 4];
-        float keep = hi ? a[i + 4] : a[i];
+        T send = hi ? a[i] : a[i + 4];
+        T keep = hi ? a[i + 4] : a[i];
         b[i] = keep + __shfl_xor_sync(full, send, 8);
     }
     hi = lane & 4;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        float send = hi ? b[i] : b[i + 2];
-        float keep = hi ? b[i + 2] : b[i];
+        T send = hi ? b[i] : b[i + 2];
+        T keep = hi ? b[i + 2] : b[i];
         c[i] = keep + __shfl_xor_sync(full, send, 4);
     }
     hi = lane & 2;
-    float send = hi ? c[0] : c[1];
-    float keep = hi ? c[1] : c[0];
-    float d = keep + __shfl_xor_sync(full, send, 2);
+    T send = hi ? c[0] : c[1];
+    T keep = hi ? c[1] : c[0];
+    T d = keep + __shfl_xor_sync(full, send, 2);
     d += __shfl_xor_sync(full, d, 1);
     return d;
 }
@@ -285,21 +286,30 @@ __global__ void __launch_bounds__(256, 1)
                         }
                     }
                     if (p.gn_sums != nullptr) {
+                        // Per-pixel partials (fixed 8-channel order) become 64-bit fixed point BEFORE any cross-thread
+                        // reduction: integer addition is associative, so the statistics are bit-identical from run
+                        // to run and independent of tiling / batch composition (no float atomics).
                         const int groups = p.Cout >> 3;
                         const int n_lo = __shfl_sync(0xffffffffu, n, 0);
                         int n_hi = __shfl_sync(0xffffffffu, n, 31);
                         if (n_hi > p.N - 1) n_hi = p.N - 1;
+                        long long q[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            q[i] = __float2ll_rn(gs[i] * ((i & 1) ? kGnSqScale : kGnSumScale));
                         for (int img = n_lo; img <= n_hi; ++img) {
                             const bool mine = valid && n == img;
-                            float mv[16];
+                            long long mv[16];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) mv[i] = mine ? gs[i] : 0.0f;
-                            const float tot = warp_reduce16_scatter(mv, lane);
+                            for (int i = 0; i < 16; ++i) mv[i] = mine ? q[i] : 0ll;
+                            const long long tot = warp_reduce16_scatter(mv, lane);
                             if ((lane & 1) == 0) {
                                 const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
                                                 ((lane >> 1) & 1);
                                 const int g = (nt * BLOCK_N + chbase) / 8 + (idx >> 1);
-                                atomicAdd(p.gn_sums + (static_cast<size_t>(img) * groups + g) * 2 + (idx & 1), tot);
+                                atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_sums) +
+                                              (static_cast<size_t>(img) * groups + g) * 2 + (idx & 1),
+                                          static_cast<unsigned long long>(tot));
                             }
                         }
                     }

@@ -23,8 +23,13 @@ struct ConvDesc {
     int relu = 0;
     const __half* residual = nullptr;  // NHWC fp16 [N, res_H, res_W, Cout]; added at (y>>res_shift, x>>res_shift)
     int res_H = 0, res_W = 0, res_shift = 0;
-    float* gn_sums = nullptr;  // [N][Cout/8][2] fp32 (sum, sum of squares of the fp16-rounded output), accumulated
+    // [N][Cout/8][2] 64-bit fixed point, accumulated: (sum * 2^20, sum of squares * 2^12) of the fp16-rounded output
+    // over each image's pixels and each group of 8 channels. Fixed point makes the reduction order-independent.
+    long long* gn_sums = nullptr;
 };
+
+constexpr float kGnSumScale = 1048576.0f;  // 2^20
+constexpr float kGnSqScale = 4096.0f;      // 2^12
 
 struct ConvParams {
     int N, Hout, Wout, Cin, Cout;
@@ -37,7 +42,7 @@ struct ConvParams {
     int relu;
     const __half* residual;
     int res_H, res_W, res_shift;
-    float* gn_sums;
+    long long* gn_sums;
     float* out_f32;
     int out_ld;
 };

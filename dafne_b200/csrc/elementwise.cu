@@ -213,7 +213,7 @@ int launch_maxpool3x3s2(const __half* in, int N, int H, int W, int C, __half* ou
 
 // ------------------------------------------------------------------------------------------------ GroupNorm + ReLU
 __global__ void gn_relu_kernel(const __half* in, __half* out, int N, int HW, int C,
-                               int groups, const float* __restrict__ sums, const float* __restrict__ gamma,
+                               int groups, const long long* __restrict__ sums, const float* __restrict__ gamma,
                                const float* __restrict__ beta, float eps) {
     const int c8 = C / 8;  // one uint4 = one group of 8 channels
     const size_t per_img = static_cast<size_t>(HW) * c8;
@@ -223,8 +223,10 @@ __global__ void gn_relu_kernel(const __half* in, __half* out, int N, int HW, int
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int g = i % c8;
         const int n = i / per_img;
-        const float s1 = __ldg(sums + (static_cast<size_t>(n) * groups + g) * 2);
-        const float s2 = __ldg(sums + (static_cast<size_t>(n) * groups + g) * 2 + 1);
+        const float s1 = static_cast<float>(static_cast<double>(__ldg(sums + (static_cast<size_t>(n) * groups + g) * 2)) *
+                                            (1.0 / kGnSumScale));
+        const float s2 = static_cast<float>(
+            static_cast<double>(__ldg(sums + (static_cast<size_t>(n) * groups + g) * 2 + 1)) * (1.0 / kGnSqScale));
         const float mean = s1 * inv_cnt;
         const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
@@ -244,7 +246,7 @@ __global__ void gn_relu_kernel(const __half* in, __half* out, int N, int HW, int
     }
 }
 
-int launch_gn_relu(const __half* in, __half* out, int N, int HW, int C, int groups, const float* sums,
+int launch_gn_relu(const __half* in, __half* out, int N, int HW, int C, int groups, const long long* sums,
                    const float* gamma, const float* beta, float eps, cudaStream_t s) {
     if (C != groups * 8) {
         set_error("gn_relu: needs C == 8 * groups (C=%d groups=%d)", C, groups);

@@ -18,8 +18,9 @@ int launch_stem(const __half* in_nhwc4, int N, int H, int W, const float* w_pack
 // 3x3 stride-2 pad-1 max pool, NHWC fp16, C % 8 == 0.
 int launch_maxpool3x3s2(const __half* in, int N, int H, int W, int C, __half* out, cudaStream_t s);
 
-// y = relu(groupnorm(x)) from per-(image, group) (sum, sumsq); NHWC fp16, (C / groups) == 8.
-int launch_gn_relu(const __half* in, __half* out, int N, int HW, int C, int groups, const float* sums,
+// y = relu(groupnorm(x)) from per-(image, group) fixed-point (sum, sumsq) (see ConvDesc::gn_sums); NHWC fp16,
+// (C / groups) == 8.
+int launch_gn_relu(const __half* in, __half* out, int N, int HW, int C, int groups, const long long* sums,
                    const float* gamma, const float* beta, float eps, cudaStream_t s);
 
 // y = relu(x), fp16, n8 = number of 8-element vectors.

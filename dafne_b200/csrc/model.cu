@@ -331,7 +331,7 @@ struct Builder {
 
     // out = epilogue(conv(in)); allocates the fp16 output unless out_f32 is given
     Act conv(const ConvLayer& L, const Act& in, bool relu, const Act* residual = nullptr, int res_shift = 0,
-             float* gn_sums = nullptr, float* out_f32 = nullptr, int out_ld = 0) {
+             long long* gn_sums = nullptr, float* out_f32 = nullptr, int out_ld = 0) {
         ConvDesc d;
         d.in = in.p;
         d.N = in.N;
@@ -426,9 +426,9 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
         lvW[l] = (lvW[l - 1] - 1) / 2 + 1;
     }
     int32_t* sizes_dev = B.persistent<int32_t>(static_cast<size_t>(N) * 4 * sizeof(int32_t));
-    const size_t sums_per = static_cast<size_t>(N) * 32 * 2 * sizeof(float);
+    const size_t sums_per = static_cast<size_t>(N) * 32 * 2 * sizeof(long long);
     const size_t sums_bytes = sums_per * 3 * 4 * 5;
-    float* sums_all = B.persistent<float>(sums_bytes);
+    long long* sums_all = B.persistent<long long>(sums_bytes);
     HeadOut ho[5][3];
     const int ld_logits = sp.num_classes <= 16 ? 16 : 32;
     for (int l = 0; l < 5; ++l)
@@ -555,10 +555,10 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
             bool own = false;
             for (int i = 0; i < 4; ++i) {
                 const std::string tw = kHead + kTowers[t] + ".";
-                float* sums = sums_all ? sums_all + ((static_cast<size_t>(t) * 4 + i) * 5 + l) * (sums_per / sizeof(float))
+                long long* sums = sums_all ? sums_all + ((static_cast<size_t>(t) * 4 + i) * 5 + l) * (sums_per / sizeof(long long))
                                        : nullptr;
                 Act raw = B.conv(B.layer(tw + std::to_string(3 * i)), cur, false, nullptr, 0,
-                                 base ? sums : reinterpret_cast<float*>(1));
+                                 base ? sums : reinterpret_cast<long long*>(1));
                 if (own) B.free_act(cur);
                 // GroupNorm + ReLU in place
                 B.launches += 1;

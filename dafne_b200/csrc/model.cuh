@@ -91,7 +91,7 @@ struct dafne_ctx {
     std::vector<cudaEvent_t> prof_events;  // ops.size() + 2
     int64_t launches_per_forward = 0;
     double flops_per_forward = 0;
-    float* gn_sums_all = nullptr;
+    long long* gn_sums_all = nullptr;
     size_t gn_sums_bytes = 0;
     int32_t* sizes_dev = nullptr;  // [N][4]
     void* images_dev = nullptr;    // staging for dafne_detect_host

@@ -1,0 +1,343 @@
+// Greedy polygon NMS on device, lazily evaluated: only the IoUs the sequential sweep can consult are computed.
+//
+// Semantics (dafne/modeling/nms/nms.py:37-92 -> external poly_gpu_nms): boxes arrive sorted by descending score; box j
+// is kept iff no KEPT earlier box i has IoU(i, j) > thr. The result only depends on IoU(i, j) for kept i, so instead of
+// the reference's full n x n bitmask (n^2/2 polygon clips, ~10 MB mask, host sweep) the boxes are processed in panels of
+// 512:
+//   nms_diag_kernel   panel x panel upper triangle for the rows/columns still alive, then (last block done) the
+//                     sequential sweep inside the panel -> the panel's kept rows
+//   nms_bcast_kernel  kept rows of the panel x every later box still alive; sets `removed` bits
+// Work drops from n^2/2 pairs to about (kept x alive) pairs. Inside both kernels a pair first goes through
+// pair_inter_is_zero() (polyiou.cuh: proves inter == 0 for separated boxes without running the clip); the pairs that
+// need the full fp32 clip are compacted into a shared-memory queue and processed with all lanes busy.
+// No decision differs from evaluating iou_poly_f32(i, j) > thr for every consulted pair.
+#include <stdio.h>
+
+#include "conv_tc.cuh"  // set_error
+#include "polyiou.cuh"
+#include "postprocess.cuh"
+
+namespace dafne {
+
+constexpr int kPanel = 512;
+constexpr int kPanelWords = kPanel / 64;  // 8
+constexpr int kDiagBlocks = kPanelWords * (kPanelWords + 1) / 2;  // 36 (rb <= cb)
+constexpr int kRowChunk = 32;   // kept rows per bcast CTA
+constexpr int kColChunk = 128;  // columns per bcast CTA
+
+typedef unsigned long long u64;
+
+static size_t a256n(size_t v) { return (v + 255) / 256 * 256; }
+
+struct NmsLayout {
+    size_t o_aux, o_removed, o_diag, o_pk, o_ctr, total;
+    int nblk;
+};
+static NmsLayout nms_layout(int N, int max_sel) {
+    NmsLayout y;
+    y.nblk = (max_sel + 63) / 64;
+    size_t o = 0;
+    y.o_aux = o;
+    o = a256n(o + static_cast<size_t>(N) * max_sel * sizeof(NmsAux));
+    y.o_removed = o;
+    o = a256n(o + static_cast<size_t>(N) * y.nblk * 8);
+    y.o_pk = o;
+    o = a256n(o + static_cast<size_t>(N) * kPanelWords * 8);
+    y.o_ctr = o;
+    o = a256n(o + static_cast<size_t>(N) * 4);
+    y.o_diag = o;
+    o = a256n(o + static_cast<size_t>(N) * kPanel * kPanelWords * 8);
+    y.total = o;
+    return y;
+}
+size_t nms_scratch_bytes(int N, int max_sel) { return nms_layout(N, max_sel < 1 ? 1 : max_sel).total; }
+
+// ------------------------------------------------------------------------------------------------ per-box scalars
+__global__ void nms_aux_kernel(const float* __restrict__ boxes, const int* __restrict__ counts, int max_sel,
+                               NmsAux* __restrict__ aux) {
+    const int n = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[n]) return;
+    const size_t r = static_cast<size_t>(n) * max_sel + i;
+    float b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b[k] = boxes[r * 8 + k];
+    aux[r] = nms_aux_of(b);
+}
+
+// ------------------------------------------------------------------------------------------------ diagonal panel
+struct DiagSmem {
+    float rbox[64][8];
+    float cbox[64][8];
+    NmsAux raux[64];
+    NmsAux caux[64];
+    u64 bits[64];
+    unsigned short queue[64 * 64];
+    int qn;
+    int last;
+};
+
+// grid (36, N), 64 threads. Block b -> (rb, cb), rb <= cb, both 64-box blocks of panel `panel`.
+__global__ void __launch_bounds__(64) nms_diag_kernel(const float* __restrict__ boxes, const NmsAux* __restrict__ aux,
+                                                      const int* __restrict__ counts, int max_sel, int nblk,
+                                                      int panel, float thr, u64* __restrict__ removed,
+                                                      u64* __restrict__ diag, u64* __restrict__ pk,
+                                                      int* __restrict__ ctr, int* __restrict__ keep,
+                                                      int* __restrict__ nkeep) {
+    const int n = blockIdx.y;
+    const int m = counts[n];
+    const int base = panel * kPanel;
+    if (base >= m) return;  // uniform for the whole image: nobody counts, nothing to resolve
+    __shared__ DiagSmem sm;
+    // decode (rb, cb) from the linear upper-triangle index
+    int rb = 0, rem = blockIdx.x;
+    while (rem >= kPanelWords - rb) {
+        rem -= kPanelWords - rb;
+        ++rb;
+    }
+    const int cb = rb + rem;
+    const int t = threadIdx.x;
+    const size_t ibase = static_cast<size_t>(n) * max_sel;
+    u64* rmv = removed + static_cast<size_t>(n) * nblk;
+    const int r0 = base + rb * 64, c0 = base + cb * 64;
+    u64 bits_out = 0;
+    if (r0 < m && c0 < m) {
+        const u64 rdead = rmv[r0 >> 6], cdead = rmv[c0 >> 6];
+        const int row = r0 + t, col = c0 + t;
+        if (row < m) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sm.rbox[t][k] = boxes[(ibase + row) * 8 + k];
+            sm.raux[t] = aux[ibase + row];
+        }
+        if (col < m) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sm.cbox[t][k] = boxes[(ibase + col) * 8 + k];
+            sm.caux[t] = aux[ibase + col];
+        }
+        sm.bits[t] = 0;
+        if (t == 0) sm.qn = 0;
+        __syncthreads();
+        const int ncol = min(64, m - c0);
+        // phase 1: thread = row; pre-filter against the alive columns, queue the pairs that need the full clip
+        if (row < m && !((rdead >> t) & 1ull)) {
+            const NmsAux P = sm.raux[t];
+            for (int j = (cb == rb) ? t + 1 : 0; j < ncol; ++j) {
+                if ((cdead >> j) & 1ull) continue;
+                const NmsAux& Q = sm.caux[j];
+                if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) continue;
+                const int pos = atomicAdd(&sm.qn, 1);
+                sm.queue[pos] = static_cast<unsigned short>((t << 6) | j);
+            }
+        }
+        __syncthreads();
+        // phase 2: all lanes busy on the queued pairs
+        const int qn = sm.qn;
+        for (int e = t; e < qn; e += 64) {
+            const int r = sm.queue[e] >> 6, j = sm.queue[e] & 63;
+            if (iou_poly_f32(sm.rbox[r], sm.cbox[j]) > thr) atomicOr(&sm.bits[r], 1ull << j);
+        }
+        __syncthreads();
+        bits_out = sm.bits[t];
+    }
+    diag[(static_cast<size_t>(n) * kPanel + rb * 64 + t) * kPanelWords + cb] = bits_out;
+    __threadfence();
+    __syncthreads();
+    if (t == 0) sm.last = (atomicAdd(&ctr[n], 1) == kDiagBlocks - 1);
+    __syncthreads();
+    if (!sm.last) return;
+    __threadfence();
+
+    // ---- last block of this image: sequential sweep inside the panel (64 rows at a time)
+    __shared__ u64 s_rem[kPanelWords], s_kept[kPanelWords];
+    const u64* dg = diag + static_cast<size_t>(n) * kPanel * kPanelWords;
+    if (t < kPanelWords) {
+        const int w = (base >> 6) + t;
+        s_rem[t] = w < nblk ? rmv[w] : ~0ull;
+        s_kept[t] = 0;
+    }
+    __syncthreads();
+    const int rows_in_panel = min(kPanel, m - base);
+    for (int b = 0; b * 64 < rows_in_panel; ++b) {
+        const int rows = min(64, rows_in_panel - b * 64);
+        // the diagonal word of each row of this block, staged so one thread can walk them back to back
+        sm.bits[t] = t < rows ? __ldcg(dg + (static_cast<size_t>(b) * 64 + t) * kPanelWords + b) : 0ull;
+        __syncthreads();
+        if (t == 0) {
+            u64 cur = s_rem[b], alive = 0;
+            if (rows < 64) cur |= ~0ull << rows;
+#pragma unroll 8
+            for (int r = 0; r < 64; ++r) {
+                if (!((cur >> r) & 1ull)) {
+                    alive |= 1ull << r;
+                    cur |= sm.bits[r];
+                }
+            }
+            s_kept[b] = alive;
+        }
+        __syncthreads();
+        // survivors of this block suppress later blocks of the panel
+        if ((s_kept[b] >> t) & 1ull) {
+            for (int w = b + 1; w < kPanelWords; ++w) {
+                const u64 v = __ldcg(dg + (static_cast<size_t>(b) * 64 + t) * kPanelWords + w);
+                if (v) atomicOr(&s_rem[w], v);
+            }
+        }
+        __syncthreads();
+    }
+    // publish: kept words, removed = not kept for the panel's own boxes, keep list in order
+    int nk = nkeep[n];
+    for (int w = 0; w < kPanelWords; ++w) {
+        const u64 kw = s_kept[w];
+        if ((kw >> t) & 1ull) keep[ibase + nk + __popcll(kw & ((1ull << t) - 1ull))] = base + w * 64 + t;
+        nk += __popcll(kw);
+    }
+    if (t < kPanelWords) {
+        pk[static_cast<size_t>(n) * kPanelWords + t] = s_kept[t];
+        const int w = (base >> 6) + t;
+        if (w < nblk) rmv[w] = ~s_kept[t];
+    }
+    if (t == 0) {
+        nkeep[n] = nk;
+        ctr[n] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ broadcast
+struct BcastSmem {
+    float rbox[kRowChunk][8];
+    NmsAux raux[kRowChunk];
+    float cbox[kColChunk][8];
+    unsigned short queue[kRowChunk * kColChunk];
+    unsigned char dead[kColChunk];
+    int rows[kRowChunk];
+    int qn;
+};
+
+// grid (column chunks after the panel, row chunks of the panel's kept rows, N), 128 threads
+__global__ void __launch_bounds__(kColChunk) nms_bcast_kernel(const float* __restrict__ boxes,
+                                                              const NmsAux* __restrict__ aux,
+                                                              const int* __restrict__ counts, int max_sel, int nblk,
+                                                              int panel, float thr, const u64* __restrict__ pk,
+                                                              u64* __restrict__ removed) {
+    const int n = blockIdx.z;
+    const int m = counts[n];
+    const int c0 = (panel + 1) * kPanel + blockIdx.x * kColChunk;
+    if (c0 >= m) return;
+    // the row chunk: kept rows number [rc*32, rc*32+32) of the panel
+    const u64* pkn = pk + static_cast<size_t>(n) * kPanelWords;
+    int total = 0;
+    u64 kw[kPanelWords];
+#pragma unroll
+    for (int w = 0; w < kPanelWords; ++w) {
+        kw[w] = pkn[w];
+        total += __popcll(kw[w]);
+    }
+    const int k0 = blockIdx.y * kRowChunk;
+    if (k0 >= total) return;
+    const int nrows = min(kRowChunk, total - k0);
+    __shared__ BcastSmem sm;
+    const int t = threadIdx.x;
+    const size_t ibase = static_cast<size_t>(n) * max_sel;
+    if (t < nrows) {
+        // the (k0 + t)-th set bit of the 512-bit kept mask
+        int want = k0 + t, w = 0;
+        while (want >= __popcll(kw[w])) {
+            want -= __popcll(kw[w]);
+            ++w;
+        }
+        u64 v = kw[w];
+        for (int i = 0; i < want; ++i) v &= v - 1;
+        sm.rows[t] = panel * kPanel + w * 64 + (__ffsll(static_cast<long long>(v)) - 1);
+    }
+    if (t == 0) sm.qn = 0;
+    __syncthreads();
+    for (int i = t; i < nrows * 8; i += kColChunk) sm.rbox[i >> 3][i & 7] = boxes[(ibase + sm.rows[i >> 3]) * 8 + (i & 7)];
+    if (t < nrows) sm.raux[t] = aux[ibase + sm.rows[t]];
+    const int col = c0 + t;
+    u64* rmv = removed + static_cast<size_t>(n) * nblk;
+    bool alive = false;
+    NmsAux Q;
+    if (col < m) {
+        alive = !((__ldcg(rmv + (col >> 6)) >> (col & 63)) & 1ull);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm.cbox[t][k] = boxes[(ibase + col) * 8 + k];
+        Q = aux[ibase + col];
+    }
+    sm.dead[t] = alive ? 0 : 1;
+    __syncthreads();
+    if (alive) {
+        for (int r = 0; r < nrows; ++r) {
+            const NmsAux& P = sm.raux[r];
+            if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) continue;
+            const int pos = atomicAdd(&sm.qn, 1);
+            sm.queue[pos] = static_cast<unsigned short>((r << 7) | t);
+        }
+    }
+    __syncthreads();
+    const int qn = sm.qn;
+    for (int e = t; e < qn; e += kColChunk) {
+        const int r = sm.queue[e] >> 7, j = sm.queue[e] & 127;
+        if (sm.dead[j]) continue;  // benign race: any kept row that hits is enough
+        if (iou_poly_f32(sm.rbox[r], sm.cbox[j]) > thr) sm.dead[j] = 1;
+    }
+    __syncthreads();
+    const bool newly = alive && sm.dead[t];
+    const unsigned bal = __ballot_sync(0xffffffffu, newly);
+    if (bal && (t & 31) == 0) {
+        const int cw = c0 + t;  // 32 columns of one warp share a 64-bit word
+        atomicOr(rmv + (cw >> 6), static_cast<u64>(bal) << (cw & 63));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+#define NMS_CHECK_LAUNCH(name)                                          \
+    do {                                                                \
+        cudaError_t e__ = cudaGetLastError();                           \
+        if (e__ != cudaSuccess) {                                       \
+            set_error("%s launch: %s", name, cudaGetErrorString(e__)); \
+            return -1;                                                  \
+        }                                                               \
+    } while (0)
+
+int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float thr, void* scratch, size_t scratch_bytes,
+            int* keep, int* nkeep, cudaStream_t s, int64_t* launches) {
+    const NmsLayout y = nms_layout(N, max_sel);
+    if (y.total > scratch_bytes) {
+        set_error("nms: scratch of %zu bytes is too small, need %zu", scratch_bytes, y.total);
+        return -1;
+    }
+    uint8_t* b = static_cast<uint8_t*>(scratch);
+    NmsAux* aux = reinterpret_cast<NmsAux*>(b + y.o_aux);
+    u64* removed = reinterpret_cast<u64*>(b + y.o_removed);
+    u64* diag = reinterpret_cast<u64*>(b + y.o_diag);
+    u64* pk = reinterpret_cast<u64*>(b + y.o_pk);
+    int* ctr = reinterpret_cast<int*>(b + y.o_ctr);
+    // removed | pk | ctr are contiguous: one clear
+    cudaError_t e = cudaMemsetAsync(removed, 0, y.o_diag - y.o_removed, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(nkeep, 0, static_cast<size_t>(N) * 4, s);
+    if (e != cudaSuccess) {
+        set_error("nms memset: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    nms_aux_kernel<<<dim3((max_sel + 127) / 128, N), 128, 0, s>>>(nmsbox, counts, max_sel, aux);
+    NMS_CHECK_LAUNCH("nms_aux_kernel");
+    const int panels = (max_sel + kPanel - 1) / kPanel;
+    int nl = 1;
+    for (int p = 0; p < panels; ++p) {
+        nms_diag_kernel<<<dim3(kDiagBlocks, N), 64, 0, s>>>(nmsbox, aux, counts, max_sel, y.nblk, p, thr, removed, diag,
+                                                            pk, ctr, keep, nkeep);
+        NMS_CHECK_LAUNCH("nms_diag_kernel");
+        ++nl;
+        const int after = max_sel - (p + 1) * kPanel;
+        if (after > 0) {
+            nms_bcast_kernel<<<dim3((after + kColChunk - 1) / kColChunk, kPanel / kRowChunk, N), kColChunk, 0, s>>>(
+                nmsbox, aux, counts, max_sel, y.nblk, p, thr, pk, removed);
+            NMS_CHECK_LAUNCH("nms_bcast_kernel");
+            ++nl;
+        }
+    }
+    if (launches) *launches += nl;
+    return 0;
+}
+
+}  // namespace dafne

@@ -20,6 +20,7 @@
 #include <stdio.h>
 
 #include "conv_tc.cuh"  // set_error
+#include "polyiou.cuh"
 
 namespace dafne {
 
@@ -35,125 +36,30 @@ namespace dafne {
 constexpr int kMaxSorted = 16384;  // candidates per image the in-smem sort handles
 constexpr int kDet = 20;
 
-// ================================================================================================ polygon IoU (fp32)
-struct P2 {
-    float x, y;
-};
-// sig(d) = (d > eps) - (d < -eps) with the reference's DOUBLE eps = 1e-8 applied to a float: for a float d,
-// (double)d > 1e-8  <=>  d > EPS_BELOW where EPS_BELOW is the largest float <= 1e-8 (there is no float in between).
-__device__ __forceinline__ int sigf(float d) {
-    const float eps_below = 9.99999993922529029e-09f;  // == (float)1e-8, which rounds down
-    return (d > eps_below) - (d < -eps_below);
-}
-__device__ __forceinline__ bool same_pt(P2 a, P2 b) { return sigf(a.x - b.x) == 0 && sigf(a.y - b.y) == 0; }
-__device__ __forceinline__ float cross3(P2 o, P2 a, P2 b) {
-    return (a.x - o.x) * (b.y - o.y) - (b.x - o.x) * (a.y - o.y);
-}
-__device__ __forceinline__ float signed_area(P2* ps, int n) {
-    float acc = 0.f;
-    ps[n] = ps[0];
-    for (int i = 0; i < n; i++) acc += ps[i].x * ps[i + 1].y - ps[i].y * ps[i + 1].x;
-    return acc / 2.0f;
-}
-__device__ __forceinline__ int line_cross(P2 a, P2 b, P2 c, P2 d, P2* out) {
-    const float s1 = cross3(a, b, c);
-    const float s2 = cross3(a, b, d);
-    if (sigf(s1) == 0 && sigf(s2) == 0) return 2;
-    if (sigf(s2 - s1) == 0) return 0;
-    out->x = (c.x * s2 - d.x * s1) / (s2 - s1);
-    out->y = (c.y * s2 - d.y * s1) / (s2 - s1);
-    return 1;
-}
-__device__ __forceinline__ void clip_left(P2* p, int* n_io, P2 a, P2 b) {
-    P2 tmp[24];
-    int n = *n_io, m = 0;
-    p[n] = p[0];
-    for (int i = 0; i < n; i++) {
-        const int si = sigf(cross3(a, b, p[i]));
-        const int sj = sigf(cross3(a, b, p[i + 1]));
-        if (si > 0) tmp[m++] = p[i];
-        if (si != sj) {
-            tmp[m].x = 0.f;  // defined where the reference reads an unwritten slot (see oracle header)
-            tmp[m].y = 0.f;
-            line_cross(a, b, p[i], p[i + 1], &tmp[m]);
-            m++;
-        }
-    }
-    n = 0;
-    for (int i = 0; i < m; i++)
-        if (i == 0 || !same_pt(tmp[i], tmp[i - 1])) p[n++] = tmp[i];
-    while (n > 1 && same_pt(p[n - 1], p[0])) n--;
-    *n_io = n;
-}
-__device__ __forceinline__ float tri_overlap(P2 a, P2 b, P2 c, P2 d) {
-    P2 o;
-    o.x = 0.f;
-    o.y = 0.f;
-    const int s1 = sigf(cross3(o, a, b));
-    const int s2 = sigf(cross3(o, c, d));
-    if (s1 == 0 || s2 == 0) return 0.f;
-    if (s1 == -1) {
-        P2 t = a;
-        a = b;
-        b = t;
-    }
-    if (s2 == -1) {
-        P2 t = c;
-        c = d;
-        d = t;
-    }
-    P2 p[12];
-    int n = 3;
-    p[0] = o;
-    p[1] = a;
-    p[2] = b;
-    clip_left(p, &n, o, c);
-    clip_left(p, &n, c, d);
-    clip_left(p, &n, d, o);
-    float res = fabsf(signed_area(p, n));
-    if (s1 * s2 == -1) res = -res;
-    return res;
-}
-__device__ float iou_poly_f32(const float* pa, const float* qa) {
-    P2 p[6], q[6];
-    for (int i = 0; i < 4; i++) {
-        p[i].x = pa[2 * i];
-        p[i].y = pa[2 * i + 1];
-        q[i].x = qa[2 * i];
-        q[i].y = qa[2 * i + 1];
-    }
-    if (signed_area(p, 4) < 0.f) {
-        P2 t = p[0];
-        p[0] = p[3];
-        p[3] = t;
-        t = p[1];
-        p[1] = p[2];
-        p[2] = t;
-    }
-    if (signed_area(q, 4) < 0.f) {
-        P2 t = q[0];
-        q[0] = q[3];
-        q[3] = t;
-        t = q[1];
-        q[1] = q[2];
-        q[2] = t;
-    }
-    p[4] = p[0];
-    q[4] = q[0];
-    float inter = 0.f;
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) inter += tri_overlap(p[i], p[i + 1], q[j], q[j + 1]);
-    const float a1 = fabsf(signed_area(p, 4));
-    const float a2 = fabsf(signed_area(q, 4));
-    const float uni = a1 + a2 - inter;
-    if (uni == 0.f) return (inter + 1.f) / (uni + 1.f);
-    return inter / uni;
-}
-
+// polygon IoU arithmetic: polyiou.cuh (shared with nms.cu)
 __global__ void poly_iou_kernel(const float* __restrict__ p, const float* __restrict__ q, float* __restrict__ out,
                                 int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = iou_poly_f32(p + 8 * i, q + 8 * i);
+}
+__global__ void pair_filter_kernel(const float* __restrict__ p, const float* __restrict__ q,
+                                   unsigned char* __restrict__ fired, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        a[k] = p[8 * i + k];
+        b[k] = q[8 * i + k];
+    }
+    const NmsAux P = nms_aux_of(a), Q = nms_aux_of(b);
+    fired[i] = (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) ? 1 : 0;
+}
+int launch_pair_filter(const float* p, const float* q, unsigned char* fired, int n, cudaStream_t s) {
+    if (n <= 0) return 0;
+    pair_filter_kernel<<<(n + 127) / 128, 128, 0, s>>>(p, q, fired, n);
+    POST_CHECK_LAUNCH("pair_filter_kernel");
+    return 0;
 }
 int launch_poly_iou(const float* p, const float* q, float* iou, int n, cudaStream_t s) {
     if (n <= 0) return 0;
@@ -258,7 +164,8 @@ struct Layout {
     int max_sel, nblk;
     // byte offsets of the per-image arrays, each [N][...]
     size_t o_cand, o_cand_cnt, o_sel, o_sel_cnt, o_poly, o_nmsbox, o_score, o_ctr, o_cls, o_level, o_loc, o_hbox,
-        o_canon, o_mask, o_keep, o_nkeep, total;
+        o_canon, o_nms, o_keep, o_nkeep, total;
+    size_t nms_bytes;
 };
 
 static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
@@ -312,8 +219,9 @@ static Layout make_layout(int N, int L, const int* level_hw, int C, int topk) {
     o = a256(o + n * ms * 16);
     y.o_canon = o;
     o = a256(o + n * ms * 4);
-    y.o_mask = o;
-    o = a256(o + n * ms * y.nblk * 8);
+    y.o_nms = o;
+    y.nms_bytes = nms_scratch_bytes(N, y.max_sel);
+    o = a256(o + y.nms_bytes);
     y.o_keep = o;
     o = a256(o + n * ms * 4);
     y.o_nkeep = o;
@@ -604,85 +512,7 @@ __global__ void __launch_bounds__(1024) sort_decode_kernel(DecodeArgs a) {
     }
 }
 
-// ================================================================================================ K4: NMS mask + sweep
-// grid (col block, row block, image), 64 threads: thread t owns row box rb*64+t and tests it against the 64 column
-// boxes staged in shared memory; only the upper triangle is evaluated. Faithful mode: every pair that the serial
-// sweep may consult is evaluated with the full polygon arithmetic -- no bounding-box or class pre-reject, because in
-// fp32 with class-shifted coordinates even disjoint boxes can produce IoU > thr.
-__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ boxes, const int* __restrict__ counts,
-                                                      int max_sel, int nblk, float thr,
-                                                      unsigned long long* __restrict__ mask) {
-    const int cb = blockIdx.x, rb = blockIdx.y, n = blockIdx.z;
-    if (cb < rb) return;
-    const int m = counts[n];
-    if (rb * 64 >= m || cb * 64 >= m) return;
-    __shared__ float s_box[64 * 8];
-    const float* b = boxes + static_cast<size_t>(n) * max_sel * 8;
-    const int ncol = min(64, m - cb * 64);
-    for (int i = threadIdx.x; i < ncol * 8; i += 64) s_box[i] = b[static_cast<size_t>(cb) * 64 * 8 + i];
-    __syncthreads();
-    const int row = rb * 64 + threadIdx.x;
-    if (row >= m) return;
-    float rbx[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) rbx[k] = b[static_cast<size_t>(row) * 8 + k];
-    unsigned long long bits = 0;
-    const int start = (cb == rb) ? threadIdx.x + 1 : 0;
-    for (int j = start; j < ncol; ++j)
-        if (iou_poly_f32(rbx, s_box + 8 * j) > thr) bits |= 1ull << j;
-    mask[(static_cast<size_t>(n) * max_sel + row) * nblk + cb] = bits;
-}
-
-// one CTA per image: resolve 64 rows at a time from the diagonal words, then OR the survivors' rows into `removed`
-__global__ void __launch_bounds__(256) nms_sweep_kernel(const unsigned long long* __restrict__ mask,
-                                                        const int* __restrict__ counts, int max_sel, int nblk,
-                                                        int* __restrict__ keep, int* __restrict__ nkeep) {
-    extern __shared__ unsigned long long s_removed[];  // nblk words
-    __shared__ unsigned long long s_diag[64];
-    __shared__ unsigned long long s_alive;
-    __shared__ int s_nk;
-    const int n = blockIdx.x;
-    const int m = counts[n];
-    const unsigned long long* mk = mask + static_cast<size_t>(n) * max_sel * nblk;
-    int* kp = keep + static_cast<size_t>(n) * max_sel;
-    for (int i = threadIdx.x; i < nblk; i += blockDim.x) s_removed[i] = 0;
-    if (threadIdx.x == 0) s_nk = 0;
-    __syncthreads();
-    const int blocks = (m + 63) / 64;
-    for (int b = 0; b < blocks; ++b) {
-        const int rows = min(64, m - b * 64);
-        if (threadIdx.x < rows) s_diag[threadIdx.x] = mk[(static_cast<size_t>(b) * 64 + threadIdx.x) * nblk + b];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long rem = s_removed[b];
-            unsigned long long alive = 0;
-            int nk = s_nk;
-            for (int t = 0; t < rows; ++t) {
-                if (!((rem >> t) & 1ull)) {
-                    alive |= 1ull << t;
-                    kp[nk++] = b * 64 + t;
-                    rem |= s_diag[t];
-                }
-            }
-            s_nk = nk;
-            s_alive = alive;
-        }
-        __syncthreads();
-        const unsigned long long alive = s_alive;
-        for (int w = b + 1 + threadIdx.x; w < blocks; w += blockDim.x) {
-            unsigned long long acc = 0;
-            unsigned long long am = alive;
-            while (am) {
-                const int t = __ffsll(static_cast<long long>(am)) - 1;
-                am &= am - 1;
-                acc |= mk[(static_cast<size_t>(b) * 64 + t) * nblk + w];
-            }
-            s_removed[w] |= acc;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) nkeep[n] = s_nk;
-}
+// K4: lazily evaluated NMS -> nms.cu (run_nms)
 
 // ================================================================================================ K5: top-k cut, rescale, clip, pack
 struct FinalArgs {
@@ -793,17 +623,6 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
 }
 
 // ================================================================================================ host orchestration
-static int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, int nblk, float thr,
-                   unsigned long long* mask, int* keep, int* nkeep, cudaStream_t s, int64_t* launches) {
-    dim3 grid(nblk, nblk, N);
-    nms_mask_kernel<<<grid, 64, 0, s>>>(nmsbox, counts, max_sel, nblk, thr, mask);
-    POST_CHECK_LAUNCH("nms_mask_kernel");
-    nms_sweep_kernel<<<N, 256, nblk * sizeof(unsigned long long), s>>>(mask, counts, max_sel, nblk, keep, nkeep);
-    POST_CHECK_LAUNCH("nms_sweep_kernel");
-    if (launches) *launches += 2;
-    return 0;
-}
-
 int launch_postprocess(const PostParams& p, cudaStream_t s, int64_t* launches) {
     int level_hw[10];
     for (int l = 0; l < p.L; ++l) {
@@ -881,7 +700,7 @@ int launch_postprocess(const PostParams& p, cudaStream_t s, int64_t* launches) {
     float* loc = reinterpret_cast<float*>(base + y.o_loc);
     float* hbox = reinterpret_cast<float*>(base + y.o_hbox);
     unsigned* canon = reinterpret_cast<unsigned*>(base + y.o_canon);
-    auto* mask = reinterpret_cast<unsigned long long*>(base + y.o_mask);
+    void* nms_scratch = base + y.o_nms;
     int* keep = reinterpret_cast<int*>(base + y.o_keep);
     int* nkeep = reinterpret_cast<int*>(base + y.o_nkeep);
     {
@@ -923,7 +742,8 @@ int launch_postprocess(const PostParams& p, cudaStream_t s, int64_t* launches) {
         if (launches) *launches += 1;
     }
     if (p.nms_thresh > 0.f) {
-        if (run_nms(nmsbox, sel_cnt, p.N, y.max_sel, y.nblk, p.nms_thresh, mask, keep, nkeep, s, launches)) return -1;
+        if (run_nms(nmsbox, sel_cnt, p.N, y.max_sel, p.nms_thresh, nms_scratch, y.nms_bytes, keep, nkeep, s, launches))
+            return -1;
     } else {
         set_error("postprocess: nms_thresh <= 0 (NMS disabled) is not supported by the fused path");
         return -1;
@@ -950,6 +770,24 @@ int launch_postprocess(const PostParams& p, cudaStream_t s, int64_t* launches) {
         finalize_kernel<<<p.N, 256, 0, s>>>(a);
         POST_CHECK_LAUNCH("finalize_kernel");
         if (launches) *launches += 1;
+    }
+    return 0;
+}
+
+int postprocess_debug_counts(const void* scratch, int N, int L, const int* level_hw, int num_classes, int pre_nms_topk,
+                             int32_t* host_out, cudaStream_t s) {
+    const Layout y = make_layout(N, L, level_hw, num_classes, pre_nms_topk);
+    const uint8_t* base = static_cast<const uint8_t*>(scratch);
+    cudaError_t e = cudaStreamSynchronize(s);
+    for (int n = 0; n < N && e == cudaSuccess; ++n) {
+        e = cudaMemcpy(host_out + 8 * n, base + y.o_cand_cnt + static_cast<size_t>(n) * 32, 5 * 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(host_out + 8 * n + 5, base + y.o_sel_cnt + static_cast<size_t>(n) * 4, 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(host_out + 8 * n + 6, base + y.o_nkeep + static_cast<size_t>(n) * 4, 4, cudaMemcpyDeviceToHost);
+        host_out[8 * n + 7] = y.max_sel;
+    }
+    if (e != cudaSuccess) {
+        set_error("postprocess_debug_counts: %s", cudaGetErrorString(e));
+        return -1;
     }
     return 0;
 }
@@ -1014,8 +852,8 @@ __global__ void nms_gather_kernel(const int* __restrict__ order, const int* __re
 }
 
 size_t poly_nms_scratch_bytes(int n) {
-    const size_t ms = n < 1 ? 1 : n, nblk = (ms + 63) / 64;
-    return a256(ms * 32) + a256(ms * 4) + a256(4) + a256(ms * nblk * 8) + a256(ms * 4) + a256(4);
+    const size_t ms = n < 1 ? 1 : n;
+    return a256(ms * 32) + a256(ms * 4) + a256(4) + a256(nms_scratch_bytes(1, static_cast<int>(ms))) + a256(ms * 4) + a256(4);
 }
 
 int launch_poly_nms(const float* polys, const float* scores, const int32_t* classes, int n, float thresh,
@@ -1042,7 +880,7 @@ int launch_poly_nms(const float* polys, const float* scores, const int32_t* clas
         set_error("poly_nms: scratch of %zu bytes is too small, need %zu", scratch_bytes, poly_nms_scratch_bytes(n));
         return -1;
     }
-    const size_t ms = n, nblk = (ms + 63) / 64;
+    const size_t ms = n;
     uint8_t* b = static_cast<uint8_t*>(scratch);
     float* nmsbox = reinterpret_cast<float*>(b);
     b += a256(ms * 32);
@@ -1050,8 +888,9 @@ int launch_poly_nms(const float* polys, const float* scores, const int32_t* clas
     b += a256(ms * 4);
     int* count = reinterpret_cast<int*>(b);
     b += a256(4);
-    auto* mask = reinterpret_cast<unsigned long long*>(b);
-    b += a256(ms * nblk * 8);
+    void* nms_scratch = b;
+    const size_t nms_bytes = nms_scratch_bytes(1, n);
+    b += a256(nms_bytes);
     int* keep_pos = reinterpret_cast<int*>(b);
     b += a256(ms * 4);
     int* nk = reinterpret_cast<int*>(b);
@@ -1070,7 +909,7 @@ int launch_poly_nms(const float* polys, const float* scores, const int32_t* clas
     }
     nms_prepare_kernel<<<1, 1024, smem, s>>>(polys, scores, classes, n, vehicle_merge, nmsbox, order, count);
     POST_CHECK_LAUNCH("nms_prepare_kernel");
-    if (run_nms(nmsbox, count, 1, n, static_cast<int>(nblk), thresh, mask, keep_pos, nk, s, nullptr)) return -1;
+    if (run_nms(nmsbox, count, 1, n, thresh, nms_scratch, nms_bytes, keep_pos, nk, s, nullptr)) return -1;
     nms_gather_kernel<<<8, 256, 0, s>>>(order, keep_pos, nk, keep_out, nkeep_out);
     POST_CHECK_LAUNCH("nms_gather_kernel");
     return 0;

@@ -36,8 +36,21 @@ struct PostParams {
 size_t postprocess_scratch_bytes(int N, int L, const int* level_hw, int num_classes, int pre_nms_topk);
 int launch_postprocess(const PostParams& p, cudaStream_t stream, int64_t* launches);
 
+// Synchronous diagnostic: per image 8 ints = candidates above threshold per level (5), boxes entering NMS, boxes kept
+// by NMS (before the post-NMS top-k), capacity of the per-image lists.
+int postprocess_debug_counts(const void* scratch, int N, int L, const int* level_hw, int num_classes, int pre_nms_topk,
+                             int32_t* host_out, cudaStream_t stream);
+
 int launch_sort_quadrilateral(const float* quads, float* out, int n, cudaStream_t stream);
 int launch_poly_iou(const float* p, const float* q, float* iou, int n, cudaStream_t stream);
+// fired[i] = 1 where the NMS pre-filter claims IoU(p[i], q[i]) == 0 without running the clip (test hook).
+int launch_pair_filter(const float* p, const float* q, unsigned char* fired, int n, cudaStream_t stream);
+
+// Lazily evaluated greedy polygon NMS of N images (nms.cu). nmsbox [N][max_sel][8] sorted by descending score with the
+// class offsets applied, counts [N]; writes keep [N][max_sel] (kept positions, ascending) and nkeep [N].
+size_t nms_scratch_bytes(int N, int max_sel);
+int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float thr, void* scratch, size_t scratch_bytes,
+            int* keep, int* nkeep, cudaStream_t stream, int64_t* launches);
 
 size_t poly_nms_scratch_bytes(int n);
 int launch_poly_nms(const float* polys, const float* scores, const int32_t* classes, int n, float thresh,

@@ -221,6 +221,15 @@ class DafneEngine:
             for o in arr
         ]
 
+    def post_counts(self) -> List[dict]:
+        """Diagnostic of the last post-processing (synchronises): per image the candidates per level, boxes entering
+        NMS and boxes kept by NMS before the post-NMS top-k."""
+        N = self._shape[0]
+        arr = (C.c_int32 * (8 * N))()
+        _capi.check(self.lib.dafne_debug_post_counts(self._ctx, arr, _capi.stream_ptr()), "dafne_debug_post_counts")
+        return [dict(candidates=list(arr[8 * n:8 * n + 5]), nms_in=arr[8 * n + 5], nms_kept=arr[8 * n + 6],
+                     capacity=arr[8 * n + 7]) for n in range(N)]
+
     def stats(self, reset: bool = False) -> Tuple[int, float]:
         launches, flops = C.c_int64(), C.c_double()
         _capi.check(self.lib.dafne_stats(self._ctx, C.byref(launches), C.byref(flops), int(reset)), "dafne_stats")

@@ -125,6 +125,10 @@ int dafne_detect_host(dafne_ctx* ctx, const void* host_images, int dtype, const 
 int dafne_debug_keep_activations(dafne_ctx* ctx, int keep);
 int dafne_debug_activation(dafne_ctx* ctx, const char* name, const void** dev_ptr, int* N, int* H, int* W, int* C);
 
+/* Diagnostic of the last dafne_postprocess / dafne_detect (synchronises the stream): host_out[N][8] = candidates above
+ * the score threshold per level (5), boxes entering NMS, boxes kept by NMS before the post-NMS top-k, list capacity. */
+int dafne_debug_post_counts(dafne_ctx* ctx, int32_t* host_out, void* stream);
+
 /* Per-launch timing of the dense forward with CUDA events on the launching stream (bench.py's roofline numbers).
  * dafne_set_profiling(ctx, 1) makes every following dafne_forward_dense record an event after each launch;
  * dafne_get_profile (after the stream has been synchronised) returns, for launch i < *count: its duration in ms,
@@ -144,15 +148,18 @@ int dafne_stats(dafne_ctx* ctx, int64_t* kernel_launches, double* conv_flops, in
 
 /* ------------------------------------------------------------------ per-kernel hooks (tests, A/B) */
 /* One convolution through the tcgen05 kernel. NHWC fp16 in/out, weights [Cout][k*k][Cin] fp16.
- * Exactly one of out_f16 / out_f32 is non-NULL (out_f32: Cout <= 32, row pitch out_ld). */
+ * Exactly one of out_f16 / out_f32 is non-NULL (out_f32: Cout <= 32, row pitch out_ld).
+ * dev_gn_sums (optional): [N][Cout/8][2] int64 fixed point, ACCUMULATED (zero it first): sum * 2^20 and sum of squares
+ * * 2^12 of the fp16-rounded outputs per image and group of 8 channels. Integer accumulation makes GroupNorm
+ * statistics bit-reproducible and independent of tiling and batch composition. */
 int dafne_conv_nhwc(const void* dev_in_f16, int N, int H, int W, int Cin, const void* dev_w_f16, int Cout, int ksize,
                     int stride, const float* dev_scale, const float* dev_shift, int relu,
-                    const void* dev_residual_f16, int res_H, int res_W, int res_shift, float* dev_gn_sums,
+                    const void* dev_residual_f16, int res_H, int res_W, int res_shift, int64_t* dev_gn_sums,
                     void* dev_out_f16, float* dev_out_f32, int out_ld, void* stream);
 
 /* GroupNorm apply + ReLU on NHWC fp16 from per-(image, group) sums produced by dafne_conv_nhwc. */
 int dafne_gn_relu_nhwc(const void* dev_in_f16, void* dev_out_f16, int N, int HW, int C, int groups,
-                       const float* dev_gn_sums, const float* dev_gamma, const float* dev_beta, float eps,
+                       const int64_t* dev_gn_sums, const float* dev_gamma, const float* dev_beta, float eps,
                        void* stream);
 
 /* sort_quadrilateral on device: quads [n,8] fp32 -> out [n,8] fp32 (sort_corners.py:26-92). */
@@ -160,6 +167,11 @@ int dafne_sort_quadrilateral(const float* dev_quads, float* dev_out, int n, void
 
 /* Pairwise polygon IoU on device in the faithful fp32 arithmetic: iou[i] = IoU(p[i], q[i]). */
 int dafne_poly_iou(const float* dev_p, const float* dev_q, float* dev_iou, int n, void* stream);
+
+/* Test hook for the NMS pre-filter: fired[i] = 1 where the library skips the polygon clip of the pair (p[i] = the
+ * higher-scored box, q[i] = the lower-scored one) because it can prove the faithful fp32 arithmetic yields IoU == 0.
+ * Contract (tests/test_postprocess_gpu.py): fired[i] implies dafne_poly_iou gives exactly 0 for that pair. */
+int dafne_poly_pair_filter(const float* dev_p, const float* dev_q, uint8_t* dev_fired, int n, void* stream);
 
 /* Class-aware polygon NMS of one image (ml_nms -> batched_nms_poly -> poly_gpu_nms semantics): polys [n,8], scores
  * [n], classes [n] int32, all on device. dev_keep receives the kept input indices in descending score order
