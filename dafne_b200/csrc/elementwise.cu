@@ -18,19 +18,22 @@ namespace dafne {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------ preprocess
+// Output canvas: fp16 [N][H+6][W+8][4] with the image at row 3 / pixel 4 and zeros around it (stem_tc.cu reads
+// 64-byte runs of it through TMA); every canvas position is written on every call.
 template <typename T>
 __global__ void preprocess_kernel(const T* __restrict__ img, const int32_t* __restrict__ sizes, int N, int H, int W,
                                   float m0, float m1, float m2, float s0, float s1, float s2,
                                   __half* __restrict__ out) {
-    const size_t total = static_cast<size_t>(N) * H * W;
+    const int PW = W + 8, PH = H + 6;
+    const size_t total = static_cast<size_t>(N) * PH * PW;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int x = i % W;
-        const int y = (i / W) % H;
-        const int n = i / (static_cast<size_t>(W) * H);
+        const int x = static_cast<int>(i % PW) - 4;
+        const int y = static_cast<int>((i / PW) % PH) - 3;
+        const int n = i / (static_cast<size_t>(PW) * PH);
         const int h = sizes[4 * n], w = sizes[4 * n + 1];  // rows of [h, w, out_h, out_w]
         float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-        if (y < h && x < w) {
+        if (y >= 0 && x >= 0 && y < h && x < w) {
             const size_t plane = static_cast<size_t>(H) * W;
             const size_t base = static_cast<size_t>(n) * 3 * plane + static_cast<size_t>(y) * W + x;
             v0 = (static_cast<float>(img[base]) - m0) / s0;
@@ -48,7 +51,7 @@ __global__ void preprocess_kernel(const T* __restrict__ img, const int32_t* __re
 
 int launch_preprocess(const void* images, int dtype, const int32_t* sizes_dev, int N, int H, int W, const float* mean3,
                       const float* std3, __half* out, cudaStream_t s) {
-    const size_t total = static_cast<size_t>(N) * H * W;
+    const size_t total = static_cast<size_t>(N) * (H + 6) * (W + 8);
     const int threads = 256;
     const int blocks = static_cast<int>((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads
                                                                                    : 148 * 16);
@@ -65,95 +68,6 @@ int launch_preprocess(const void* images, int dtype, const int32_t* sizes_dev, i
         return -1;
     }
     DAFNE_CHECK_LAUNCH("preprocess_kernel");
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------ stem
-// One block = 16x16 output pixels of one image, all 64 output channels; one thread = one pixel.
-constexpr int STEM_T = 16;
-constexpr int STEM_P = 2 * STEM_T + 5;  // input patch edge (37)
-constexpr int STEM_SMEM = 49 * 4 * 64 * 4 + STEM_P * STEM_P * 8;
-
-__global__ void __launch_bounds__(256) stem_kernel(const __half* __restrict__ in, int N, int H, int W,
-                                                   const float* __restrict__ wp, const float* __restrict__ scale,
-                                                   const float* __restrict__ shift, __half* __restrict__ out) {
-    extern __shared__ __align__(16) uint8_t sm[];
-    float4* s_w = reinterpret_cast<float4*>(sm);                       // [49*4][16] float4
-    uint2* s_in = reinterpret_cast<uint2*>(sm + 49 * 4 * 64 * 4);      // [37][37] x 4 halves
-    const int Ho = H / 2, Wo = W / 2;
-    const int n = blockIdx.z;
-    const int oy0 = blockIdx.y * STEM_T, ox0 = blockIdx.x * STEM_T;
-    for (int i = threadIdx.x; i < 49 * 4 * 16; i += 256) s_w[i] = reinterpret_cast<const float4*>(wp)[i];
-    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
-    for (int i = threadIdx.x; i < STEM_P * STEM_P; i += 256) {
-        const int py = i / STEM_P, px = i % STEM_P;
-        const int iy = iy0 + py, ix = ix0 + px;
-        uint2 v = make_uint2(0, 0);
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-            v = reinterpret_cast<const uint2*>(in)[(static_cast<size_t>(n) * H + iy) * W + ix];
-        s_in[i] = v;
-    }
-    __syncthreads();
-    const int ty = threadIdx.x / STEM_T, tx = threadIdx.x % STEM_T;
-    float acc[64];
-#pragma unroll
-    for (int c = 0; c < 64; ++c) acc[c] = 0.f;
-#pragma unroll 1
-    for (int ky = 0; ky < 7; ++ky) {
-#pragma unroll 1
-        for (int kx = 0; kx < 7; ++kx) {
-            const uint2 pv = s_in[(2 * ty + ky) * STEM_P + 2 * tx + kx];
-            const float2 p01 = __half22float2(*reinterpret_cast<const __half2*>(&pv.x));
-            const float2 p23 = __half22float2(*reinterpret_cast<const __half2*>(&pv.y));
-            const float pin[3] = {p01.x, p01.y, p23.x};
-            const float4* wt = s_w + (ky * 7 + kx) * 4 * 16;
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const float4 w4 = wt[ci * 16 + q];
-                    acc[4 * q] = fmaf(pin[ci], w4.x, acc[4 * q]);
-                    acc[4 * q + 1] = fmaf(pin[ci], w4.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(pin[ci], w4.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(pin[ci], w4.w, acc[4 * q + 3]);
-                }
-            }
-        }
-    }
-    const int oy = oy0 + ty, ox = ox0 + tx;
-    if (oy < Ho && ox < Wo) {
-        uint4* op = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * 64);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = q * 8 + 2 * j;
-                const float a0 = fmaxf(fmaf(acc[c], __ldg(scale + c), __ldg(shift + c)), 0.f);
-                const float a1 = fmaxf(fmaf(acc[c + 1], __ldg(scale + c + 1), __ldg(shift + c + 1)), 0.f);
-                const __half2 h = __floats2half2_rn(a0, a1);
-                pk[j] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            op[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
-    }
-}
-
-int launch_stem(const __half* in, int N, int H, int W, const float* wp, const float* scale, const float* shift,
-                __half* out, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
-        if (e != cudaSuccess) {
-            set_error("stem_kernel smem attribute: %s", cudaGetErrorString(e));
-            return -1;
-        }
-        configured = true;
-    }
-    const int Ho = H / 2, Wo = W / 2;
-    dim3 grid((Wo + STEM_T - 1) / STEM_T, (Ho + STEM_T - 1) / STEM_T, N);
-    stem_kernel<<<grid, 256, STEM_SMEM, s>>>(in, N, H, W, wp, scale, shift, out);
-    DAFNE_CHECK_LAUNCH("stem_kernel");
     return 0;
 }
 
@@ -304,18 +218,6 @@ int launch_pack_conv_weight(const float* w, int Cout, int Cin, int k, __half* ou
     if (blocks > 4096) blocks = 4096;
     pack_conv_weight_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(w, Cout, Cin, k, out);
     DAFNE_CHECK_LAUNCH("pack_conv_weight_kernel");
-    return 0;
-}
-
-__global__ void pack_stem_weight_kernel(const float* __restrict__ w, float* __restrict__ o) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [49][4][64]
-    if (i >= 49 * 4 * 64) return;
-    const int co = i % 64, ci = (i / 64) % 4, tap = i / 256;
-    o[i] = ci < 3 ? w[(co * 3 + ci) * 49 + tap] : 0.f;
-}
-int launch_pack_stem_weight(const float* w, float* out, cudaStream_t s) {
-    pack_stem_weight_kernel<<<(49 * 4 * 64 + 255) / 256, 256, 0, s>>>(w, out);
-    DAFNE_CHECK_LAUNCH("pack_stem_weight_kernel");
     return 0;
 }
 

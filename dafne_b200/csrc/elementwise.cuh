@@ -6,14 +6,11 @@
 
 namespace dafne {
 
-// NCHW uint8 / fp32 image batch -> (x - mean) / std, zero outside each image's (h, w), fp16 NHWC with 4 channels
-// (channel 3 = 0). sizes_dev: N rows of (h, w, out_h, out_w) int32 on the device.
+// NCHW uint8 / fp32 image batch -> (x - mean) / std, zero outside each image's (h, w), written as fp16 NHWC4
+// (channel 3 = 0) onto the zero canvas [N][H+6][W+8][4] the tensor-core stem reads (image at row 3, pixel 4).
+// sizes_dev: N rows of (h, w, out_h, out_w) int32 on the device.
 int launch_preprocess(const void* images, int dtype, const int32_t* sizes_dev, int N, int H, int W, const float* mean3,
-                      const float* std3, __half* out_nhwc4, cudaStream_t s);
-
-// Stem: 7x7 stride-2 pad-3 conv 3->64 + folded FrozenBN + ReLU. in NHWC4 fp16, w [49][4][64] fp32, out NHWC fp16.
-int launch_stem(const __half* in_nhwc4, int N, int H, int W, const float* w_packed, const float* scale,
-                const float* shift, __half* out, cudaStream_t s);
+                      const float* std3, __half* out_canvas, cudaStream_t s);
 
 // 3x3 stride-2 pad-1 max pool, NHWC fp16, C % 8 == 0.
 int launch_maxpool3x3s2(const __half* in, int N, int H, int W, int C, __half* out, cudaStream_t s);
@@ -28,8 +25,6 @@ int launch_relu_copy(const __half* in, __half* out, size_t n8, cudaStream_t s);
 
 // fp32 [Cout, Cin, k, k] -> fp16 [Cout][k*k][Cin]
 int launch_pack_conv_weight(const float* w, int Cout, int Cin, int k, __half* out, cudaStream_t s);
-// fp32 [64, 3, 7, 7] -> fp32 [49][4][64] (channel 3 = 0)
-int launch_pack_stem_weight(const float* w, float* out, cudaStream_t s);
 // FrozenBN fold: scale = gamma * rsqrt(var + eps), shift = beta - mean * scale
 int launch_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int C,
                    float* scale, float* shift, cudaStream_t s);

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "elementwise.cuh"
+#include "stem_tc.cuh"
 
 namespace dafne {
 
@@ -235,13 +236,13 @@ int ctx_finalize(dafne_ctx* c, cudaStream_t s) {
         }
     const float bn_eps = 1e-5f;  // detectron2 FrozenBatchNorm2d default
     if (!c->stem_w) {
-        CUDA_OK(cudaMalloc(&c->stem_w, 49 * 4 * 64 * sizeof(float)));
+        CUDA_OK(cudaMalloc(&c->stem_w, 64 * 224 * sizeof(__half)));
         CUDA_OK(cudaMalloc(&c->stem_scale, 64 * sizeof(float)));
         CUDA_OK(cudaMalloc(&c->stem_shift, 64 * sizeof(float)));
         CUDA_OK(cudaMalloc(&c->scales_dev, 8 * sizeof(float)));
     }
     const std::string st = kBU + "stem.conv1";
-    if (launch_pack_stem_weight(raw_of(c, st + ".weight"), c->stem_w, s)) return -1;
+    if (launch_pack_stem_weight_tc(raw_of(c, st + ".weight"), c->stem_w, s)) return -1;
     if (launch_fold_bn(raw_of(c, st + ".norm.weight"), raw_of(c, st + ".norm.bias"),
                        raw_of(c, st + ".norm.running_mean"), raw_of(c, st + ".norm.running_var"), bn_eps, 64,
                        c->stem_scale, c->stem_shift, s))
@@ -409,7 +410,7 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
         c->ops.clear();
         c->named.clear();
         c->op_info.clear();
-        B.info("preprocess", 0, 0, (double)N * H * W * (3 + 8));
+        B.info("preprocess", 0, 0, (double)N * H * W * 3 + (double)N * (H + 6) * (W + 8) * 8);
     }
     const dafne_model_spec& sp = c->spec;
 
@@ -451,21 +452,26 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     float* dets_dev = B.persistent<float>(static_cast<size_t>(N) * det_cap * DAFNE_DET_STRIDE * sizeof(float));
     int32_t* counts_dev = B.persistent<int32_t>(static_cast<size_t>(N) * sizeof(int32_t));
 
-    // ---- stem
-    Act x0 = B.new_act(N, H, W, 4);
+    // ---- stem (tensor cores; the preprocess kernel writes the zero-bordered NHWC4 canvas it reads)
+    Act x0;
+    x0.N = N;
+    x0.H = H + 6;
+    x0.W = W + 8;
+    x0.C = 4;
+    x0.bytes = static_cast<size_t>(N) * (H + 6) * (W + 8) * 4 * sizeof(__half);
+    x0.off = B.arena.alloc(x0.bytes);
+    x0.p = base ? reinterpret_cast<__half*>(base + x0.off) : nullptr;
     __half* x0p_saved = x0.p;
     Act s1 = B.new_act(N, H / 2, W / 2, 64);
     B.launches += 2;
     B.flops += 2.0 * N * (H / 2) * (W / 2) * 64.0 * 49 * 3;
     if (base) {
         // op 0 (preprocess) is issued by ctx_forward because it takes the per-call image pointer
-        __half* x0p = x0.p;
-        __half* s1p = s1.p;
-        const float* sw = c->stem_w;
-        const float* ssc = c->stem_scale;
-        const float* ssh = c->stem_shift;
-        c->ops.push_back([=](cudaStream_t s) { return launch_stem(x0p, N, H, W, sw, ssc, ssh, s1p, s); });
-        B.info("stem", 0, 2.0 * N * (H / 2) * (W / 2) * 64.0 * 147, (double)N * H * W * 8 + (double)N * (H / 2) * (W / 2) * 128);
+        StemPlan sp_;
+        if (stem_plan_build(x0.p, N, H, W, c->stem_w, c->stem_scale, c->stem_shift, s1.p, &sp_, c->num_sms)) return -1;
+        c->ops.push_back([sp_](cudaStream_t s) { return stem_plan_launch(sp_, s); });
+        B.info("stem", 2, 2.0 * N * (H / 2) * (W / 2) * 64.0 * 147,
+               (double)x0.bytes + (double)N * (H / 2) * (W / 2) * 128);
     }
     Act x = B.new_act(N, H / 4, W / 4, 64);
     B.launches += 1;

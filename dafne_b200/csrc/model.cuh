@@ -75,7 +75,7 @@ struct dafne_ctx {
     // layers
     std::vector<dafne::ConvLayer> convs;
     std::unordered_map<std::string, int> conv_index;  // first part prefix -> index in convs
-    float* stem_w = nullptr;                          // [49][4][64] fp32
+    __half* stem_w = nullptr;                         // [64][7 ky][8 px][4 ch] fp16 (stem_tc.cu)
     float* stem_scale = nullptr;
     float* stem_shift = nullptr;
     float* scales_dev = nullptr;  // [L]
@@ -83,7 +83,7 @@ struct dafne_ctx {
     // plan (valid after bind)
     int N = 0, H = 0, W = 0;
     uint8_t* ws = nullptr;
-    __half* x0 = nullptr;  // preprocess output (NHWC4 fp16)
+    __half* x0 = nullptr;  // preprocess output: zero-bordered NHWC4 fp16 canvas [N][H+6][W+8][4]
     size_t ws_bytes = 0;
     std::vector<std::function<int(cudaStream_t)>> ops;
     std::vector<dafne::OpInfo> op_info;  // parallel to ops (+ entry 0 = preprocess)

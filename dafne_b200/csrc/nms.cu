@@ -24,6 +24,7 @@ constexpr int kPanelWords = kPanel / 64;  // 8
 constexpr int kDiagBlocks = kPanelWords * (kPanelWords + 1) / 2;  // 36 (rb <= cb)
 constexpr int kRowChunk = 32;   // kept rows per bcast CTA
 constexpr int kColChunk = 128;  // columns per bcast CTA
+constexpr int kBcastThreads = 256;
 
 typedef unsigned long long u64;
 
@@ -65,7 +66,49 @@ __global__ void nms_aux_kernel(const float* __restrict__ boxes, const int* __res
     aux[r] = nms_aux_of(b);
 }
 
+// Boxes are staged in shared memory already (re)oriented like iou_poly_f32 does (polyiou.cpp:95-96), once per box.
+__device__ __forceinline__ void stage_oriented(const float* __restrict__ src, float* dst) {
+    float b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b[k] = src[k];
+    P2 p[6];
+    load_oriented(b, p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        dst[2 * k] = p[k].x;
+        dst[2 * k + 1] = p[k].y;
+    }
+}
+
+// One queued pair is evaluated by 16 consecutive lanes, lane k = 4*i + j computing the signed overlap of edge
+// triangle i of P with edge triangle j of Q; the group leader then adds the 16 terms in the reference's order
+// (i outer, j inner) and finishes the IoU with the algorithm's own a1, a2. Returns IoU > thr on the leader lane.
+__device__ __forceinline__ bool pair_suppresses_16(const float* P, const float* Q, float a1, float a2, float thr,
+                                                   bool active, unsigned lane) {
+    float val = 0.f;
+    if (active) {
+        const int i = (lane >> 2) & 3, j = lane & 3;
+        P2 a, b, c, d;
+        a.x = P[2 * i];
+        a.y = P[2 * i + 1];
+        b.x = P[2 * ((i + 1) & 3)];
+        b.y = P[2 * ((i + 1) & 3) + 1];
+        c.x = Q[2 * j];
+        c.y = Q[2 * j + 1];
+        d.x = Q[2 * ((j + 1) & 3)];
+        d.y = Q[2 * ((j + 1) & 3) + 1];
+        val = tri_overlap(a, b, c, d);
+    }
+    float inter = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) inter += __shfl_sync(0xffffffffu, val, (lane & 16) + k);
+    const float uni = a1 + a2 - inter;
+    const float iou = (uni == 0.f) ? (inter + 1.f) / (uni + 1.f) : inter / uni;
+    return active && iou > thr;
+}
+
 // ------------------------------------------------------------------------------------------------ diagonal panel
+constexpr int kDiagThreads = 256;
 struct DiagSmem {
     float rbox[64][8];
     float cbox[64][8];
@@ -77,8 +120,8 @@ struct DiagSmem {
     int last;
 };
 
-// grid (36, N), 64 threads. Block b -> (rb, cb), rb <= cb, both 64-box blocks of panel `panel`.
-__global__ void __launch_bounds__(64) nms_diag_kernel(const float* __restrict__ boxes, const NmsAux* __restrict__ aux,
+// grid (36, N), 256 threads. Block b -> (rb, cb), rb <= cb, both 64-box blocks of panel `panel`.
+__global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __restrict__ boxes, const NmsAux* __restrict__ aux,
                                                       const int* __restrict__ counts, int max_sel, int nblk,
                                                       int panel, float thr, u64* __restrict__ removed,
                                                       u64* __restrict__ diag, u64* __restrict__ pk,
@@ -104,42 +147,49 @@ __global__ void __launch_bounds__(64) nms_diag_kernel(const float* __restrict__ 
     if (r0 < m && c0 < m) {
         const u64 rdead = rmv[r0 >> 6], cdead = rmv[c0 >> 6];
         const int row = r0 + t, col = c0 + t;
-        if (row < m) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) sm.rbox[t][k] = boxes[(ibase + row) * 8 + k];
-            sm.raux[t] = aux[ibase + row];
+        if (t < 64) {
+            if (row < m) {
+                stage_oriented(boxes + (ibase + row) * 8, sm.rbox[t]);
+                sm.raux[t] = aux[ibase + row];
+            }
+            if (col < m) {
+                stage_oriented(boxes + (ibase + col) * 8, sm.cbox[t]);
+                sm.caux[t] = aux[ibase + col];
+            }
+            sm.bits[t] = 0;
         }
-        if (col < m) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) sm.cbox[t][k] = boxes[(ibase + col) * 8 + k];
-            sm.caux[t] = aux[ibase + col];
-        }
-        sm.bits[t] = 0;
         if (t == 0) sm.qn = 0;
         __syncthreads();
         const int ncol = min(64, m - c0);
-        // phase 1: thread = row; pre-filter against the alive columns, queue the pairs that need the full clip
-        if (row < m && !((rdead >> t) & 1ull)) {
-            const NmsAux P = sm.raux[t];
-            for (int j = (cb == rb) ? t + 1 : 0; j < ncol; ++j) {
-                if ((cdead >> j) & 1ull) continue;
-                const NmsAux& Q = sm.caux[j];
-                if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) continue;
-                const int pos = atomicAdd(&sm.qn, 1);
-                sm.queue[pos] = static_cast<unsigned short>((t << 6) | j);
+        // phase 1: 4 threads per row, 16 columns each; pre-filter against the alive columns, queue what needs the clip
+        {
+            const int r = t >> 2, jq = (t & 3) * 16;
+            if (r0 + r < m && !((rdead >> r) & 1ull)) {
+                const NmsAux P = sm.raux[r];
+                for (int j = max(jq, (cb == rb) ? r + 1 : 0); j < min(jq + 16, ncol); ++j) {
+                    if ((cdead >> j) & 1ull) continue;
+                    const NmsAux& Q = sm.caux[j];
+                    if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) continue;
+                    const int pos = atomicAdd(&sm.qn, 1);
+                    sm.queue[pos] = static_cast<unsigned short>((r << 6) | j);
+                }
             }
         }
         __syncthreads();
-        // phase 2: all lanes busy on the queued pairs
+        // phase 2: 16 lanes per queued pair
         const int qn = sm.qn;
-        for (int e = t; e < qn; e += 64) {
-            const int r = sm.queue[e] >> 6, j = sm.queue[e] & 63;
-            if (iou_poly_f32(sm.rbox[r], sm.cbox[j]) > thr) atomicOr(&sm.bits[r], 1ull << j);
+        const unsigned lane = t & 31;
+        for (int e0 = 0; e0 < qn; e0 += kDiagThreads / 16) {
+            const int e = e0 + (t >> 4);
+            const bool active = e < qn;
+            const int r = active ? sm.queue[e] >> 6 : 0, j = active ? sm.queue[e] & 63 : 0;
+            const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active, lane);
+            if (hit && (lane & 15) == 0) atomicOr(&sm.bits[r], 1ull << j);
         }
         __syncthreads();
-        bits_out = sm.bits[t];
+        if (t < 64) bits_out = sm.bits[t];
     }
-    diag[(static_cast<size_t>(n) * kPanel + rb * 64 + t) * kPanelWords + cb] = bits_out;
+    if (t < 64)     diag[(static_cast<size_t>(n) * kPanel + rb * 64 + t) * kPanelWords + cb] = bits_out;
     __threadfence();
     __syncthreads();
     if (t == 0) sm.last = (atomicAdd(&ctr[n], 1) == kDiagBlocks - 1);
@@ -160,7 +210,7 @@ __global__ void __launch_bounds__(64) nms_diag_kernel(const float* __restrict__ 
     for (int b = 0; b * 64 < rows_in_panel; ++b) {
         const int rows = min(64, rows_in_panel - b * 64);
         // the diagonal word of each row of this block, staged so one thread can walk them back to back
-        sm.bits[t] = t < rows ? __ldcg(dg + (static_cast<size_t>(b) * 64 + t) * kPanelWords + b) : 0ull;
+        if (t < 64) sm.bits[t] = t < rows ? __ldcg(dg + (static_cast<size_t>(b) * 64 + t) * kPanelWords + b) : 0ull;
         __syncthreads();
         if (t == 0) {
             u64 cur = s_rem[b], alive = 0;
@@ -176,7 +226,7 @@ __global__ void __launch_bounds__(64) nms_diag_kernel(const float* __restrict__ 
         }
         __syncthreads();
         // survivors of this block suppress later blocks of the panel
-        if ((s_kept[b] >> t) & 1ull) {
+        if (t < 64 && ((s_kept[b] >> t) & 1ull)) {
             for (int w = b + 1; w < kPanelWords; ++w) {
                 const u64 v = __ldcg(dg + (static_cast<size_t>(b) * 64 + t) * kPanelWords + w);
                 if (v) atomicOr(&s_rem[w], v);
@@ -188,7 +238,7 @@ __global__ void __launch_bounds__(64) nms_diag_kernel(const float* __restrict__ 
     int nk = nkeep[n];
     for (int w = 0; w < kPanelWords; ++w) {
         const u64 kw = s_kept[w];
-        if ((kw >> t) & 1ull) keep[ibase + nk + __popcll(kw & ((1ull << t) - 1ull))] = base + w * 64 + t;
+        if (t < 64 && ((kw >> t) & 1ull)) keep[ibase + nk + __popcll(kw & ((1ull << t) - 1ull))] = base + w * 64 + t;
         nk += __popcll(kw);
     }
     if (t < kPanelWords) {
@@ -207,14 +257,16 @@ struct BcastSmem {
     float rbox[kRowChunk][8];
     NmsAux raux[kRowChunk];
     float cbox[kColChunk][8];
+    NmsAux caux[kColChunk];
     unsigned short queue[kRowChunk * kColChunk];
     unsigned char dead[kColChunk];
+    unsigned char newdead[kColChunk];
     int rows[kRowChunk];
     int qn;
 };
 
-// grid (column chunks after the panel, row chunks of the panel's kept rows, N), 128 threads
-__global__ void __launch_bounds__(kColChunk) nms_bcast_kernel(const float* __restrict__ boxes,
+// grid (column chunks after the panel, row chunks of the panel's kept rows, N), 256 threads
+__global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* __restrict__ boxes,
                                                               const NmsAux* __restrict__ aux,
                                                               const int* __restrict__ counts, int max_sel, int nblk,
                                                               int panel, float thr, const u64* __restrict__ pk,
@@ -251,41 +303,59 @@ __global__ void __launch_bounds__(kColChunk) nms_bcast_kernel(const float* __res
     }
     if (t == 0) sm.qn = 0;
     __syncthreads();
-    for (int i = t; i < nrows * 8; i += kColChunk) sm.rbox[i >> 3][i & 7] = boxes[(ibase + sm.rows[i >> 3]) * 8 + (i & 7)];
-    if (t < nrows) sm.raux[t] = aux[ibase + sm.rows[t]];
-    const int col = c0 + t;
+    if (t < nrows) {
+        stage_oriented(boxes + (ibase + sm.rows[t]) * 8, sm.rbox[t]);
+        sm.raux[t] = aux[ibase + sm.rows[t]];
+    }
     u64* rmv = removed + static_cast<size_t>(n) * nblk;
     bool alive = false;
-    NmsAux Q;
-    if (col < m) {
-        alive = !((__ldcg(rmv + (col >> 6)) >> (col & 63)) & 1ull);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) sm.cbox[t][k] = boxes[(ibase + col) * 8 + k];
-        Q = aux[ibase + col];
+    if (t < kColChunk) {
+        const int col = c0 + t;
+        if (col < m) {
+            alive = !((__ldcg(rmv + (col >> 6)) >> (col & 63)) & 1ull);
+            if (alive) {
+                stage_oriented(boxes + (ibase + col) * 8, sm.cbox[t]);
+                sm.caux[t] = aux[ibase + col];
+            }
+        }
+        sm.dead[t] = alive ? 0 : 1;
+        sm.newdead[t] = 0;
     }
-    sm.dead[t] = alive ? 0 : 1;
     __syncthreads();
-    if (alive) {
-        for (int r = 0; r < nrows; ++r) {
-            const NmsAux& P = sm.raux[r];
-            if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) continue;
-            const int pos = atomicAdd(&sm.qn, 1);
-            sm.queue[pos] = static_cast<unsigned short>((r << 7) | t);
+    // phase 1: 2 threads per column, half of the rows each
+    {
+        const int j = t & (kColChunk - 1), half = t >> 7;
+        if (!sm.dead[j]) {
+            const NmsAux Q = sm.caux[j];
+            const int rmid = (nrows + 1) >> 1;
+            for (int r = half ? rmid : 0; r < (half ? nrows : rmid); ++r) {
+                const NmsAux& P = sm.raux[r];
+                if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) continue;
+                const int pos = atomicAdd(&sm.qn, 1);
+                sm.queue[pos] = static_cast<unsigned short>((r << 7) | j);
+            }
         }
     }
     __syncthreads();
+    // phase 2: 16 lanes per queued pair
     const int qn = sm.qn;
-    for (int e = t; e < qn; e += kColChunk) {
-        const int r = sm.queue[e] >> 7, j = sm.queue[e] & 127;
-        if (sm.dead[j]) continue;  // benign race: any kept row that hits is enough
-        if (iou_poly_f32(sm.rbox[r], sm.cbox[j]) > thr) sm.dead[j] = 1;
+    const unsigned lane = t & 31;
+    for (int e0 = 0; e0 < qn; e0 += kBcastThreads / 16) {
+        const int e = e0 + (t >> 4);
+        bool active = e < qn;
+        const int r = active ? sm.queue[e] >> 7 : 0, j = active ? sm.queue[e] & 127 : 0;
+        if (active && sm.newdead[j]) active = false;  // benign race: any kept row that hits is enough
+        const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active, lane);
+        if (hit && (lane & 15) == 0) sm.newdead[j] = 1;
     }
     __syncthreads();
-    const bool newly = alive && sm.dead[t];
-    const unsigned bal = __ballot_sync(0xffffffffu, newly);
-    if (bal && (t & 31) == 0) {
-        const int cw = c0 + t;  // 32 columns of one warp share a 64-bit word
-        atomicOr(rmv + (cw >> 6), static_cast<u64>(bal) << (cw & 63));
+    if (t < kColChunk) {
+        const bool newly = alive && sm.newdead[t];
+        const unsigned bal = __ballot_sync(0xffffffffu, newly);
+        if (bal && (t & 31) == 0) {
+            const int cw = c0 + t;  // 32 columns of one warp share a 64-bit word
+            atomicOr(rmv + (cw >> 6), static_cast<u64>(bal) << (cw & 63));
+        }
     }
 }
 
@@ -324,13 +394,13 @@ int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float th
     const int panels = (max_sel + kPanel - 1) / kPanel;
     int nl = 1;
     for (int p = 0; p < panels; ++p) {
-        nms_diag_kernel<<<dim3(kDiagBlocks, N), 64, 0, s>>>(nmsbox, aux, counts, max_sel, y.nblk, p, thr, removed, diag,
+        nms_diag_kernel<<<dim3(kDiagBlocks, N), kDiagThreads, 0, s>>>(nmsbox, aux, counts, max_sel, y.nblk, p, thr, removed, diag,
                                                             pk, ctr, keep, nkeep);
         NMS_CHECK_LAUNCH("nms_diag_kernel");
         ++nl;
         const int after = max_sel - (p + 1) * kPanel;
         if (after > 0) {
-            nms_bcast_kernel<<<dim3((after + kColChunk - 1) / kColChunk, kPanel / kRowChunk, N), kColChunk, 0, s>>>(
+            nms_bcast_kernel<<<dim3((after + kColChunk - 1) / kColChunk, kPanel / kRowChunk, N), kBcastThreads, 0, s>>>(
                 nmsbox, aux, counts, max_sel, y.nblk, p, thr, pk, removed);
             NMS_CHECK_LAUNCH("nms_bcast_kernel");
             ++nl;

@@ -119,8 +119,10 @@ def test_end_to_end_detections_vs_fp32_oracle(setup):
             d = np.stack([np.abs(g4[:, o] - w4).reshape(len(a), -1).max(1) for o in orders], 1)
             # ... and a quad within the drift of sort_quadrilateral's degenerate branch (no separating vertex ->
             # rows partly zero, sort_corners.py:41-43,55) flips between "sorted" and "zeros".
-            assert (d.min(1) > 1.0).mean() <= 0.01, "more than 1% of the matched quads differ by more than a pixel"
-            assert (d[:, 0] > 1.0).mean() <= 0.02, "more than 2% of the matched quads changed vertex order"
+            # the head regresses in stride units (|d reg| <= 5e-2 above), so the pixel tolerance grows with the level
+            tol = np.maximum(1.0, 0.06 * np.array(spec.fpn_strides, np.float32)[dets[i, b, 15].astype(np.int64)])
+            assert (d.min(1) > tol).sum() <= max(1, 0.01 * len(a)), "more than 1% of the matched quads are off"
+            assert (d[:, 0] > tol).sum() <= max(2, 0.02 * len(a)), "more than 2% of the matched quads changed vertex order"
 
 
 def test_r101_plan_runs_and_matches_oracle_heads():
