@@ -62,7 +62,19 @@ int dafne_conv_nhwc(const void* in, int N, int H, int W, int Cin, const void* w,
     d.gn_sums = reinterpret_cast<long long*>(gn_sums);
     ConvPlan plan;
     if (conv_plan_build(d, &plan, num_sms_cached())) return -1;
-    return conv_plan_launch(plan, static_cast<cudaStream_t>(stream));
+    // test / A-B hook: the problem descriptor goes through a small per-thread device buffer (synchronous upload)
+    static thread_local ConvProblem* dev_prob = nullptr;
+    if (!dev_prob && cudaMalloc(&dev_prob, sizeof(ConvProblem)) != cudaSuccess) {
+        set_error("dafne_conv_nhwc: cudaMalloc of the problem descriptor failed");
+        return -1;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaStreamSynchronize(s) != cudaSuccess ||
+        cudaMemcpy(dev_prob, &plan.prob, sizeof(ConvProblem), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("dafne_conv_nhwc: descriptor upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    return conv_group_launch(dev_prob, 1, plan.prob.p.total_tiles, plan.block_n, num_sms_cached(), s);
 }
 
 int dafne_gn_relu_nhwc(const void* in, void* out, int N, int HW, int C, int groups, const int64_t* sums,

@@ -80,10 +80,7 @@ __device__ __forceinline__ T warp_reduce16_scatter(const T (&v)[16], uint32_t la
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
-    conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
-                   const __grid_constant__ ConvParams p) {
+    conv_tc_kernel(const ConvProblem* __restrict__ probs, int nprob, int total_tiles) {
     using Cfg = ConvCfg<BLOCK_N>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -108,12 +105,14 @@ __global__ void __launch_bounds__(256, 1)
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(aux + 16 * STAGES + 32);
     float* s_scale = reinterpret_cast<float*>(aux + 256);
     float* s_shift = s_scale + BLOCK_N;
+    int* s_begin = reinterpret_cast<int*>(aux + 16 * STAGES + 40);  // nprob + 1 tile offsets
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA0);
-        tma_prefetch_desc(&tmB);
-        if (BLOCK_N >= 64) tma_prefetch_desc(&tmOut);
+    if (warp == 0 && lane < nprob) {
+        tma_prefetch_desc(&probs[lane].tmA[0]);
+        tma_prefetch_desc(&probs[lane].tmB);
+        if (BLOCK_N >= 64) tma_prefetch_desc(&probs[lane].tmOut);
     }
+    if (warp == 3 && lane <= nprob) s_begin[lane] = lane < nprob ? probs[lane].p.tile_begin : total_tiles;
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(bar_full + 8 * i, 1);
@@ -134,30 +133,33 @@ __global__ void __launch_bounds__(256, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int num_kb = p.num_taps * p.cin_blocks;
-
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+            int g = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                while (t >= s_begin[g + 1]) ++g;
+                const ConvProblem* pr = probs + g;
+                const ConvParams& p = pr->p;
+                const int lt = t - s_begin[g];
+                const int mt = lt % p.m_tiles, nt = lt / p.m_tiles;
                 const int tx = mt % p.tiles_x;
                 const int r = mt / p.tiles_x;
                 const int ty = r % p.tiles_y, tn = r / p.tiles_y;
                 const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tn * p.nb;
-                for (int tap = 0; tap < p.num_taps; ++tap) {
-                    const int view = p.tap_view[tap];
-                    const CUtensorMap* mA = view == 0 ? &tmA0 : (view == 1 ? &tmA1 : (view == 2 ? &tmA2 : &tmA3));
+                const int num_taps = p.num_taps, cin_blocks = p.cin_blocks, Cin = p.Cin;
+                for (int tap = 0; tap < num_taps; ++tap) {
+                    const CUtensorMap* mA = &pr->tmA[p.tap_view[tap]];
                     const int cx = x0 + p.tap_dx[tap], cy = y0 + p.tap_dy[tap];
-                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    for (int cb = 0; cb < cin_blocks; ++cb) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t full = bar_full + 8 * stage;
                         mbar_arrive_expect_tx(full, Cfg::STAGE_BYTES);
                         const uint32_t sA = s_tiles + stage * Cfg::STAGE_BYTES;
                         tma_load_4d(sA, mA, full, cb * 64, cx, cy, n0);
-                        tma_load_2d(sA + Cfg::A_BYTES, &tmB, full, tap * p.Cin + cb * 64, nt * BLOCK_N);
+                        tma_load_2d(sA + Cfg::A_BYTES, &pr->tmB, full, tap * Cin + cb * 64, nt * BLOCK_N);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -174,7 +176,10 @@ __global__ void __launch_bounds__(256, 1)
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            int g = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                while (t >= s_begin[g + 1]) ++g;
+                const int num_kb = probs[g].p.num_taps * probs[g].p.cin_blocks;
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * BLOCK_N;
@@ -205,18 +210,46 @@ __global__ void __launch_bounds__(256, 1)
         const int wi = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32*wi, 32*wi+32)
         const int et = threadIdx.x - 128;
         const int row = wi * 32 + lane;
-        const int rx = row % p.tw;
-        const int ry = (row / p.tw) % p.th;
-        const int rn = row / (p.tw * p.th);
         int acc = 0;
         uint32_t acc_phase = 0;
         int store_buf = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const int mt = t % p.m_tiles, nt = t / p.m_tiles;
-            const int tx = mt % p.tiles_x;
-            const int r = mt / p.tiles_x;
-            const int ty = r % p.tiles_y, tn = r / p.tiles_y;
-            const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tn * p.nb;
+        int g = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            while (t >= s_begin[g + 1]) ++g;
+            const ConvProblem* pr = probs + g;
+            // this problem's parameters, in registers for the tile
+            struct {
+                int N, Hout, Wout, Cout, relu, res_H, res_W, res_shift, out_ld;
+                const float *scale, *shift;
+                const __half* residual;
+                long long* gn_sums;
+                float* out_f32;
+            } p;
+            p.N = pr->p.N;
+            p.Hout = pr->p.Hout;
+            p.Wout = pr->p.Wout;
+            p.Cout = pr->p.Cout;
+            p.relu = pr->p.relu;
+            p.res_H = pr->p.res_H;
+            p.res_W = pr->p.res_W;
+            p.res_shift = pr->p.res_shift;
+            p.out_ld = pr->p.out_ld;
+            p.scale = pr->p.scale;
+            p.shift = pr->p.shift;
+            p.residual = pr->p.residual;
+            p.gn_sums = pr->p.gn_sums;
+            p.out_f32 = pr->p.out_f32;
+            const int tw = pr->p.tw, th = pr->p.th;
+            const int rx = row % tw;
+            const int ry = (row / tw) % th;
+            const int rn = row / (tw * th);
+            const int lt = t - s_begin[g];
+            const int m_tiles = pr->p.m_tiles, tiles_x = pr->p.tiles_x, tiles_y = pr->p.tiles_y;
+            const int mt = lt % m_tiles, nt = lt / m_tiles;
+            const int tx = mt % tiles_x;
+            const int r = mt / tiles_x;
+            const int ty = r % tiles_y, tn = r / tiles_y;
+            const int x0 = tx * tw, y0 = ty * th, n0 = tn * pr->p.nb;
             const int x = x0 + rx, y = y0 + ry, n = n0 + rn;
             const bool valid = x < p.Wout && y < p.Hout && n < p.N;
 
@@ -327,7 +360,7 @@ __global__ void __launch_bounds__(256, 1)
                     fence_proxy_async_smem();
                     named_bar_sync(1, 128);
                     if (et == 0) {
-                        tma_store_4d(&tmOut, buf, nt * BLOCK_N + chbase, x0, y0, n0);
+                        tma_store_4d(&pr->tmOut, buf, nt * BLOCK_N + chbase, x0, y0, n0);
                         tma_store_commit();
                     }
                     store_buf ^= 1;
@@ -457,7 +490,7 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
         }
         bn = d.Cout % 256 == 0 ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
     }
-    ConvParams& p = plan->p;
+    ConvParams& p = plan->prob.p;
     p.N = d.N;
     p.Hout = d.Hout;
     p.Wout = d.Wout;
@@ -474,6 +507,7 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
     p.n_tiles = (d.Cout + bn - 1) / bn;
     p.total_tiles = p.m_tiles * p.n_tiles;
+    p.tile_begin = 0;
     p.scale = d.scale;
     p.shift = d.shift;
     p.relu = d.relu;
@@ -494,8 +528,8 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     if (d.stride == 1) {
         const uint64_t dims[4] = {C, W, H, (uint64_t)d.N};
         const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
-        if (encode_map(&plan->tmA[0], d.in, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A")) return -1;
-        for (int v = 1; v < 4; ++v) plan->tmA[v] = plan->tmA[0];
+        if (encode_map(&plan->prob.tmA[0], d.in, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A")) return -1;
+        for (int v = 1; v < 4; ++v) plan->prob.tmA[v] = plan->prob.tmA[0];
         for (int t = 0; t < p.num_taps; ++t) {
             p.tap_view[t] = 0;
             p.tap_dy[t] = d.ksize == 3 ? t / 3 - 1 : 0;
@@ -519,7 +553,7 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
                 const uint64_t str[3] = {2 * C * 2, 2 * W * C * 2, H * W * C * 2};
                 const __half* base = d.in + ((size_t)py * W + px) * C;
                 if (view_empty[v]) base = d.in;
-                if (encode_map(&plan->tmA[v], base, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A-s2"))
+                if (encode_map(&plan->prob.tmA[v], base, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A-s2"))
                     return -1;
             }
         for (int t = 0; t < p.num_taps; ++t) {
@@ -536,15 +570,15 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
         const uint64_t dims[2] = {K, (uint64_t)d.Cout};
         const uint64_t str[1] = {K * 2};
         const uint32_t box[2] = {64u, (uint32_t)bn};
-        if (encode_map(&plan->tmB, d.w, 2, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "B")) return -1;
+        if (encode_map(&plan->prob.tmB, d.w, 2, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "B")) return -1;
     }
     if (!small) {
         const uint64_t Co = d.Cout, Wo = d.Wout, Ho = d.Hout;
         const uint64_t dims[4] = {Co, Wo, Ho, (uint64_t)d.N};
         const uint64_t str[3] = {Co * 2, Wo * Co * 2, Ho * Wo * Co * 2};
-        if (encode_map(&plan->tmOut, d.out, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "Out")) return -1;
+        if (encode_map(&plan->prob.tmOut, d.out, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "Out")) return -1;
     } else {
-        plan->tmOut = plan->tmB;
+        plan->prob.tmOut = plan->prob.tmB;
     }
     switch (bn) {
         case 16: plan->smem_bytes = ConvCfg<16>::SMEM_BYTES; break;
@@ -557,7 +591,7 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
 }
 
 template <int BN>
-static int launch_bn(const ConvPlan& pl, cudaStream_t stream) {
+static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -569,8 +603,7 @@ static int launch_bn(const ConvPlan& pl, cudaStream_t stream) {
         }
         configured = true;
     }
-    conv_tc_kernel<BN><<<pl.grid, 256, ConvCfg<BN>::SMEM_BYTES, stream>>>(pl.tmA[0], pl.tmA[1], pl.tmA[2], pl.tmA[3],
-                                                                           pl.tmB, pl.tmOut, pl.p);
+    conv_tc_kernel<BN><<<grid, 256, ConvCfg<BN>::SMEM_BYTES, stream>>>(dev_probs, nprob, total_tiles);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("conv_tc_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
@@ -579,16 +612,22 @@ static int launch_bn(const ConvPlan& pl, cudaStream_t stream) {
     return 0;
 }
 
-int conv_plan_launch(const ConvPlan& pl, cudaStream_t stream) {
-    if (pl.p.total_tiles == 0) return 0;
-    switch (pl.block_n) {
-        case 16: return launch_bn<16>(pl, stream);
-        case 32: return launch_bn<32>(pl, stream);
-        case 64: return launch_bn<64>(pl, stream);
-        case 128: return launch_bn<128>(pl, stream);
-        case 256: return launch_bn<256>(pl, stream);
+int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int num_sms,
+                      cudaStream_t stream) {
+    if (total_tiles == 0) return 0;
+    if (nprob < 1 || nprob > kMaxConvProblems) {
+        set_error("conv_tc: %d problems in one launch (1..%d supported)", nprob, kMaxConvProblems);
+        return -1;
     }
-    set_error("conv_tc: bad block_n %d", pl.block_n);
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    switch (block_n) {
+        case 16: return launch_bn<16>(dev_probs, nprob, total_tiles, grid, stream);
+        case 32: return launch_bn<32>(dev_probs, nprob, total_tiles, grid, stream);
+        case 64: return launch_bn<64>(dev_probs, nprob, total_tiles, grid, stream);
+        case 128: return launch_bn<128>(dev_probs, nprob, total_tiles, grid, stream);
+        case 256: return launch_bn<256>(dev_probs, nprob, total_tiles, grid, stream);
+    }
+    set_error("conv_tc: bad block_n %d", block_n);
     return -1;
 }
 

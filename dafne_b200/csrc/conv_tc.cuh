@@ -36,6 +36,7 @@ struct ConvParams {
     int num_taps, cin_blocks;
     int tw, th, nb;
     int tiles_x, tiles_y, tiles_n, m_tiles, n_tiles, total_tiles;
+    int tile_begin;  // index of this problem's first tile inside a grouped launch
     int tap_view[9], tap_dy[9], tap_dx[9];
     const float* scale;
     const float* shift;
@@ -47,13 +48,20 @@ struct ConvParams {
     int out_ld;
 };
 
-struct ConvPlan {
-    alignas(64) CUtensorMap tmA[4];
-    alignas(64) CUtensorMap tmB;
-    alignas(64) CUtensorMap tmOut;
+// One convolution as the kernel sees it. A launch works through an array of these in device memory (tiles of all
+// problems form one index space), so e.g. one head-tower layer over the five FPN levels is ONE persistent launch.
+constexpr int kMaxConvProblems = 16;
+struct alignas(128) ConvProblem {
+    CUtensorMap tmA[4];
+    CUtensorMap tmB;
+    CUtensorMap tmOut;
     ConvParams p;
+};
+
+struct ConvPlan {
+    ConvProblem prob;  // host copy; conv_group_launch() needs it in device memory
     int block_n;
-    int grid;
+    int grid;  // CTAs for a stand-alone launch
     size_t smem_bytes;
     double flops;  // 2*MACs, algorithmic (unpadded)
 };
@@ -66,7 +74,10 @@ inline void conv_out_dims(ConvDesc& d) {
 
 // Returns 0 on success; on failure writes a message retrievable with dafne_last_error().
 int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms);
-int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream);
+// Launch over `nprob` (<= kMaxConvProblems) problems with the same block_n, stored contiguously in DEVICE memory with
+// p.tile_begin already assigned (prefix sums of p.total_tiles).
+int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int num_sms,
+                      cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
 const char* get_error();

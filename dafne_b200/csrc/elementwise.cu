@@ -126,54 +126,107 @@ int launch_maxpool3x3s2(const __half* in, int N, int H, int W, int C, __half* ou
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm + ReLU
-__global__ void gn_relu_kernel(const __half* in, __half* out, int N, int HW, int C,
-                               int groups, const long long* __restrict__ sums, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, float eps) {
-    const int c8 = C / 8;  // one uint4 = one group of 8 channels
-    const size_t per_img = static_cast<size_t>(HW) * c8;
-    const size_t total = per_img * N;
-    const float inv_cnt = 1.0f / (static_cast<float>(HW) * 8.0f);
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int g = i % c8;
-        const int n = i / per_img;
-        const float s1 = static_cast<float>(static_cast<double>(__ldg(sums + (static_cast<size_t>(n) * groups + g) * 2)) *
-                                            (1.0 / kGnSumScale));
-        const float s2 = static_cast<float>(
-            static_cast<double>(__ldg(sums + (static_cast<size_t>(n) * groups + g) * 2 + 1)) * (1.0 / kGnSqScale));
-        const float mean = s1 * inv_cnt;
-        const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + eps);
-        const uint4 v = reinterpret_cast<const uint4*>(in)[i];  // may alias out (in-place)
-        const uint32_t vin[4] = {v.x, v.y, v.z, v.w};
-        uint32_t vo[4];
+// One launch normalises up to kMaxGnProblems tensors (e.g. one tower layer on all five FPN levels, both towers).
+// Block = 256 threads = 32 channel vectors (8 channels = one group each) x 8 pixel lanes; it handles kGnPixPerBlock
+// consecutive pixels of ONE image of one problem, so every thread keeps its group's affine y = x * a + b in registers
+// and streams 16-byte vectors with four loads in flight.
+constexpr int kGnPixPerBlock = 128;
+
+__global__ void __launch_bounds__(256) gn_relu_group_kernel(const GnGroupArgs args) {
+    int g = 0;
+    while (g + 1 < args.count && static_cast<int>(blockIdx.x) >= args.block_begin[g + 1]) ++g;
+    const GnProblem& pr = args.prob[g];
+    const int blocks_per_img = (pr.HW + kGnPixPerBlock - 1) / kGnPixPerBlock;
+    const int lb = blockIdx.x - args.block_begin[g];
+    const int n = lb / blocks_per_img;
+    const int p0 = (lb % blocks_per_img) * kGnPixPerBlock;
+    const int cv = threadIdx.x & 31;  // channel vector = group index (C == 256, 32 groups of 8)
+    const int pl = threadIdx.x >> 5;  // pixel lane 0..7
+    const float inv_cnt = 1.0f / (static_cast<float>(pr.HW) * 8.0f);
+    const float s1 = static_cast<float>(static_cast<double>(__ldg(pr.sums + (static_cast<size_t>(n) * 32 + cv) * 2)) *
+                                        (1.0 / kGnSumScale));
+    const float s2 = static_cast<float>(
+        static_cast<double>(__ldg(pr.sums + (static_cast<size_t>(n) * 32 + cv) * 2 + 1)) * (1.0 / kGnSqScale));
+    const float mean = s1 * inv_cnt;
+    const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + args.eps);
+    float ga[8], be[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&vin[j]));
-            const int c = g * 8 + 2 * j;
-            const float a0 = fmaxf((f.x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c), 0.f);
-            const float a1 = fmaxf((f.y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1), 0.f);
-            const __half2 h = __floats2half2_rn(a0, a1);
-            vo[j] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        reinterpret_cast<uint4*>(out)[i] = make_uint4(vo[0], vo[1], vo[2], vo[3]);
+    for (int k = 0; k < 8; ++k) {
+        ga[k] = __ldg(pr.gamma + cv * 8 + k);
+        be[k] = __ldg(pr.beta + cv * 8 + k);
     }
+    uint4* base = reinterpret_cast<uint4*>(pr.x) + (static_cast<size_t>(n) * pr.HW) * 32 + cv;
+    const int pend = min(p0 + kGnPixPerBlock, pr.HW);
+    for (int q0 = p0 + pl; q0 < pend; q0 += 32) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = q0 + 8 * u;
+            if (q < pend) v[u] = base[static_cast<size_t>(q) * 32];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = q0 + 8 * u;
+            if (q >= pend) continue;
+            const uint32_t vin[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            uint32_t vo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&vin[j]));
+                const float a0 = fmaxf((f.x - mean) * rstd * ga[2 * j] + be[2 * j], 0.f);
+                const float a1 = fmaxf((f.y - mean) * rstd * ga[2 * j + 1] + be[2 * j + 1], 0.f);
+                const __half2 h = __floats2half2_rn(a0, a1);
+                vo[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            base[static_cast<size_t>(q) * 32] = make_uint4(vo[0], vo[1], vo[2], vo[3]);
+        }
+    }
+}
+
+int launch_gn_relu_group(const GnProblem* probs, int count, float eps, cudaStream_t s) {
+    if (count < 1 || count > kMaxGnProblems) {
+        set_error("gn_relu: %d tensors in one launch (1..%d supported)", count, kMaxGnProblems);
+        return -1;
+    }
+    GnGroupArgs a;
+    a.count = count;
+    a.eps = eps;
+    int total = 0;
+    for (int i = 0; i < count; ++i) {
+        a.prob[i] = probs[i];
+        a.block_begin[i] = total;
+        total += probs[i].N * ((probs[i].HW + kGnPixPerBlock - 1) / kGnPixPerBlock);
+    }
+    a.block_begin[count] = total;
+    if (total == 0) return 0;
+    gn_relu_group_kernel<<<total, 256, 0, s>>>(a);
+    DAFNE_CHECK_LAUNCH("gn_relu_group_kernel");
+    return 0;
 }
 
 int launch_gn_relu(const __half* in, __half* out, int N, int HW, int C, int groups, const long long* sums,
                    const float* gamma, const float* beta, float eps, cudaStream_t s) {
-    if (C != groups * 8) {
-        set_error("gn_relu: needs C == 8 * groups (C=%d groups=%d)", C, groups);
+    if (C != 256 || groups != 32) {
+        set_error("gn_relu: needs C == 256 and 32 groups (C=%d groups=%d)", C, groups);
         return -1;
     }
-    const size_t total = static_cast<size_t>(N) * HW * (C / 8);
-    if (total == 0) return 0;
-    const int threads = 256;
-    size_t blocks = (total + threads - 1) / threads;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    gn_relu_kernel<<<static_cast<int>(blocks), threads, 0, s>>>(in, out, N, HW, C, groups, sums, gamma, beta, eps);
-    DAFNE_CHECK_LAUNCH("gn_relu_kernel");
-    return 0;
+    if (in != out) {
+        cudaError_t e = cudaMemcpyAsync(out, in, static_cast<size_t>(N) * HW * C * sizeof(__half),
+                                        cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) {
+            set_error("gn_relu copy: %s", cudaGetErrorString(e));
+            return -1;
+        }
+    }
+    GnProblem pr;
+    pr.x = out;
+    pr.sums = sums;
+    pr.gamma = gamma;
+    pr.beta = beta;
+    pr.N = N;
+    pr.HW = HW;
+    return launch_gn_relu_group(&pr, 1, eps, s);
 }
 
 // ------------------------------------------------------------------------------------------------ relu copy

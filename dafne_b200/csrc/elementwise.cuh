@@ -15,6 +15,23 @@ int launch_preprocess(const void* images, int dtype, const int32_t* sizes_dev, i
 // 3x3 stride-2 pad-1 max pool, NHWC fp16, C % 8 == 0.
 int launch_maxpool3x3s2(const __half* in, int N, int H, int W, int C, __half* out, cudaStream_t s);
 
+// In-place y = relu(groupnorm(x)) of several NHWC fp16 tensors [N, HW, 256] (32 groups of 8 channels) in one launch.
+constexpr int kMaxGnProblems = 16;
+struct GnProblem {
+    __half* x;              // normalised in place
+    const long long* sums;  // [N][32][2] fixed-point statistics written by the producing conv (ConvDesc::gn_sums)
+    const float* gamma;
+    const float* beta;
+    int N, HW;
+};
+struct GnGroupArgs {
+    GnProblem prob[kMaxGnProblems];
+    int block_begin[kMaxGnProblems + 1];
+    int count;
+    float eps;
+};
+int launch_gn_relu_group(const GnProblem* probs, int count, float eps, cudaStream_t s);
+
 // y = relu(groupnorm(x)) from per-(image, group) fixed-point (sum, sumsq) (see ConvDesc::gn_sums); NHWC fp16,
 // (C / groups) == 8.
 int launch_gn_relu(const __half* in, __half* out, int N, int HW, int C, int groups, const long long* sums,

@@ -280,6 +280,7 @@ int ctx_finalize(dafne_ctx* c, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------ plan
 namespace {
+constexpr size_t kMaxPlanProblems = 512;
 struct Builder {
     dafne_ctx* c;
     uint8_t* base;  // nullptr = dry run (size query)
@@ -287,6 +288,50 @@ struct Builder {
     int64_t launches = 0;
     double flops = 0;
     bool failed = false;
+    // convolutions are appended to `probs`; a launch covers the contiguous range of one group
+    std::vector<ConvProblem> probs;
+    ConvProblem* dev_probs = nullptr;
+    bool grouping = false;
+    size_t group_first = 0;
+    int group_bn = 0;
+    double group_flops = 0, group_bytes = 0;
+    std::string group_name;
+    OpInfo group_info;
+
+    void begin_group(const std::string& name) {
+        grouping = true;
+        group_first = probs.size();
+        group_bn = 0;
+        group_flops = group_bytes = 0;
+        group_name = name;
+    }
+    void end_group() {
+        grouping = false;
+        ++launches;
+        if (!base || failed) return;
+        const size_t first = group_first, cnt = probs.size() - first;
+        if (cnt == 0 || cnt > static_cast<size_t>(kMaxConvProblems)) {
+            set_error("plan: group '%s' has %zu problems", group_name.c_str(), cnt);
+            failed = true;
+            return;
+        }
+        int total = 0;
+        for (size_t i = first; i < probs.size(); ++i) {
+            probs[i].p.tile_begin = total;
+            total += probs[i].p.total_tiles;
+        }
+        const ConvProblem* dp = dev_probs + first;
+        const int bn = group_bn, sms = c->num_sms, n = static_cast<int>(cnt);
+        c->ops.push_back([=](cudaStream_t s) { return conv_group_launch(dp, n, total, bn, sms, s); });
+        OpInfo o = group_info;
+        snprintf(o.name, sizeof(o.name), "%s", group_name.size() > 46 ? group_name.substr(group_name.size() - 46).c_str()
+                                                                      : group_name.c_str());
+        o.kind = 1;
+        o.flops = group_flops;
+        o.bytes = group_bytes;
+        o.block_n = bn;
+        c->op_info.push_back(o);
+    }
 
     Act new_act(int N, int H, int W, int C) {
         Act a;
@@ -366,7 +411,8 @@ struct Builder {
             d.res_shift = res_shift;
         }
         d.gn_sums = gn_sums;
-        ++launches;
+        const bool single = !grouping;
+        if (single) begin_group(L.parts[0].prefix);
         flops += 2.0 * in.N * d.Hout * d.Wout * (double)L.Cout * L.k * L.k * L.Cin;
         if (base) {
             if (in.C != L.Cin) {
@@ -379,15 +425,34 @@ struct Builder {
                 failed = true;
                 return out;
             }
-            c->ops.push_back([plan](cudaStream_t s) { return conv_plan_launch(plan, s); });
+            if (group_bn != 0 && group_bn != plan.block_n) {
+                set_error("plan: group '%s' mixes tile widths %d and %d", group_name.c_str(), group_bn, plan.block_n);
+                failed = true;
+                return out;
+            }
+            if (probs.size() >= kMaxPlanProblems) {
+                set_error("plan: more than %d convolutions", kMaxPlanProblems);
+                failed = true;
+                return out;
+            }
+            group_bn = plan.block_n;
+            probs.push_back(plan.prob);
             const double px_in = (double)in.N * in.H * in.W, px_out = (double)in.N * d.Hout * d.Wout;
-            const double by = px_in * L.Cin * 2 + (double)L.Cout * L.k * L.k * L.Cin * 2 +
-                              px_out * (out_f32 ? out_ld * 4.0 : L.Cout * 2.0) +
-                              (residual ? (double)residual->N * residual->H * residual->W * L.Cout * 2 : 0.0);
-            std::string nm = L.parts[0].prefix;
-            if (nm.size() > 40) nm = nm.substr(nm.size() - 40);
-            info(nm.c_str(), 1, plan.flops, by, plan.block_n, L.k, L.stride, L.Cin, L.Cout, d.Hout, d.Wout);
+            group_bytes += px_in * L.Cin * 2 + (double)L.Cout * L.k * L.k * L.Cin * 2 +
+                           px_out * (out_f32 ? out_ld * 4.0 : L.Cout * 2.0) +
+                           (residual ? (double)residual->N * residual->H * residual->W * L.Cout * 2 : 0.0);
+            group_flops += plan.flops;
+            if (probs.size() - group_first == 1) {
+                group_info = OpInfo();
+                group_info.ksize = L.k;
+                group_info.stride = L.stride;
+                group_info.Cin = L.Cin;
+                group_info.Cout = L.Cout;
+                group_info.Hout = d.Hout;
+                group_info.Wout = d.Wout;
+            }
         }
+        if (single) end_group();
         return out;
     }
 };
@@ -427,6 +492,7 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
         lvW[l] = (lvW[l - 1] - 1) / 2 + 1;
     }
     int32_t* sizes_dev = B.persistent<int32_t>(static_cast<size_t>(N) * 4 * sizeof(int32_t));
+    B.dev_probs = B.persistent<ConvProblem>(kMaxPlanProblems * sizeof(ConvProblem));
     const size_t sums_per = static_cast<size_t>(N) * 32 * 2 * sizeof(long long);
     const size_t sums_bytes = sums_per * 3 * 4 * 5;
     long long* sums_all = B.persistent<long long>(sums_bytes);
@@ -548,51 +614,102 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     B.name("p7", P[4]);
     if (B.failed) return -1;
 
-    // ---- head: three 4-conv GN towers + prediction convs per level (weights shared across levels)
-    for (int l = 0; l < 5; ++l) {
+    // ---- head: three 4-conv GN towers + prediction convs; the weights are shared by the five levels, so every
+    // tower layer is ONE grouped launch over all levels (and over the two towers that run side by side):
+    //   cls_tower(f), center_tower(f), corners_tower(center_tower(f))                        (dafne.py:362-404)
+    for (int l = 0; l < 5; ++l)
         if (P[l].H != lvH[l] || P[l].W != lvW[l]) {
             set_error("plan: level %d is %dx%d, expected %dx%d", l, P[l].H, P[l].W, lvH[l], lvW[l]);
             return -1;
         }
-        Act tower_out[3];
-        for (int t = 0; t < 3; ++t) {
-            // cls_tower(f), center_tower(f), corners_tower(center_tower(f))   (dafne.py:362-404)
-            Act cur = (t == 2) ? tower_out[1] : P[l];
-            bool own = false;
-            for (int i = 0; i < 4; ++i) {
-                const std::string tw = kHead + kTowers[t] + ".";
-                long long* sums = sums_all ? sums_all + ((static_cast<size_t>(t) * 4 + i) * 5 + l) * (sums_per / sizeof(long long))
-                                       : nullptr;
-                Act raw = B.conv(B.layer(tw + std::to_string(3 * i)), cur, false, nullptr, 0,
-                                 base ? sums : reinterpret_cast<long long*>(1));
-                if (own) B.free_act(cur);
-                // GroupNorm + ReLU in place
-                B.launches += 1;
-                if (base) {
-                    __half* rp = raw.p;
-                    const int HW = raw.H * raw.W;
-                    const float* gamma = raw_of(c, tw + std::to_string(3 * i + 1) + ".weight");
-                    const float* beta = raw_of(c, tw + std::to_string(3 * i + 1) + ".bias");
-                    c->ops.push_back(
-                        [=](cudaStream_t s) { return launch_gn_relu(rp, rp, N, HW, 256, 32, sums, gamma, beta, 1e-5f, s); });
-                    B.info("gn_relu", 0, 0, (double)N * HW * 256 * 4);
-                }
-                cur = raw;
-                own = true;
-                if (B.failed) return -1;
-            }
-            tower_out[t] = cur;
-            B.name(std::string(kTowers[t]) + ".l" + std::to_string(l), cur);
+    auto sums_of = [&](int t, int i, int l) -> long long* {
+        return sums_all ? sums_all + ((static_cast<size_t>(t) * 4 + i) * 5 + l) * (sums_per / sizeof(long long))
+                        : reinterpret_cast<long long*>(1);
+    };
+    auto gn_group = [&](const std::vector<std::pair<int, Act*>>& items, int layer) {
+        // items: (tower index, activation) -> normalise in place
+        B.launches += 1;
+        if (!base) return;
+        std::vector<GnProblem> gp;
+        double bytes = 0;
+        int k = 0;
+        for (auto& it : items) {
+            const std::string tw = kHead + kTowers[it.first] + ".";
+            GnProblem g;
+            g.x = it.second->p;
+            g.sums = sums_of(it.first, layer, k % 5);
+            g.gamma = raw_of(c, tw + std::to_string(3 * layer + 1) + ".weight");
+            g.beta = raw_of(c, tw + std::to_string(3 * layer + 1) + ".bias");
+            g.N = N;
+            g.HW = it.second->H * it.second->W;
+            gp.push_back(g);
+            bytes += (double)N * g.HW * 256 * 4;
+            ++k;
         }
-        B.conv(B.layer(kHead + "cls_logits"), tower_out[0], false, nullptr, 0, nullptr,
-               base ? ho[l][0].p : reinterpret_cast<float*>(1), ho[l][0].ld);
-        B.conv(B.layer(kHead + "ctrness"), tower_out[2], false, nullptr, 0, nullptr,
-               base ? ho[l][1].p : reinterpret_cast<float*>(1), ho[l][1].ld);
-        B.conv(B.layer(kHead + "center_pred"), tower_out[1], false, nullptr, 0, nullptr,
-               base ? ho[l][2].p : reinterpret_cast<float*>(1), ho[l][2].ld);
-        for (int t = 0; t < 3; ++t) B.free_act(tower_out[t]);
-        B.free_act(P[l]);
+        c->ops.push_back([gp](cudaStream_t s) { return launch_gn_relu_group(gp.data(), (int)gp.size(), 1e-5f, s); });
+        B.info("gn_relu", 0, 0, bytes);
+    };
+    Act cur[3][5];
+    for (int i = 0; i < 4; ++i) {  // cls_tower and center_tower, layer i, all levels
+        Act raw[2][5];
+        B.begin_group(std::string("cls_tower+center_tower.") + std::to_string(3 * i));
+        for (int t = 0; t < 2; ++t)
+            for (int l = 0; l < 5; ++l)
+                raw[t][l] = B.conv(B.layer(kHead + kTowers[t] + "." + std::to_string(3 * i)), i == 0 ? P[l] : cur[t][l],
+                                   false, nullptr, 0, sums_of(t, i, l));
+        B.end_group();
         if (B.failed) return -1;
+        std::vector<std::pair<int, Act*>> items;
+        for (int t = 0; t < 2; ++t)
+            for (int l = 0; l < 5; ++l) {
+                if (i == 0) {
+                    if (t == 1) B.free_act(P[l]);
+                } else {
+                    B.free_act(cur[t][l]);
+                }
+                cur[t][l] = raw[t][l];
+                items.push_back({t, &cur[t][l]});
+            }
+        gn_group(items, i);
+    }
+    for (int i = 0; i < 4; ++i) {  // corners_tower on top of the center tower
+        Act raw[5];
+        B.begin_group(std::string("corners_tower.") + std::to_string(3 * i));
+        for (int l = 0; l < 5; ++l)
+            raw[l] = B.conv(B.layer(kHead + "corners_tower." + std::to_string(3 * i)), i == 0 ? cur[1][l] : cur[2][l],
+                            false, nullptr, 0, sums_of(2, i, l));
+        B.end_group();
+        if (B.failed) return -1;
+        std::vector<std::pair<int, Act*>> items;
+        for (int l = 0; l < 5; ++l) {
+            if (i > 0) B.free_act(cur[2][l]);
+            cur[2][l] = raw[l];
+            items.push_back({2, &cur[2][l]});
+        }
+        gn_group(items, i);
+    }
+    for (int t = 0; t < 3; ++t)
+        for (int l = 0; l < 5; ++l) B.name(std::string(kTowers[t]) + ".l" + std::to_string(l), cur[t][l]);
+    B.begin_group("pred.cls_logits+center_pred");
+    for (int l = 0; l < 5; ++l) {
+        B.conv(B.layer(kHead + "cls_logits"), cur[0][l], false, nullptr, 0, nullptr,
+               base ? ho[l][0].p : reinterpret_cast<float*>(1), ho[l][0].ld);
+        B.conv(B.layer(kHead + "center_pred"), cur[1][l], false, nullptr, 0, nullptr,
+               base ? ho[l][2].p : reinterpret_cast<float*>(1), ho[l][2].ld);
+    }
+    B.end_group();
+    B.begin_group("pred.ctrness+corners_pred");
+    for (int l = 0; l < 5; ++l)
+        B.conv(B.layer(kHead + "ctrness"), cur[2][l], false, nullptr, 0, nullptr,
+               base ? ho[l][1].p : reinterpret_cast<float*>(1), ho[l][1].ld);
+    B.end_group();
+    for (int t = 0; t < 3; ++t)
+        for (int l = 0; l < 5; ++l) B.free_act(cur[t][l]);
+    if (B.failed) return -1;
+
+    if (base) {
+        // the kernels read their problem descriptors (tensor maps + parameters) from device memory
+        CUDA_OK(cudaMemcpy(B.dev_probs, B.probs.data(), B.probs.size() * sizeof(ConvProblem), cudaMemcpyHostToDevice));
     }
 
     if (needed) *needed = B.arena.peak;

@@ -121,8 +121,12 @@ def test_end_to_end_detections_vs_fp32_oracle(setup):
             # rows partly zero, sort_corners.py:41-43,55) flips between "sorted" and "zeros".
             # the head regresses in stride units (|d reg| <= 5e-2 above), so the pixel tolerance grows with the level
             tol = np.maximum(1.0, 0.06 * np.array(spec.fpn_strides, np.float32)[dets[i, b, 15].astype(np.int64)])
-            assert (d.min(1) > tol).sum() <= max(1, 0.01 * len(a)), "more than 1% of the matched quads are off"
-            assert (d[:, 0] > tol).sum() <= max(2, 0.02 * len(a)), "more than 2% of the matched quads changed vertex order"
+            # a quad within the drift of sort_quadrilateral's degenerate branch (no separating vertex -> vertices left
+            # at (0, 0), sort_corners.py:41-43,55) flips between "sorted" and "zeros": excluded, but bounded
+            degen = ((g4 == 0).all(2).any(1)) | ((w4 == 0).all(2).any(1))
+            assert degen.sum() <= max(2, 0.05 * len(a)), "more than 5% of the matched quads hit the degenerate branch"
+            assert ((d.min(1) > tol) & ~degen).sum() <= max(1, 0.01 * len(a)), "more than 1% of the matched quads are off"
+            assert ((d[:, 0] > tol) & ~degen).sum() <= max(2, 0.02 * len(a)), "more than 2% changed vertex order"
 
 
 def test_r101_plan_runs_and_matches_oracle_heads():
