@@ -31,16 +31,22 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-template <int BLOCK_N>
+// EPI_WGS = number of epilogue warpgroups. 1: compute-bound shapes (deep K), four operand stages. 2: HBM-bound
+// shapes (K <= 256, the epilogue is the critical path): two warpgroups drain alternate tiles (one TMEM accumulator
+// stage each) so two tile epilogues are in flight, at the price of one operand stage.
+template <int BLOCK_N, int EPI_WGS>
 struct ConvCfg {
     static constexpr int A_BYTES = 128 * 128;      // 128 pixels x 64 ch fp16
     static constexpr int B_BYTES = BLOCK_N * 128;  // BLOCK_N couts x 64 ch fp16
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
-    static constexpr int EPI_BYTES = BLOCK_N >= 64 ? 2 * 16384 : 0;
-    static constexpr int AUX_BYTES = 256 + 2 * BLOCK_N * 4;  // barriers + tmem ptr, then scale/shift
+    static constexpr int STAGES =
+        BLOCK_N == 256 ? (EPI_WGS == 2 ? 3 : 4) : (BLOCK_N == 128 ? (EPI_WGS == 2 ? 4 : 6) : (EPI_WGS == 2 ? 6 : 8));
+    static constexpr int EPI_BYTES = BLOCK_N >= 64 ? EPI_WGS * 2 * 16384 : 0;
+    static constexpr int AUX_BYTES = 256 + EPI_WGS * 2 * BLOCK_N * 4;  // barriers + tmem ptr, then scale/shift per WG
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + AUX_BYTES;
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    static constexpr int THREADS = 128 + 128 * EPI_WGS;
+    static_assert(SMEM_BYTES <= 232448, "more than 227 KB of shared memory");
 };
 
 // Sum 16 per-lane values across the warp; lane l returns the total of value index
@@ -78,10 +84,10 @@ __device__ __forceinline__ T warp_reduce16_scatter(const T (&v)[16], uint32_t la
     return d;
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(256, 1)
+template <int BLOCK_N, int EPI_WGS>
+__global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
     conv_tc_kernel(const ConvProblem* __restrict__ probs, int nprob, int total_tiles) {
-    using Cfg = ConvCfg<BLOCK_N>;
+    using Cfg = ConvCfg<BLOCK_N, EPI_WGS>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
 
@@ -103,8 +109,7 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t bar_tfull = s_aux + 16 * STAGES;      // 2 x 8 B
     const uint32_t bar_tempty = s_aux + 16 * STAGES + 16;  // 2 x 8 B
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(aux + 16 * STAGES + 32);
-    float* s_scale = reinterpret_cast<float*>(aux + 256);
-    float* s_shift = s_scale + BLOCK_N;
+    float* s_scale_all = reinterpret_cast<float*>(aux + 256);
     int* s_begin = reinterpret_cast<int*>(aux + 16 * STAGES + 40);  // nprob + 1 tile offsets
 
     if (warp == 0 && lane < nprob) {
@@ -132,7 +137,11 @@ __global__ void __launch_bounds__(256, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-
+    // EPI_WGS == 2: 384 threads start with 168 registers each; the producer/MMA warpgroup hands its surplus to the two
+    // epilogue warpgroups (128 x 56 + 256 x 224 = 384 x 168).
+    if (warp < 4) {
+        if constexpr (EPI_WGS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    }
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
@@ -207,14 +216,23 @@ __global__ void __launch_bounds__(256, 1)
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue
-        const int wi = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32*wi, 32*wi+32)
-        const int et = threadIdx.x - 128;
+        if constexpr (EPI_WGS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int wg = (warp - 4) >> 2;  // epilogue warpgroup
+        const int wi = warp & 3;         // this warp may touch TMEM lanes [32*wi, 32*wi+32)
+        const int et = (threadIdx.x - 128) & 127;
         const int row = wi * 32 + lane;
-        int acc = 0;
-        uint32_t acc_phase = 0;
+        const uint32_t bar_id = 1 + wg;
+        float* s_scale = s_scale_all + wg * 2 * BLOCK_N;
+        float* s_shift = s_scale + BLOCK_N;
+        const uint32_t s_epi_wg = s_epi + wg * 2 * 16384;
+        uint32_t acc_phase = 0;  // EPI_WGS == 2: this warpgroup always drains accumulator stage `wg`
+        int acc = EPI_WGS == 2 ? wg : 0;
         int store_buf = 0;
         int g = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int table_key = -1;  // (problem, n-tile) the scale/shift table in shared memory belongs to
+        int it = 0;          // running tile count of this CTA
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            if (EPI_WGS == 2 && (it & 1) != wg) continue;
             while (t >= s_begin[g + 1]) ++g;
             const ConvProblem* pr = probs + g;
             // this problem's parameters, in registers for the tile
@@ -253,13 +271,29 @@ __global__ void __launch_bounds__(256, 1)
             const int x = x0 + rx, y = y0 + ry, n = n0 + rn;
             const bool valid = x < p.Wout && y < p.Hout && n < p.N;
 
-            named_bar_sync(1, 128);  // everyone is done reading the previous tile's scale/shift
-            for (int i = et; i < BLOCK_N; i += 128) {
-                const int ch = nt * BLOCK_N + i;
-                s_scale[i] = (p.scale != nullptr && ch < p.Cout) ? __ldg(p.scale + ch) : 1.0f;
-                s_shift[i] = (p.shift != nullptr && ch < p.Cout) ? __ldg(p.shift + ch) : 0.0f;
+            // residual of the first 64-channel chunk: issued before anything else so it overlaps the waits below
+            const __half* res_row = nullptr;
+            uint4 res_cur[8];
+            if (BLOCK_N >= 64 && p.residual != nullptr) {
+                res_row = p.residual +
+                          ((static_cast<size_t>(n) * p.res_H + (y >> p.res_shift)) * p.res_W + (x >> p.res_shift)) *
+                              p.Cout +
+                          nt * BLOCK_N;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    res_cur[q] = valid ? __ldg(reinterpret_cast<const uint4*>(res_row) + q) : make_uint4(0, 0, 0, 0);
             }
-            named_bar_sync(1, 128);
+
+            if (table_key != g * 4096 + nt) {
+                table_key = g * 4096 + nt;
+                named_bar_sync(bar_id, 128);  // everyone is done reading the previous table
+                for (int i = et; i < BLOCK_N; i += 128) {
+                    const int ch = nt * BLOCK_N + i;
+                    s_scale[i] = (p.scale != nullptr && ch < p.Cout) ? __ldg(p.scale + ch) : 1.0f;
+                    s_shift[i] = (p.shift != nullptr && ch < p.Cout) ? __ldg(p.shift + ch) : 0.0f;
+                }
+                named_bar_sync(bar_id, 128);
+            }
 
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
@@ -270,16 +304,12 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll 1
                 for (int j = 0; j < CHUNKS; ++j) {
                     const int chbase = j * 64;
-                    uint4 resv[8];
-                    if (p.residual != nullptr) {
-                        const __half* rp =
-                            p.residual +
-                            ((static_cast<size_t>(n) * p.res_H + (y >> p.res_shift)) * p.res_W + (x >> p.res_shift)) *
-                                p.Cout +
-                            nt * BLOCK_N + chbase;
+                    uint4 res_next[8];
+                    if (p.residual != nullptr && j + 1 < CHUNKS) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
-                            resv[q] = valid ? __ldg(reinterpret_cast<const uint4*>(rp) + q) : make_uint4(0, 0, 0, 0);
+                            res_next[q] = valid ? __ldg(reinterpret_cast<const uint4*>(res_row + chbase + 64) + q)
+                                                : make_uint4(0, 0, 0, 0);
                     }
                     uint32_t v[64];
                     DAFNE_TMEM_LD_X32(taddr + chbase, v);
@@ -300,7 +330,7 @@ __global__ void __launch_bounds__(256, 1)
                         float a0 = fmaf(__uint_as_float(v[c]), s_scale[chbase + c], s_shift[chbase + c]);
                         float a1 = fmaf(__uint_as_float(v[c + 1]), s_scale[chbase + c + 1], s_shift[chbase + c + 1]);
                         if (p.residual != nullptr) {
-                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(resv);
+                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(res_cur);
                             const __half2 rh = *reinterpret_cast<const __half2*>(&rw[c >> 1]);
                             const float2 rf = __half22float2(rh);
                             a0 += rf.x;
@@ -317,6 +347,10 @@ __global__ void __launch_bounds__(256, 1)
                             gs[(c >> 3) * 2] += f.x + f.y;
                             gs[(c >> 3) * 2 + 1] += f.x * f.x + f.y * f.y;
                         }
+                    }
+                    if (p.residual != nullptr && j + 1 < CHUNKS) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) res_cur[q] = res_next[q];
                     }
                     if (p.gn_sums != nullptr) {
                         // Per-pixel partials (fixed 8-channel order) become 64-bit fixed point BEFORE any cross-thread
@@ -339,17 +373,17 @@ __global__ void __launch_bounds__(256, 1)
                             if ((lane & 1) == 0) {
                                 const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
                                                 ((lane >> 1) & 1);
-                                const int g = (nt * BLOCK_N + chbase) / 8 + (idx >> 1);
+                                const int gg = (nt * BLOCK_N + chbase) / 8 + (idx >> 1);
                                 atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_sums) +
-                                              (static_cast<size_t>(img) * groups + g) * 2 + (idx & 1),
+                                              (static_cast<size_t>(img) * groups + gg) * 2 + (idx & 1),
                                           static_cast<unsigned long long>(tot));
                             }
                         }
                     }
                     // stage through swizzled smem, then one TMA store per 128 px x 64 ch chunk
-                    const uint32_t buf = s_epi + store_buf * 16384;
+                    const uint32_t buf = s_epi_wg + store_buf * 16384;
                     if (et == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained
-                    named_bar_sync(1, 128);
+                    named_bar_sync(bar_id, 128);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t dst = buf + row * 128 + ((q ^ (row & 7)) << 4);
@@ -358,7 +392,7 @@ __global__ void __launch_bounds__(256, 1)
                                      : "memory");
                     }
                     fence_proxy_async_smem();
-                    named_bar_sync(1, 128);
+                    named_bar_sync(bar_id, 128);
                     if (et == 0) {
                         tma_store_4d(&pr->tmOut, buf, nt * BLOCK_N + chbase, x0, y0, n0);
                         tma_store_commit();
@@ -398,8 +432,12 @@ __global__ void __launch_bounds__(256, 1)
                     }
                 }
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (EPI_WGS == 2) {
+                acc_phase ^= 1;
+            } else {
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
         }
         if (BLOCK_N >= 64 && et == 0) tma_store_wait_all();
     }
@@ -580,39 +618,35 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     } else {
         plan->prob.tmOut = plan->prob.tmB;
     }
-    switch (bn) {
-        case 16: plan->smem_bytes = ConvCfg<16>::SMEM_BYTES; break;
-        case 32: plan->smem_bytes = ConvCfg<32>::SMEM_BYTES; break;
-        case 64: plan->smem_bytes = ConvCfg<64>::SMEM_BYTES; break;
-        case 128: plan->smem_bytes = ConvCfg<128>::SMEM_BYTES; break;
-        default: plan->smem_bytes = ConvCfg<256>::SMEM_BYTES; break;
-    }
+    // K <= 256 (every 1x1 of res2-res4, the 3x3 of res2): HBM-bound, the epilogue is the critical path
+    plan->epi_wgs = (!small && p.num_taps * d.Cin <= 256) ? 2 : 1;
     return 0;
 }
 
-template <int BN>
+template <int BN, int WGS>
 static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, cudaStream_t stream) {
+    using Cfg = ConvCfg<BN, WGS>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             ConvCfg<BN>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, WGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES);
         if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(conv_tc_kernel<%d>, smem=%d): %s", BN, ConvCfg<BN>::SMEM_BYTES,
+            set_error("cudaFuncSetAttribute(conv_tc_kernel<%d,%d>, smem=%d): %s", BN, WGS, Cfg::SMEM_BYTES,
                       cudaGetErrorString(e));
             return -1;
         }
         configured = true;
     }
-    conv_tc_kernel<BN><<<grid, 256, ConvCfg<BN>::SMEM_BYTES, stream>>>(dev_probs, nprob, total_tiles);
+    conv_tc_kernel<BN, WGS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(dev_probs, nprob, total_tiles);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-        set_error("conv_tc_kernel<%d> launch: %s", BN, cudaGetErrorString(e));
+        set_error("conv_tc_kernel<%d,%d> launch: %s", BN, WGS, cudaGetErrorString(e));
         return -1;
     }
     return 0;
 }
 
-int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int num_sms,
+int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int epi_wgs, int num_sms,
                       cudaStream_t stream) {
     if (total_tiles == 0) return 0;
     if (nprob < 1 || nprob > kMaxConvProblems) {
@@ -620,14 +654,18 @@ int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, 
         return -1;
     }
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    switch (block_n) {
-        case 16: return launch_bn<16>(dev_probs, nprob, total_tiles, grid, stream);
-        case 32: return launch_bn<32>(dev_probs, nprob, total_tiles, grid, stream);
-        case 64: return launch_bn<64>(dev_probs, nprob, total_tiles, grid, stream);
-        case 128: return launch_bn<128>(dev_probs, nprob, total_tiles, grid, stream);
-        case 256: return launch_bn<256>(dev_probs, nprob, total_tiles, grid, stream);
+    const int key = block_n * 10 + epi_wgs;
+    switch (key) {
+        case 161: return launch_bn<16, 1>(dev_probs, nprob, total_tiles, grid, stream);
+        case 321: return launch_bn<32, 1>(dev_probs, nprob, total_tiles, grid, stream);
+        case 641: return launch_bn<64, 1>(dev_probs, nprob, total_tiles, grid, stream);
+        case 642: return launch_bn<64, 2>(dev_probs, nprob, total_tiles, grid, stream);
+        case 1281: return launch_bn<128, 1>(dev_probs, nprob, total_tiles, grid, stream);
+        case 1282: return launch_bn<128, 2>(dev_probs, nprob, total_tiles, grid, stream);
+        case 2561: return launch_bn<256, 1>(dev_probs, nprob, total_tiles, grid, stream);
+        case 2562: return launch_bn<256, 2>(dev_probs, nprob, total_tiles, grid, stream);
     }
-    set_error("conv_tc: bad block_n %d", block_n);
+    set_error("conv_tc: unsupported tile width %d with %d epilogue warpgroups", block_n, epi_wgs);
     return -1;
 }
 

@@ -61,8 +61,8 @@ struct alignas(128) ConvProblem {
 struct ConvPlan {
     ConvProblem prob;  // host copy; conv_group_launch() needs it in device memory
     int block_n;
-    int grid;  // CTAs for a stand-alone launch
-    size_t smem_bytes;
+    int epi_wgs;  // epilogue warpgroups the shape wants (1 | 2, see ConvCfg)
+    int grid;     // CTAs for a stand-alone launch
     double flops;  // 2*MACs, algorithmic (unpadded)
 };
 
@@ -76,7 +76,7 @@ inline void conv_out_dims(ConvDesc& d) {
 int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms);
 // Launch over `nprob` (<= kMaxConvProblems) problems with the same block_n, stored contiguously in DEVICE memory with
 // p.tile_begin already assigned (prefix sums of p.total_tiles).
-int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int num_sms,
+int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int epi_wgs, int num_sms,
                       cudaStream_t stream);
 
 void set_error(const char* fmt, ...);

@@ -293,7 +293,7 @@ struct Builder {
     ConvProblem* dev_probs = nullptr;
     bool grouping = false;
     size_t group_first = 0;
-    int group_bn = 0;
+    int group_bn = 0, group_wgs = 0;
     double group_flops = 0, group_bytes = 0;
     std::string group_name;
     OpInfo group_info;
@@ -302,6 +302,7 @@ struct Builder {
         grouping = true;
         group_first = probs.size();
         group_bn = 0;
+        group_wgs = 0;
         group_flops = group_bytes = 0;
         group_name = name;
     }
@@ -321,8 +322,8 @@ struct Builder {
             total += probs[i].p.total_tiles;
         }
         const ConvProblem* dp = dev_probs + first;
-        const int bn = group_bn, sms = c->num_sms, n = static_cast<int>(cnt);
-        c->ops.push_back([=](cudaStream_t s) { return conv_group_launch(dp, n, total, bn, sms, s); });
+        const int bn = group_bn, wgs = group_wgs, sms = c->num_sms, n = static_cast<int>(cnt);
+        c->ops.push_back([=](cudaStream_t s) { return conv_group_launch(dp, n, total, bn, wgs, sms, s); });
         OpInfo o = group_info;
         snprintf(o.name, sizeof(o.name), "%s", group_name.size() > 46 ? group_name.substr(group_name.size() - 46).c_str()
                                                                       : group_name.c_str());
@@ -436,6 +437,7 @@ struct Builder {
                 return out;
             }
             group_bn = plan.block_n;
+            group_wgs = group_wgs == 0 ? plan.epi_wgs : (group_wgs < plan.epi_wgs ? group_wgs : plan.epi_wgs);
             probs.push_back(plan.prob);
             const double px_in = (double)in.N * in.H * in.W, px_out = (double)in.N * d.Hout * d.Wout;
             group_bytes += px_in * L.Cin * 2 + (double)L.Cout * L.k * L.k * L.Cin * 2 +
