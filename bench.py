@@ -245,6 +245,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     det_counts = counts.cpu().tolist()
     post_counts = eng.post_counts()
+    nms_work = eng.nms_stats()
 
     # per-launch timing of one forward (CUDA events on the launching stream) for the roofline of the dominant kernel
     prof = eng.profile_forward(dev_sets[0], sizes)
@@ -286,6 +287,7 @@ def run_ours(args):
                 "nms_boxes_in_per_image": [c["nms_in"] for c in post_counts[:8]],
                 "nms_boxes_kept_per_image": [c["nms_kept"] for c in post_counts[:8]],
                 "candidates_per_level_image0": post_counts[0]["candidates"],
+                "nms_work_per_batch": nms_work,
                 "gflop_per_image": gflop_img,
                 "conv_roofline_frac_whole_step": value / world * gflop_img * 1e9 / (peak_tf * 1e12),
             },

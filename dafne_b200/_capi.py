@@ -88,6 +88,7 @@ _SIGNATURES = {
     "dafne_debug_keep_activations": (_i, [_vp, _i]),
     "dafne_debug_activation": (_i, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "dafne_debug_post_counts": (_i, [_vp, C.POINTER(C.c_int32), _vp]),
+    "dafne_debug_nms_stats": (_i, [_vp, C.POINTER(C.c_uint64), _vp]),
     "dafne_set_profiling": (_i, [_vp, _i]),
     "dafne_get_profile": (_i, [_vp, C.c_void_p, _i, C.POINTER(_i)]),
     "dafne_stats": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_double), _i]),

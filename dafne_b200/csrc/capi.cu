@@ -290,6 +290,22 @@ int dafne_debug_post_counts(dafne_ctx* ctx, int32_t* host_out, void* stream) {
                                     host_out, static_cast<cudaStream_t>(stream));
 }
 
+int dafne_debug_nms_stats(dafne_ctx* ctx, uint64_t* host_out, void* stream) {
+    NEED_CTX(ctx, "dafne_debug_nms_stats");
+    if (!ctx->ws) {
+        set_error("dafne_debug_nms_stats: no workspace bound");
+        return -1;
+    }
+    int hw[10];
+    for (int l = 0; l < 5; ++l) {
+        hw[2 * l] = ctx->head_out[l][0].H;
+        hw[2 * l + 1] = ctx->head_out[l][0].W;
+    }
+    return postprocess_debug_nms_stats(ctx->post_scratch, ctx->N, 5, hw, ctx->spec.num_classes,
+                                       ctx->spec.pre_nms_topk, reinterpret_cast<unsigned long long*>(host_out),
+                                       static_cast<cudaStream_t>(stream));
+}
+
 int dafne_set_profiling(dafne_ctx* ctx, int enable) {
     NEED_CTX(ctx, "dafne_set_profiling");
     ctx->profiling = enable != 0;

@@ -9,7 +9,10 @@
 //   nms_bcast_kernel  kept rows of the panel x every later box still alive; sets `removed` bits
 // Work drops from n^2/2 pairs to about (kept x alive) pairs. Inside both kernels a pair first goes through
 // pair_inter_is_zero() (polyiou.cuh: proves inter == 0 for separated boxes without running the clip); the pairs that
-// need the full fp32 clip are compacted into a shared-memory queue and processed with all lanes busy.
+// need the full fp32 clip are compacted into a shared-memory queue. A queued pair is 16 signed triangle overlaps
+// (edge triangle i of P x edge triangle j of Q, polyiou.cpp:91-103); most of those collapse to 0 through the algorithm's
+// own early-outs, so the queue is expanded once more into (pair, i, j) ITEMS that really need the three clips, and the
+// items -- not the pairs -- are spread over the lanes (eval_queue). The 16 terms are then added in the reference's order.
 // No decision differs from evaluating iou_poly_f32(i, j) > thr for every consulted pair.
 #include <stdio.h>
 
@@ -27,11 +30,15 @@ constexpr int kColChunk = 128;  // columns per bcast CTA
 constexpr int kBcastThreads = 256;
 
 typedef unsigned long long u64;
+// work counters of the last run_nms (diagnostics, bench.py): pairs the sweep consulted, pairs that needed the clip,
+// (pair, i, j) triangle items that ran the three clips -- for the diagonal panels and the broadcast separately
+constexpr int kNmsStats = 8;
+enum { kStDiagPairs = 0, kStDiagQueued = 1, kStDiagItems = 2, kStBcastPairs = 3, kStBcastQueued = 4, kStBcastItems = 5 };
 
 static size_t a256n(size_t v) { return (v + 255) / 256 * 256; }
 
 struct NmsLayout {
-    size_t o_aux, o_removed, o_diag, o_pk, o_ctr, total;
+    size_t o_aux, o_removed, o_diag, o_pk, o_ctr, o_stats, total;
     int nblk;
 };
 static NmsLayout nms_layout(int N, int max_sel) {
@@ -46,6 +53,8 @@ static NmsLayout nms_layout(int N, int max_sel) {
     o = a256n(o + static_cast<size_t>(N) * kPanelWords * 8);
     y.o_ctr = o;
     o = a256n(o + static_cast<size_t>(N) * 4);
+    y.o_stats = o;
+    o = a256n(o + kNmsStats * 8);
     y.o_diag = o;
     o = a256n(o + static_cast<size_t>(N) * kPanel * kPanelWords * 8);
     y.total = o;
@@ -80,31 +89,153 @@ __device__ __forceinline__ void stage_oriented(const float* __restrict__ src, fl
     }
 }
 
-// One queued pair is evaluated by 16 consecutive lanes, lane k = 4*i + j computing the signed overlap of edge
-// triangle i of P with edge triangle j of Q; the group leader then adds the 16 terms in the reference's order
-// (i outer, j inner) and finishes the IoU with the algorithm's own a1, a2. Returns IoU > thr on the leader lane.
-__device__ __forceinline__ bool pair_suppresses_16(const float* P, const float* Q, float a1, float a2, float thr,
-                                                   bool active, unsigned lane) {
-    float val = 0.f;
-    if (active) {
-        const int i = (lane >> 2) & 3, j = lane & 3;
-        P2 a, b, c, d;
-        a.x = P[2 * i];
-        a.y = P[2 * i + 1];
-        b.x = P[2 * ((i + 1) & 3)];
-        b.y = P[2 * ((i + 1) & 3) + 1];
-        c.x = Q[2 * j];
-        c.y = Q[2 * j + 1];
-        d.x = Q[2 * ((j + 1) & 3)];
-        d.y = Q[2 * ((j + 1) & 3) + 1];
-        val = tri_overlap(a, b, c, d);
-    }
-    float inter = 0.f;
+// ------------------------------------------------------------------------------------------------ queued pairs
+// A queued pair needs inter = sum_{i,j} tri_overlap(P_i, P_i+1, Q_j, Q_j+1) (polyiou.cpp:91-103). tri_overlap returns
+// an exact 0 before its three clips when an edge triangle is degenerate (s1 == 0 or s2 == 0) or when both P vertices
+// lie strictly right of the ray O->c (polyiou.cuh); for typical boxes that is most of the 16 terms. So the queue is
+// worked off in chunks of kChunk pairs:
+//   B  one thread per pair: the early-out tests of all 16 terms from 8 + 16 cross products (the very expressions
+//      tri_overlap evaluates) -> the terms that need the clips become ITEMS (pair, i, j) in a second queue
+//   C  one lane per item: tri_overlap, result into vals[term][pair]  (every lane runs the long path: no divergence
+//      between "returns 0 at once" and "clips three times", which is what made one-pair-per-16-lanes slow)
+//   D  one thread per pair: the 16 terms added in the reference's order (i outer, j inner; early-out terms are the
+//      exact +0 the reference adds), union, IoU, decision
+constexpr int kChunk = 256;
+struct EvalSmem {
+    float vals[16][kChunk];
+    unsigned short items[16 * kChunk];
+    int nitems;
+    unsigned stat_items;
+};
+
+// bit (4*i + j) set = term (i, j) needs the clips
+__device__ __forceinline__ unsigned long_path_mask(const float* P, const float* Q) {
+    P2 o;
+    o.x = 0.f;
+    o.y = 0.f;
+    P2 p[4], q[4];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) inter += __shfl_sync(0xffffffffu, val, (lane & 16) + k);
-    const float uni = a1 + a2 - inter;
-    const float iou = (uni == 0.f) ? (inter + 1.f) / (uni + 1.f) : inter / uni;
-    return active && iou > thr;
+    for (int k = 0; k < 4; ++k) {
+        p[k].x = P[2 * k];
+        p[k].y = P[2 * k + 1];
+        q[k].x = Q[2 * k];
+        q[k].y = Q[2 * k + 1];
+    }
+    int s1[4], s2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s1[k] = sigf(cross3(o, p[k], p[(k + 1) & 3]));
+        s2[k] = sigf(cross3(o, q[k], q[(k + 1) & 3]));
+    }
+    // right[c] bit v: P vertex v strictly right of the ray O -> Q vertex c
+    unsigned right[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned m = 0;
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+            if (sigf(q[c].x * p[v].y - p[v].x * q[c].y) < 0) m |= 1u << v;
+        right[c] = m;
+    }
+    unsigned mask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (s1[i] == 0) continue;
+        const unsigned both = (1u << i) | (1u << ((i + 1) & 3));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (s2[j] == 0) continue;
+            const int c = s2[j] == -1 ? ((j + 1) & 3) : j;  // tri_overlap swaps (c, d) for clockwise triangles
+            if ((right[c] & both) == both) continue;
+            mask |= 1u << (4 * i + j);
+        }
+    }
+    return mask;
+}
+
+// Works off `qn` queued (row, column) pairs; entry e = (row << COLBITS) | column. A hit sets bit `column` of
+// hit_bits[row] (diagonal panels) or newdead[column] (broadcast; a pair whose column is already dead is skipped --
+// any kept row that hits is enough). All threads of the 256-thread CTA must call it.
+template <int COLBITS, bool BCAST>
+__device__ __forceinline__ void eval_queue(EvalSmem& ev, const unsigned short* queue, int qn, const float (*rbox)[8],
+                                           const float (*cbox)[8], const NmsAux* raux, const NmsAux* caux, float thr,
+                                           u64* hit_bits, unsigned char* newdead) {
+    const int t = threadIdx.x;
+    const unsigned lane = t & 31;
+    for (int e0 = 0; e0 < qn; e0 += kChunk) {
+        if (t == 0) ev.nitems = 0;
+        __syncthreads();
+        // ---- B
+        const int e = e0 + t;
+        int r = 0, j = 0;
+        unsigned mask = 0;
+        bool active = e < qn;
+        if (active) {
+            r = queue[e] >> COLBITS;
+            j = queue[e] & ((1 << COLBITS) - 1);
+            if (BCAST && newdead[j]) active = false;
+        }
+        if (active) mask = long_path_mask(rbox[r], cbox[j]);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) ev.vals[k][t] = 0.f;
+        {
+            // warp-aggregated append of popc(mask) items per lane
+            int cnt = __popc(mask), incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+            int wbase = 0;
+            if (lane == 31 && wtot) wbase = atomicAdd(&ev.nitems, wtot);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            int pos = wbase + incl - cnt;
+            unsigned m = mask;
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                ev.items[pos++] = static_cast<unsigned short>((t << 4) | k);
+            }
+        }
+        __syncthreads();
+        // ---- C
+        const int nitems = ev.nitems;
+        for (int it = t; it < nitems; it += kChunk) {
+            const int item = ev.items[it];
+            const int pt = item >> 4, k = item & 15, i = k >> 2, jj = k & 3;
+            const unsigned short qe = queue[e0 + pt];
+            const float* P = rbox[qe >> COLBITS];
+            const float* Q = cbox[qe & ((1 << COLBITS) - 1)];
+            P2 a, b, c, d;
+            a.x = P[2 * i];
+            a.y = P[2 * i + 1];
+            b.x = P[2 * ((i + 1) & 3)];
+            b.y = P[2 * ((i + 1) & 3) + 1];
+            c.x = Q[2 * jj];
+            c.y = Q[2 * jj + 1];
+            d.x = Q[2 * ((jj + 1) & 3)];
+            d.y = Q[2 * ((jj + 1) & 3) + 1];
+            ev.vals[k][pt] = tri_overlap(a, b, c, d);
+        }
+        if (t == 0) ev.stat_items += nitems;
+        __syncthreads();
+        // ---- D
+        if (active) {
+            float inter = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) inter += ev.vals[k][t];
+            const float uni = raux[r].area + caux[j].area - inter;
+            const float iou = (uni == 0.f) ? (inter + 1.f) / (uni + 1.f) : inter / uni;
+            if (iou > thr) {
+                if (BCAST)
+                    newdead[j] = 1;
+                else
+                    atomicOr(&hit_bits[r], 1ull << j);
+            }
+        }
+        // the next chunk's B rewrites vals / nitems only after its own barrier; D reads vals[.][t] of its own thread
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ diagonal panel
@@ -118,7 +249,21 @@ struct DiagSmem {
     unsigned short queue[64 * 64];
     int qn;
     int last;
+    unsigned stat_pairs;
+    EvalSmem ev;
 };
+
+// Appends `want` lanes' entries to a shared-memory queue with one atomic per warp. All 32 lanes must call it.
+__device__ __forceinline__ void queue_push(unsigned short* queue, int* qn, bool want, unsigned short entry,
+                                           unsigned lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (static_cast<int>(lane) == leader) base = atomicAdd(qn, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) queue[base + __popc(m & ((1u << lane) - 1u))] = entry;
+}
 
 // grid (36, N), 256 threads. Block b -> (rb, cb), rb <= cb, both 64-box blocks of panel `panel`.
 __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __restrict__ boxes, const NmsAux* __restrict__ aux,
@@ -126,7 +271,7 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
                                                       int panel, float thr, u64* __restrict__ removed,
                                                       u64* __restrict__ diag, u64* __restrict__ pk,
                                                       int* __restrict__ ctr, int* __restrict__ keep,
-                                                      int* __restrict__ nkeep) {
+                                                      int* __restrict__ nkeep, u64* __restrict__ stats) {
     const int n = blockIdx.y;
     const int m = counts[n];
     const int base = panel * kPanel;
@@ -158,35 +303,44 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
             }
             sm.bits[t] = 0;
         }
-        if (t == 0) sm.qn = 0;
+        if (t == 0) {
+            sm.qn = 0;
+            sm.stat_pairs = 0;
+            sm.ev.stat_items = 0;
+        }
         __syncthreads();
         const int ncol = min(64, m - c0);
         // phase 1: 4 threads per row, 16 columns each; pre-filter against the alive columns, queue what needs the clip
         {
             const int r = t >> 2, jq = (t & 3) * 16;
-            if (r0 + r < m && !((rdead >> r) & 1ull)) {
-                const NmsAux P = sm.raux[r];
-                for (int j = max(jq, (cb == rb) ? r + 1 : 0); j < min(jq + 16, ncol); ++j) {
-                    if ((cdead >> j) & 1ull) continue;
+            const unsigned lane = t & 31;
+            const bool row_on = r0 + r < m && !((rdead >> r) & 1ull);
+            const NmsAux P = sm.raux[row_on ? r : 0];
+            const int jlo = max(jq, (cb == rb) ? r + 1 : 0), jhi = min(jq + 16, ncol);
+            unsigned npairs = 0;
+            for (int u = 0; u < 16; ++u) {
+                const int j = jq + u;
+                bool want = row_on && j >= jlo && j < jhi && !((cdead >> j) & 1ull);
+                if (want) {
+                    ++npairs;
                     const NmsAux& Q = sm.caux[j];
-                    if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) continue;
-                    const int pos = atomicAdd(&sm.qn, 1);
-                    sm.queue[pos] = static_cast<unsigned short>((r << 6) | j);
+                    if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) want = false;
                 }
+                queue_push(sm.queue, &sm.qn, want, static_cast<unsigned short>((r << 6) | j), lane);
             }
+            for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
+            if (lane == 0 && npairs) atomicAdd(&sm.stat_pairs, npairs);
         }
         __syncthreads();
-        // phase 2: 16 lanes per queued pair
+        // phase 2: the queued pairs, as (pair, i, j) items
         const int qn = sm.qn;
-        const unsigned lane = t & 31;
-        for (int e0 = 0; e0 < qn; e0 += kDiagThreads / 16) {
-            const int e = e0 + (t >> 4);
-            const bool active = e < qn;
-            const int r = active ? sm.queue[e] >> 6 : 0, j = active ? sm.queue[e] & 63 : 0;
-            const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active, lane);
-            if (hit && (lane & 15) == 0) atomicOr(&sm.bits[r], 1ull << j);
-        }
+        eval_queue<6, false>(sm.ev, sm.queue, qn, sm.rbox, sm.cbox, sm.raux, sm.caux, thr, sm.bits, nullptr);
         __syncthreads();
+        if (t == 0) {
+            atomicAdd(stats + kStDiagPairs, static_cast<u64>(sm.stat_pairs));
+            atomicAdd(stats + kStDiagQueued, static_cast<u64>(qn));
+            atomicAdd(stats + kStDiagItems, static_cast<u64>(sm.ev.stat_items));
+        }
         if (t < 64) bits_out = sm.bits[t];
     }
     if (t < 64)     diag[(static_cast<size_t>(n) * kPanel + rb * 64 + t) * kPanelWords + cb] = bits_out;
@@ -263,6 +417,8 @@ struct BcastSmem {
     unsigned char newdead[kColChunk];
     int rows[kRowChunk];
     int qn;
+    unsigned stat_pairs;
+    EvalSmem ev;
 };
 
 // grid (column chunks after the panel, row chunks of the panel's kept rows, N), 256 threads
@@ -270,7 +426,7 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
                                                               const NmsAux* __restrict__ aux,
                                                               const int* __restrict__ counts, int max_sel, int nblk,
                                                               int panel, float thr, const u64* __restrict__ pk,
-                                                              u64* __restrict__ removed) {
+                                                              u64* __restrict__ removed, u64* __restrict__ stats) {
     const int n = blockIdx.z;
     const int m = counts[n];
     const int c0 = (panel + 1) * kPanel + blockIdx.x * kColChunk;
@@ -301,7 +457,11 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
         for (int i = 0; i < want; ++i) v &= v - 1;
         sm.rows[t] = panel * kPanel + w * 64 + (__ffsll(static_cast<long long>(v)) - 1);
     }
-    if (t == 0) sm.qn = 0;
+    if (t == 0) {
+        sm.qn = 0;
+        sm.stat_pairs = 0;
+        sm.ev.stat_items = 0;
+    }
     __syncthreads();
     if (t < nrows) {
         stage_oriented(boxes + (ibase + sm.rows[t]) * 8, sm.rbox[t]);
@@ -325,28 +485,33 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
     // phase 1: 2 threads per column, half of the rows each
     {
         const int j = t & (kColChunk - 1), half = t >> 7;
-        if (!sm.dead[j]) {
-            const NmsAux Q = sm.caux[j];
-            const int rmid = (nrows + 1) >> 1;
-            for (int r = half ? rmid : 0; r < (half ? nrows : rmid); ++r) {
+        const unsigned lane = t & 31;
+        const bool col_on = !sm.dead[j];
+        const NmsAux Q = sm.caux[col_on ? j : 0];
+        const int rmid = (nrows + 1) >> 1;
+        const int rlo = half ? rmid : 0, rhi = half ? nrows : rmid;
+        unsigned npairs = 0;
+        for (int u = 0; u < (kRowChunk + 1) / 2; ++u) {
+            const int r = rlo + u;
+            bool want = col_on && r < rhi;
+            if (want) {
+                ++npairs;
                 const NmsAux& P = sm.raux[r];
-                if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) continue;
-                const int pos = atomicAdd(&sm.qn, 1);
-                sm.queue[pos] = static_cast<unsigned short>((r << 7) | j);
+                if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) want = false;
             }
+            queue_push(sm.queue, &sm.qn, want, static_cast<unsigned short>((r << 7) | j), lane);
         }
+        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
+        if (lane == 0 && npairs) atomicAdd(&sm.stat_pairs, npairs);
     }
     __syncthreads();
-    // phase 2: 16 lanes per queued pair
+    // phase 2: the queued pairs, as (pair, i, j) items
     const int qn = sm.qn;
-    const unsigned lane = t & 31;
-    for (int e0 = 0; e0 < qn; e0 += kBcastThreads / 16) {
-        const int e = e0 + (t >> 4);
-        bool active = e < qn;
-        const int r = active ? sm.queue[e] >> 7 : 0, j = active ? sm.queue[e] & 127 : 0;
-        if (active && sm.newdead[j]) active = false;  // benign race: any kept row that hits is enough
-        const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active, lane);
-        if (hit && (lane & 15) == 0) sm.newdead[j] = 1;
+    eval_queue<7, true>(sm.ev, sm.queue, qn, sm.rbox, sm.cbox, sm.raux, sm.caux, thr, nullptr, sm.newdead);
+    if (t == 0) {
+        atomicAdd(stats + kStBcastPairs, static_cast<u64>(sm.stat_pairs));
+        atomicAdd(stats + kStBcastQueued, static_cast<u64>(qn));
+        atomicAdd(stats + kStBcastItems, static_cast<u64>(sm.ev.stat_items));
     }
     __syncthreads();
     if (t < kColChunk) {
@@ -382,7 +547,8 @@ int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float th
     u64* diag = reinterpret_cast<u64*>(b + y.o_diag);
     u64* pk = reinterpret_cast<u64*>(b + y.o_pk);
     int* ctr = reinterpret_cast<int*>(b + y.o_ctr);
-    // removed | pk | ctr are contiguous: one clear
+    u64* stats = reinterpret_cast<u64*>(b + y.o_stats);
+    // removed | pk | ctr | stats are contiguous: one clear
     cudaError_t e = cudaMemsetAsync(removed, 0, y.o_diag - y.o_removed, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(nkeep, 0, static_cast<size_t>(N) * 4, s);
     if (e != cudaSuccess) {
@@ -395,18 +561,30 @@ int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float th
     int nl = 1;
     for (int p = 0; p < panels; ++p) {
         nms_diag_kernel<<<dim3(kDiagBlocks, N), kDiagThreads, 0, s>>>(nmsbox, aux, counts, max_sel, y.nblk, p, thr, removed, diag,
-                                                            pk, ctr, keep, nkeep);
+                                                            pk, ctr, keep, nkeep, stats);
         NMS_CHECK_LAUNCH("nms_diag_kernel");
         ++nl;
         const int after = max_sel - (p + 1) * kPanel;
         if (after > 0) {
             nms_bcast_kernel<<<dim3((after + kColChunk - 1) / kColChunk, kPanel / kRowChunk, N), kBcastThreads, 0, s>>>(
-                nmsbox, aux, counts, max_sel, y.nblk, p, thr, pk, removed);
+                nmsbox, aux, counts, max_sel, y.nblk, p, thr, pk, removed, stats);
             NMS_CHECK_LAUNCH("nms_bcast_kernel");
             ++nl;
         }
     }
     if (launches) *launches += nl;
+    return 0;
+}
+
+int nms_read_stats(const void* scratch, int N, int max_sel, unsigned long long* host_out, cudaStream_t s) {
+    const NmsLayout y = nms_layout(N, max_sel < 1 ? 1 : max_sel);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(host_out, static_cast<const uint8_t*>(scratch) + y.o_stats, kNmsStats * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        set_error("nms_read_stats: %s", cudaGetErrorString(e));
+        return -1;
+    }
     return 0;
 }
 

@@ -792,6 +792,12 @@ int postprocess_debug_counts(const void* scratch, int N, int L, const int* level
     return 0;
 }
 
+int postprocess_debug_nms_stats(const void* scratch, int N, int L, const int* level_hw, int num_classes,
+                                int pre_nms_topk, unsigned long long* host_out, cudaStream_t s) {
+    const Layout y = make_layout(N, L, level_hw, num_classes, pre_nms_topk);
+    return nms_read_stats(static_cast<const uint8_t*>(scratch) + y.o_nms, N, y.max_sel, host_out, s);
+}
+
 // ================================================================================================ stand-alone NMS hook
 // ml_nms semantics for one image given boxes / scores / classes in arbitrary order.
 __global__ void __launch_bounds__(1024) nms_prepare_kernel(const float* __restrict__ polys,

@@ -230,6 +230,13 @@ class DafneEngine:
         return [dict(candidates=list(arr[8 * n:8 * n + 5]), nms_in=arr[8 * n + 5], nms_kept=arr[8 * n + 6],
                      capacity=arr[8 * n + 7]) for n in range(N)]
 
+    def nms_stats(self) -> dict:
+        """Work counters of the rotated NMS of the last post-processing (synchronises), summed over the batch."""
+        arr = (C.c_uint64 * 8)()
+        _capi.check(self.lib.dafne_debug_nms_stats(self._ctx, arr, _capi.stream_ptr()), "dafne_debug_nms_stats")
+        return dict(diag_pairs=arr[0], diag_clipped_pairs=arr[1], diag_triangle_items=arr[2], bcast_pairs=arr[3],
+                    bcast_clipped_pairs=arr[4], bcast_triangle_items=arr[5])
+
     def stats(self, reset: bool = False) -> Tuple[int, float]:
         launches, flops = C.c_int64(), C.c_double()
         _capi.check(self.lib.dafne_stats(self._ctx, C.byref(launches), C.byref(flops), int(reset)), "dafne_stats")

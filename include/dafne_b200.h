@@ -129,6 +129,13 @@ int dafne_debug_activation(dafne_ctx* ctx, const char* name, const void** dev_pt
  * the score threshold per level (5), boxes entering NMS, boxes kept by NMS before the post-NMS top-k, list capacity. */
 int dafne_debug_post_counts(dafne_ctx* ctx, int32_t* host_out, void* stream);
 
+/* Work counters of the rotated NMS of the last dafne_postprocess / dafne_detect (synchronises the stream), summed over
+ * the batch: host_out[0..2] = box pairs the greedy sweep consulted / pairs that needed the polygon clip / (pair, edge,
+ * edge) triangle overlaps that ran the three half-plane clips, inside the 512-box diagonal panels; host_out[3..5] = the
+ * same for the kept-rows x later-boxes broadcast; host_out[6..7] reserved. The reference's poly_gpu_nms evaluates
+ * n * (n - 1) / 2 pairs x 16 triangle overlaps per image (nms.py:91). */
+int dafne_debug_nms_stats(dafne_ctx* ctx, uint64_t* host_out, void* stream);
+
 /* Per-launch timing of the dense forward with CUDA events on the launching stream (bench.py's roofline numbers).
  * dafne_set_profiling(ctx, 1) makes every following dafne_forward_dense record an event after each launch;
  * dafne_get_profile (after the stream has been synchronised) returns, for launch i < *count: its duration in ms,

@@ -91,6 +91,14 @@ def test_fused_postprocess_equals_oracle_on_gpu_heads(setup):
         assert np.array_equal(dets[i, :n, 18].view(np.uint32).astype(np.int64), w["canon"])
         assert np.array_equal(dets[i, :n, 0:8], w["pred_corners"])
         assert np.array_equal(dets[i, :n, 12], w["scores"])
+    # work counters of the lazily evaluated NMS: never more clips than consulted pairs, never more than 16 triangle
+    # items per clipped pair, and far fewer consulted pairs than the reference's n(n-1)/2 would allow at most
+    st = eng.nms_stats()
+    n_in = [c["nms_in"] for c in eng.post_counts()]
+    assert 0 < st["diag_pairs"] + st["bcast_pairs"] <= sum(k * (k - 1) // 2 for k in n_in)
+    assert st["diag_clipped_pairs"] <= st["diag_pairs"] and st["bcast_clipped_pairs"] <= st["bcast_pairs"]
+    assert st["diag_triangle_items"] <= 16 * st["diag_clipped_pairs"]
+    assert st["bcast_triangle_items"] <= 16 * st["bcast_clipped_pairs"]
 
 
 def test_end_to_end_detections_vs_fp32_oracle(setup):
@@ -115,19 +123,25 @@ def test_end_to_end_detections_vs_fp32_oracle(setup):
             # many rows needed one.
             g4 = dets[i, b, 0:8].reshape(-1, 4, 2)
             w4 = w["pred_corners"][a].reshape(-1, 4, 2)
-            orders = [np.roll(np.arange(4), s) for s in range(4)] + [np.roll(np.arange(4)[::-1], s) for s in range(4)]
-            d = np.stack([np.abs(g4[:, o] - w4).reshape(len(a), -1).max(1) for o in orders], 1)
-            # ... and a quad within the drift of sort_quadrilateral's degenerate branch (no separating vertex ->
-            # rows partly zero, sort_corners.py:41-43,55) flips between "sorted" and "zeros".
+            import itertools
+
+            dihedral = [tuple(np.roll(np.arange(4), s)) for s in range(4)] + \
+                       [tuple(np.roll(np.arange(4)[::-1], s)) for s in range(4)]
+            perms = dihedral + [p for p in itertools.permutations(range(4)) if p not in dihedral]
+            d = np.stack([np.abs(g4[:, list(o)] - w4).reshape(len(a), -1).max(1) for o in perms], 1)
             # the head regresses in stride units (|d reg| <= 5e-2 above), so the pixel tolerance grows with the level
             tol = np.maximum(1.0, 0.06 * np.array(spec.fpn_strides, np.float32)[dets[i, b, 15].astype(np.int64)])
             # a quad within the drift of sort_quadrilateral's degenerate branch (no separating vertex -> vertices left
             # at (0, 0), sort_corners.py:41-43,55) flips between "sorted" and "zeros": excluded, but bounded
             degen = ((g4 == 0).all(2).any(1)) | ((w4 == 0).all(2).any(1))
             assert degen.sum() <= max(2, 0.05 * len(a)), "more than 5% of the matched quads hit the degenerate branch"
-            assert ((d.min(1) > tol) & ~degen).sum() <= max(1, 0.01 * len(a)), "more than 1% of the matched quads are off"
-            assert ((d[:, 0] > tol) & ~degen).sum() <= max(2, 0.02 * len(a)), "more than 2% changed vertex order"
-
+            # sort_quadrilateral is a pure permutation of the four decoded vertices: as a point SET every matched
+            # quad must agree (a non-convex quad near a sign change of sort_corners.py:65-69 may come out in one
+            # of the 16 non-dihedral orders, i.e. as another polygon through the same vertices)
+            off = (d.min(1) > tol) & ~degen
+            assert off.sum() == 0, f"vertex sets differ: got {g4[off][:2]}, want {w4[off][:2]}"
+            assert ((d[:, :8].min(1) > tol) & ~degen).sum() <= max(2, 0.03 * len(a)), "more than 3% are another polygon"
+            assert ((d[:, 0] > tol) & ~degen).sum() <= max(2, 0.03 * len(a)), "more than 3% changed vertex order"
 
 def test_r101_plan_runs_and_matches_oracle_heads():
     from dafne_b200.engine import DafneEngine
