@@ -74,7 +74,8 @@ int dafne_conv_nhwc(const void* in, int N, int H, int W, int Cin, const void* w,
         set_error("dafne_conv_nhwc: descriptor upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return -1;
     }
-    return conv_group_launch(dev_prob, 1, plan.prob.p.total_tiles, plan.block_n, plan.epi_wgs, num_sms_cached(), s);
+    return conv_group_launch(dev_prob, 1, plan.prob.p.total_tiles, plan.block_n, plan.epi_wgs, plan.res_tma,
+                             num_sms_cached(), s);
 }
 
 int dafne_gn_relu_nhwc(const void* in, void* out, int N, int HW, int C, int groups, const int64_t* sums,

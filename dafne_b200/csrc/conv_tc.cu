@@ -11,8 +11,13 @@
 // zero-filled by TMA, which is exactly the conv zero padding. Nothing im2col-shaped ever exists in HBM.
 //
 // Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (TMEM -> registers -> scale/shift/residual/ReLU -> fp16 -> swizzled smem -> TMA store).
-// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+// warp 3 = residual producer, warps 4-7 = epilogue (TMEM -> registers -> scale/shift/residual/ReLU -> fp16 -> swizzled
+// smem -> TMA store). Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Residual (the bottleneck shortcut, detectron2 BottleneckBlock `out += shortcut`): the 128 px x 64 ch residual chunk
+// is TMA-loaded by warp 3 into the very ring slot the epilogue later stages its output in (same box, same swizzle), so
+// the epilogue adds it from shared memory in place and the slot goes load -> add/ReLU -> store -> free. The loads run
+// a whole ring ahead of the epilogue; nothing on that path is an uncoalesced per-thread global load.
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -31,23 +36,26 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-// EPI_WGS = number of epilogue warpgroups. 1: compute-bound shapes (deep K), four operand stages. 2: HBM-bound
-// shapes (K <= 256, the epilogue is the critical path): two warpgroups drain alternate tiles (one TMEM accumulator
-// stage each) so two tile epilogues are in flight, at the price of one operand stage.
+// EPI_WGS = number of epilogue warpgroups. 1: compute-bound shapes (deep K). 2: HBM-bound shapes (K <= 256, the
+// epilogue is the critical path): two warpgroups drain alternate tiles (one TMEM accumulator stage each) so two tile
+// epilogues are in flight. The number of operand stages and of 16 KB epilogue ring slots per warpgroup is chosen at
+// launch (conv_smem_config) -- shared memory is carved up at run time.
 template <int BLOCK_N, int EPI_WGS>
 struct ConvCfg {
     static constexpr int A_BYTES = 128 * 128;      // 128 pixels x 64 ch fp16
     static constexpr int B_BYTES = BLOCK_N * 128;  // BLOCK_N couts x 64 ch fp16
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES =
-        BLOCK_N == 256 ? (EPI_WGS == 2 ? 3 : 4) : (BLOCK_N == 128 ? (EPI_WGS == 2 ? 4 : 6) : (EPI_WGS == 2 ? 6 : 8));
-    static constexpr int EPI_BYTES = BLOCK_N >= 64 ? EPI_WGS * 2 * 16384 : 0;
-    static constexpr int AUX_BYTES = 256 + EPI_WGS * 2 * BLOCK_N * 4;  // barriers + tmem ptr, then scale/shift per WG
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + AUX_BYTES;
+    static constexpr int SLOT_BYTES = 16384;  // 128 pixels x 64 ch fp16, one epilogue chunk
+    static constexpr int AUX_HDR = 512;       // barriers, tmem pointer, tile offsets
+    static constexpr int AUX_BYTES = AUX_HDR + EPI_WGS * BLOCK_N * 8;  // + (scale, shift) pairs per warpgroup
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
     static constexpr int THREADS = 128 + 128 * EPI_WGS;
-    static_assert(SMEM_BYTES <= 232448, "more than 227 KB of shared memory");
+    static constexpr int MAX_STAGES = 8, MAX_RING = 4;
+    static constexpr int smem_bytes(int stages, int ring) {
+        return stages * STAGE_BYTES + (BLOCK_N >= 64 ? EPI_WGS * ring * SLOT_BYTES : 0) + AUX_BYTES;
+    }
 };
+constexpr int kMaxSmem = 232448;  // 227 KB
 
 // Sum 16 per-lane values across the warp; lane l returns the total of value index
 // 8*b4 + 4*b3 + 2*b2 + b1 (b_i = bit i of l). 16 shuffles instead of 80.
@@ -84,11 +92,28 @@ __device__ __forceinline__ T warp_reduce16_scatter(const T (&v)[16], uint32_t la
     return d;
 }
 
+// tile index inside a problem -> (m tile, n tile): the n tile is the FAST index, so CTAs that run side by side share
+// the activation tile (second reader hits L2) instead of re-reading the whole input once per n tile.
+struct TileCoord {
+    int x0, y0, n0, nt;
+};
+__device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int lt) {
+    TileCoord c;
+    c.nt = lt % p.n_tiles;
+    const int mt = lt / p.n_tiles;
+    const int tx = mt % p.tiles_x;
+    const int r = mt / p.tiles_x;
+    c.x0 = tx * p.tw;
+    c.y0 = (r % p.tiles_y) * p.th;
+    c.n0 = (r / p.tiles_y) * p.nb;
+    return c;
+}
+
 template <int BLOCK_N, int EPI_WGS>
 __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
-    conv_tc_kernel(const ConvProblem* __restrict__ probs, int nprob, int total_tiles) {
+    conv_tc_kernel(const ConvProblem* __restrict__ probs, int nprob, int total_tiles, int stages, int ring,
+                   int res_tma) {
     using Cfg = ConvCfg<BLOCK_N, EPI_WGS>;
-    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
 
     const uint32_t smem_base = smem_u32(smem);
@@ -99,33 +124,41 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
         __trap();
     }
 
-    // carve-up: [stages x (A | B)] [epilogue staging] [barriers | tmem ptr] [scale | shift]
+    // carve-up: [stages x (A | B)] [EPI_WGS x ring x 16 KB epilogue slots] [512 B header] [(scale, shift) tables]
+    const int epi_bytes = BLOCK_N >= 64 ? EPI_WGS * ring * Cfg::SLOT_BYTES : 0;
     const uint32_t s_tiles = smem_base;
-    const uint32_t s_epi = smem_base + STAGES * Cfg::STAGE_BYTES;
-    const uint32_t s_aux = s_epi + Cfg::EPI_BYTES;
-    uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES;
-    const uint32_t bar_full = s_aux;                     // STAGES x 8 B
-    const uint32_t bar_empty = s_aux + 8 * STAGES;       // STAGES x 8 B
-    const uint32_t bar_tfull = s_aux + 16 * STAGES;      // 2 x 8 B
-    const uint32_t bar_tempty = s_aux + 16 * STAGES + 16;  // 2 x 8 B
-    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(aux + 16 * STAGES + 32);
-    float* s_scale_all = reinterpret_cast<float*>(aux + 256);
-    int* s_begin = reinterpret_cast<int*>(aux + 16 * STAGES + 40);  // nprob + 1 tile offsets
+    const uint32_t s_epi = smem_base + stages * Cfg::STAGE_BYTES;
+    const uint32_t s_aux = s_epi + epi_bytes;
+    uint8_t* aux = smem + stages * Cfg::STAGE_BYTES + epi_bytes;
+    const uint32_t bar_full = s_aux;             // 8 x 8 B
+    const uint32_t bar_empty = s_aux + 64;       // 8 x 8 B
+    const uint32_t bar_tfull = s_aux + 128;      // 2 x 8 B
+    const uint32_t bar_tempty = s_aux + 144;     // 2 x 8 B
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(aux + 160);
+    int* s_begin = reinterpret_cast<int*>(aux + 168);  // nprob + 1 tile offsets (<= 17 ints)
+    const uint32_t bar_rfull = s_aux + 256;      // [EPI_WGS][4] x 8 B: residual chunk landed in the slot
+    const uint32_t bar_rempty = s_aux + 320;     // [EPI_WGS][4] x 8 B: the slot's output store has been read out
+    float2* s_tab_all = reinterpret_cast<float2*>(aux + Cfg::AUX_HDR);
 
     if (warp == 0 && lane < nprob) {
         tma_prefetch_desc(&probs[lane].tmA[0]);
         tma_prefetch_desc(&probs[lane].tmB);
         if (BLOCK_N >= 64) tma_prefetch_desc(&probs[lane].tmOut);
+        if (BLOCK_N >= 64 && res_tma) tma_prefetch_desc(&probs[lane].tmRes);
     }
     if (warp == 3 && lane <= nprob) s_begin[lane] = lane < nprob ? probs[lane].p.tile_begin : total_tiles;
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) {
+        for (int i = 0; i < stages; ++i) {
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
+        }
+        for (int i = 0; i < 8; ++i) {
+            mbar_init(bar_rfull + 8 * i, 1);
+            mbar_init(bar_rempty + 8 * i, 1);
         }
         fence_barrier_init();
     }
@@ -143,7 +176,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
         if constexpr (EPI_WGS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     }
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------ TMA producer (operands)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -152,24 +185,19 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                 while (t >= s_begin[g + 1]) ++g;
                 const ConvProblem* pr = probs + g;
                 const ConvParams& p = pr->p;
-                const int lt = t - s_begin[g];
-                const int mt = lt % p.m_tiles, nt = lt / p.m_tiles;
-                const int tx = mt % p.tiles_x;
-                const int r = mt / p.tiles_x;
-                const int ty = r % p.tiles_y, tn = r / p.tiles_y;
-                const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tn * p.nb;
+                const TileCoord tc = tile_coord(p, t - s_begin[g]);
                 const int num_taps = p.num_taps, cin_blocks = p.cin_blocks, Cin = p.Cin;
                 for (int tap = 0; tap < num_taps; ++tap) {
                     const CUtensorMap* mA = &pr->tmA[p.tap_view[tap]];
-                    const int cx = x0 + p.tap_dx[tap], cy = y0 + p.tap_dy[tap];
+                    const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
                     for (int cb = 0; cb < cin_blocks; ++cb) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t full = bar_full + 8 * stage;
                         mbar_arrive_expect_tx(full, Cfg::STAGE_BYTES);
                         const uint32_t sA = s_tiles + stage * Cfg::STAGE_BYTES;
-                        tma_load_4d(sA, mA, full, cb * 64, cx, cy, n0);
-                        tma_load_2d(sA + Cfg::A_BYTES, &pr->tmB, full, tap * Cin + cb * 64, nt * BLOCK_N);
-                        if (++stage == STAGES) {
+                        tma_load_4d(sA, mA, full, cb * 64, cx, cy, tc.n0);
+                        tma_load_2d(sA + Cfg::A_BYTES, &pr->tmB, full, tap * Cin + cb * 64, tc.nt * BLOCK_N);
+                        if (++stage == stages) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -204,7 +232,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                         umma_f16(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
                     }
                     umma_commit(bar_empty + 8 * stage);
-                    if (++stage == STAGES) {
+                    if (++stage == stages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -212,6 +240,29 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                 umma_commit(bar_tfull + 8 * acc);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------ residual producer
+        if (BLOCK_N >= 64 && res_tma && lane == 0) {
+            constexpr int CHUNKS = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;
+            int cnt[2] = {0, 0};  // chunks issued per epilogue warpgroup
+            int g = 0, it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                while (t >= s_begin[g + 1]) ++g;
+                const ConvProblem* pr = probs + g;
+                const TileCoord tc = tile_coord(pr->p, t - s_begin[g]);
+                const int wg = EPI_WGS == 2 ? (it & 1) : 0;
+                for (int j = 0; j < CHUNKS; ++j) {
+                    const int c = cnt[wg]++;
+                    const int slot = c % ring;
+                    const uint32_t round = static_cast<uint32_t>(c / ring);
+                    mbar_wait(bar_rempty + 8 * (wg * 4 + slot), (round & 1) ^ 1);
+                    const uint32_t full = bar_rfull + 8 * (wg * 4 + slot);
+                    mbar_arrive_expect_tx(full, Cfg::SLOT_BYTES);
+                    tma_load_4d(s_epi + (wg * ring + slot) * Cfg::SLOT_BYTES, &pr->tmRes, full,
+                                tc.nt * BLOCK_N + j * 64, tc.x0, tc.y0, tc.n0);
+                }
             }
         }
     } else if (warp >= 4) {
@@ -222,12 +273,11 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
         const int et = (threadIdx.x - 128) & 127;
         const int row = wi * 32 + lane;
         const uint32_t bar_id = 1 + wg;
-        float* s_scale = s_scale_all + wg * 2 * BLOCK_N;
-        float* s_shift = s_scale + BLOCK_N;
-        const uint32_t s_epi_wg = s_epi + wg * 2 * 16384;
+        float2* s_tab = s_tab_all + wg * BLOCK_N;
+        const uint32_t s_epi_wg = s_epi + wg * ring * Cfg::SLOT_BYTES;
         uint32_t acc_phase = 0;  // EPI_WGS == 2: this warpgroup always drains accumulator stage `wg`
         int acc = EPI_WGS == 2 ? wg : 0;
-        int store_buf = 0;
+        int chunk_cnt = 0;  // chunks this warpgroup has staged so far (ring position)
         int g = 0;
         int table_key = -1;  // (problem, n-tile) the scale/shift table in shared memory belongs to
         int it = 0;          // running tile count of this CTA
@@ -261,36 +311,29 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             const int rx = row % tw;
             const int ry = (row / tw) % th;
             const int rn = row / (tw * th);
-            const int lt = t - s_begin[g];
-            const int m_tiles = pr->p.m_tiles, tiles_x = pr->p.tiles_x, tiles_y = pr->p.tiles_y;
-            const int mt = lt % m_tiles, nt = lt / m_tiles;
-            const int tx = mt % tiles_x;
-            const int r = mt / tiles_x;
-            const int ty = r % tiles_y, tn = r / tiles_y;
-            const int x0 = tx * tw, y0 = ty * th, n0 = tn * pr->p.nb;
+            const TileCoord tc = tile_coord(pr->p, t - s_begin[g]);
+            const int nt = tc.nt, x0 = tc.x0, y0 = tc.y0, n0 = tc.n0;
             const int x = x0 + rx, y = y0 + ry, n = n0 + rn;
             const bool valid = x < p.Wout && y < p.Hout && n < p.N;
+            // residual read by the threads themselves: only the FPN top-down add (nearest-upsampled, res_shift == 1)
+            const bool res_ldg = BLOCK_N >= 64 && p.residual != nullptr && !res_tma;
 
-            // residual of the first 64-channel chunk: issued before anything else so it overlaps the waits below
             const __half* res_row = nullptr;
-            uint4 res_cur[8];
-            if (BLOCK_N >= 64 && p.residual != nullptr) {
+            if (res_ldg)
                 res_row = p.residual +
                           ((static_cast<size_t>(n) * p.res_H + (y >> p.res_shift)) * p.res_W + (x >> p.res_shift)) *
                               p.Cout +
                           nt * BLOCK_N;
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    res_cur[q] = valid ? __ldg(reinterpret_cast<const uint4*>(res_row) + q) : make_uint4(0, 0, 0, 0);
-            }
 
             if (table_key != g * 4096 + nt) {
                 table_key = g * 4096 + nt;
                 named_bar_sync(bar_id, 128);  // everyone is done reading the previous table
                 for (int i = et; i < BLOCK_N; i += 128) {
                     const int ch = nt * BLOCK_N + i;
-                    s_scale[i] = (p.scale != nullptr && ch < p.Cout) ? __ldg(p.scale + ch) : 1.0f;
-                    s_shift[i] = (p.shift != nullptr && ch < p.Cout) ? __ldg(p.shift + ch) : 0.0f;
+                    float2 v;
+                    v.x = (p.scale != nullptr && ch < p.Cout) ? __ldg(p.scale + ch) : 1.0f;
+                    v.y = (p.shift != nullptr && ch < p.Cout) ? __ldg(p.shift + ch) : 0.0f;
+                    s_tab[i] = v;
                 }
                 named_bar_sync(bar_id, 128);
             }
@@ -302,18 +345,32 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             if constexpr (BLOCK_N >= 64) {
                 constexpr int CHUNKS = BLOCK_N / 64;
 #pragma unroll 1
-                for (int j = 0; j < CHUNKS; ++j) {
+                for (int j = 0; j < CHUNKS; ++j, ++chunk_cnt) {
                     const int chbase = j * 64;
-                    uint4 res_next[8];
-                    if (p.residual != nullptr && j + 1 < CHUNKS) {
+                    const int slot = chunk_cnt % ring;
+                    const uint32_t buf = s_epi_wg + slot * Cfg::SLOT_BYTES;
+                    uint4 res[8];
+                    if (res_ldg) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
-                            res_next[q] = valid ? __ldg(reinterpret_cast<const uint4*>(res_row + chbase + 64) + q)
-                                                : make_uint4(0, 0, 0, 0);
+                            res[q] = valid ? __ldg(reinterpret_cast<const uint4*>(res_row + chbase) + q)
+                                           : make_uint4(0, 0, 0, 0);
                     }
                     uint32_t v[64];
                     DAFNE_TMEM_LD_X32(taddr + chbase, v);
                     DAFNE_TMEM_LD_X32(taddr + chbase + 32, (v + 32));
+                    if (res_tma) {
+                        // the residual chunk of this tile, TMA-loaded into the slot the output is staged in
+                        mbar_wait(bar_rfull + 8 * (wg * 4 + slot), static_cast<uint32_t>(chunk_cnt / ring) & 1);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t src = buf + row * 128 + ((q ^ (row & 7)) << 4);
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(res[q].x), "=r"(res[q].y), "=r"(res[q].z), "=r"(res[q].w)
+                                         : "r"(src)
+                                         : "memory");
+                        }
+                    }
                     tmem_ld_wait();
                     if (j == CHUNKS - 1) {
                         // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
@@ -321,16 +378,18 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                     }
+                    const bool has_res = res_ldg || res_tma;
                     uint32_t packed[32];
                     float gs[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) gs[i] = 0.0f;
 #pragma unroll
                     for (int c = 0; c < 64; c += 2) {
-                        float a0 = fmaf(__uint_as_float(v[c]), s_scale[chbase + c], s_shift[chbase + c]);
-                        float a1 = fmaf(__uint_as_float(v[c + 1]), s_scale[chbase + c + 1], s_shift[chbase + c + 1]);
-                        if (p.residual != nullptr) {
-                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(res_cur);
+                        const float4 tb = *reinterpret_cast<const float4*>(&s_tab[chbase + c]);  // (scale, shift) x 2
+                        float a0 = fmaf(__uint_as_float(v[c]), tb.x, tb.y);
+                        float a1 = fmaf(__uint_as_float(v[c + 1]), tb.z, tb.w);
+                        if (has_res) {
+                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(res);
                             const __half2 rh = *reinterpret_cast<const __half2*>(&rw[c >> 1]);
                             const float2 rf = __half22float2(rh);
                             a0 += rf.x;
@@ -347,10 +406,6 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                             gs[(c >> 3) * 2] += f.x + f.y;
                             gs[(c >> 3) * 2 + 1] += f.x * f.x + f.y * f.y;
                         }
-                    }
-                    if (p.residual != nullptr && j + 1 < CHUNKS) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) res_cur[q] = res_next[q];
                     }
                     if (p.gn_sums != nullptr) {
                         // Per-pixel partials (fixed 8-channel order) become 64-bit fixed point BEFORE any cross-thread
@@ -380,10 +435,11 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                             }
                         }
                     }
-                    // stage through swizzled smem, then one TMA store per 128 px x 64 ch chunk
-                    const uint32_t buf = s_epi_wg + store_buf * 16384;
-                    if (et == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained
-                    named_bar_sync(bar_id, 128);
+                    // Stage the chunk in its ring slot (swizzled like the TMA box), then one TMA store per
+                    // 128 px x 64 ch chunk. Every thread writes only the row it (in residual mode) just read, and the
+                    // slot is known to be free: in residual mode because its reload was gated on the previous store
+                    // (bar_rempty), otherwise because the elected thread waited for that store before the barrier
+                    // of the PREVIOUS chunk (wait_group.read ring-2 below).
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t dst = buf + row * 128 + ((q ^ (row & 7)) << 4);
@@ -392,12 +448,25 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                                      : "memory");
                     }
                     fence_proxy_async_smem();
+                    if (et == 0 && !res_tma) {
+                        // before anyone may write the NEXT chunk's slot, the store that last read it must be done
+                        if (ring == 2)
+                            tma_store_wait_read<0>();
+                        else if (ring == 3)
+                            tma_store_wait_read<1>();
+                        else
+                            tma_store_wait_read<2>();
+                    }
                     named_bar_sync(bar_id, 128);
                     if (et == 0) {
                         tma_store_4d(&pr->tmOut, buf, nt * BLOCK_N + chbase, x0, y0, n0);
                         tma_store_commit();
+                        if (res_tma && chunk_cnt > 0) {
+                            // the previous chunk's store has read its slot: the residual producer may refill it
+                            tma_store_wait_read<1>();
+                            mbar_arrive(bar_rempty + 8 * (wg * 4 + (chunk_cnt - 1) % ring));
+                        }
                     }
-                    store_buf ^= 1;
                 }
             } else {
                 // small-Cout prediction convs: fp32 NHWC rows written straight from registers
@@ -416,11 +485,13 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
 #pragma unroll
                     for (int c = 0; c < BLOCK_N; c += 4) {
                         if (c < p.out_ld) {
+                            const float4 t0 = *reinterpret_cast<const float4*>(&s_tab[c]);
+                            const float4 t1 = *reinterpret_cast<const float4*>(&s_tab[c + 2]);
                             float4 o;
-                            o.x = fmaf(__uint_as_float(v[c]), s_scale[c], s_shift[c]);
-                            o.y = fmaf(__uint_as_float(v[c + 1]), s_scale[c + 1], s_shift[c + 1]);
-                            o.z = fmaf(__uint_as_float(v[c + 2]), s_scale[c + 2], s_shift[c + 2]);
-                            o.w = fmaf(__uint_as_float(v[c + 3]), s_scale[c + 3], s_shift[c + 3]);
+                            o.x = fmaf(__uint_as_float(v[c]), t0.x, t0.y);
+                            o.y = fmaf(__uint_as_float(v[c + 1]), t0.z, t0.w);
+                            o.z = fmaf(__uint_as_float(v[c + 2]), t1.x, t1.y);
+                            o.w = fmaf(__uint_as_float(v[c + 3]), t1.z, t1.w);
                             if (p.relu) {
                                 o.x = fmaxf(o.x, 0.f);
                                 o.y = fmaxf(o.y, 0.f);
@@ -618,26 +689,67 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     } else {
         plan->prob.tmOut = plan->prob.tmB;
     }
+    plan->prob.tmRes = plan->prob.tmOut;
+    plan->res_tma = 0;
+    if (!small && d.residual != nullptr && d.res_shift == 0) {
+        if (d.res_H != d.Hout || d.res_W != d.Wout) {
+            set_error("conv_tc: residual %dx%d does not match the output %dx%d", d.res_H, d.res_W, d.Hout, d.Wout);
+            return -1;
+        }
+        const uint64_t Co = d.Cout, Wo = d.Wout, Ho = d.Hout;
+        const uint64_t dims[4] = {Co, Wo, Ho, (uint64_t)d.N};
+        const uint64_t str[3] = {Co * 2, Wo * Co * 2, Ho * Wo * Co * 2};
+        if (encode_map(&plan->prob.tmRes, d.residual, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "Res"))
+            return -1;
+        plan->res_tma = 1;
+    }
     // K <= 256 (every 1x1 of res2-res4, the 3x3 of res2): HBM-bound, the epilogue is the critical path
     plan->epi_wgs = (!small && p.num_taps * d.Cin <= 256) ? 2 : 1;
     return 0;
 }
 
+// Operand stages / epilogue ring slots per warpgroup for a launch: as deep as 227 KB allows. With a TMA residual the
+// ring is the prefetch depth of the residual stream, so it gets four slots at the price of operand stages.
 template <int BN, int WGS>
-static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, cudaStream_t stream) {
+static void conv_smem_config(int res_tma, int* stages, int* ring) {
+    using Cfg = ConvCfg<BN, WGS>;
+    if (BN < 64) {
+        *ring = 2;
+        *stages = Cfg::MAX_STAGES;
+        return;
+    }
+    int r = res_tma ? 4 : (WGS == 2 ? 3 : 2);
+    int st = Cfg::MAX_STAGES;
+    while (st > 2 && Cfg::smem_bytes(st, r) > kMaxSmem) --st;
+    while (r > 2 && Cfg::smem_bytes(st, r) > kMaxSmem) --r;
+    *stages = st;
+    *ring = r;
+}
+
+template <int BN, int WGS>
+static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, int res_tma,
+                     cudaStream_t stream) {
     using Cfg = ConvCfg<BN, WGS>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, WGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_BYTES);
+                                             kMaxSmem);
         if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(conv_tc_kernel<%d,%d>, smem=%d): %s", BN, WGS, Cfg::SMEM_BYTES,
+            set_error("cudaFuncSetAttribute(conv_tc_kernel<%d,%d>, smem=%d): %s", BN, WGS, kMaxSmem,
                       cudaGetErrorString(e));
             return -1;
         }
         configured = true;
     }
-    conv_tc_kernel<BN, WGS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(dev_probs, nprob, total_tiles);
+    int stages, ring;
+    conv_smem_config<BN, WGS>(res_tma, &stages, &ring);
+    const int smem = Cfg::smem_bytes(stages, ring);
+    if (smem > kMaxSmem) {
+        set_error("conv_tc_kernel<%d,%d>: %d stages + %d ring slots need %d bytes of shared memory", BN, WGS, stages,
+                  ring, smem);
+        return -1;
+    }
+    conv_tc_kernel<BN, WGS><<<grid, Cfg::THREADS, smem, stream>>>(dev_probs, nprob, total_tiles, stages, ring, res_tma);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("conv_tc_kernel<%d,%d> launch: %s", BN, WGS, cudaGetErrorString(e));
@@ -646,8 +758,8 @@ static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, i
     return 0;
 }
 
-int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int epi_wgs, int num_sms,
-                      cudaStream_t stream) {
+int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int epi_wgs, int res_tma,
+                      int num_sms, cudaStream_t stream) {
     if (total_tiles == 0) return 0;
     if (nprob < 1 || nprob > kMaxConvProblems) {
         set_error("conv_tc: %d problems in one launch (1..%d supported)", nprob, kMaxConvProblems);
@@ -656,14 +768,14 @@ int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, 
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     const int key = block_n * 10 + epi_wgs;
     switch (key) {
-        case 161: return launch_bn<16, 1>(dev_probs, nprob, total_tiles, grid, stream);
-        case 321: return launch_bn<32, 1>(dev_probs, nprob, total_tiles, grid, stream);
-        case 641: return launch_bn<64, 1>(dev_probs, nprob, total_tiles, grid, stream);
-        case 642: return launch_bn<64, 2>(dev_probs, nprob, total_tiles, grid, stream);
-        case 1281: return launch_bn<128, 1>(dev_probs, nprob, total_tiles, grid, stream);
-        case 1282: return launch_bn<128, 2>(dev_probs, nprob, total_tiles, grid, stream);
-        case 2561: return launch_bn<256, 1>(dev_probs, nprob, total_tiles, grid, stream);
-        case 2562: return launch_bn<256, 2>(dev_probs, nprob, total_tiles, grid, stream);
+        case 161: return launch_bn<16, 1>(dev_probs, nprob, total_tiles, grid, 0, stream);
+        case 321: return launch_bn<32, 1>(dev_probs, nprob, total_tiles, grid, 0, stream);
+        case 641: return launch_bn<64, 1>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
+        case 642: return launch_bn<64, 2>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
+        case 1281: return launch_bn<128, 1>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
+        case 1282: return launch_bn<128, 2>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
+        case 2561: return launch_bn<256, 1>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
+        case 2562: return launch_bn<256, 2>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
     }
     set_error("conv_tc: unsupported tile width %d with %d epilogue warpgroups", block_n, epi_wgs);
     return -1;

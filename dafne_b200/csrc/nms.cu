@@ -9,10 +9,10 @@
 //   nms_bcast_kernel  kept rows of the panel x every later box still alive; sets `removed` bits
 // Work drops from n^2/2 pairs to about (kept x alive) pairs. Inside both kernels a pair first goes through
 // pair_inter_is_zero() (polyiou.cuh: proves inter == 0 for separated boxes without running the clip); the pairs that
-// need the full fp32 clip are compacted into a shared-memory queue. A queued pair is 16 signed triangle overlaps
-// (edge triangle i of P x edge triangle j of Q, polyiou.cpp:91-103); most of those collapse to 0 through the algorithm's
-// own early-outs, so the queue is expanded once more into (pair, i, j) ITEMS that really need the three clips, and the
-// items -- not the pairs -- are spread over the lanes (eval_queue). The 16 terms are then added in the reference's order.
+// need the full fp32 clip are compacted into a shared-memory queue and processed with all lanes busy: a queued pair is
+// 16 signed triangle overlaps (edge triangle i of P x edge triangle j of Q, polyiou.cpp:91-103), one per lane, added
+// in the reference's order. (Measured: of those 16 terms 14 on average run all three half-plane clips for a pair the
+// pre-filter lets through, so a second, per-triangle queue only costs -- tried in r1e, 8 % slower end to end.)
 // No decision differs from evaluating iou_poly_f32(i, j) > thr for every consulted pair.
 #include <stdio.h>
 
@@ -30,10 +30,10 @@ constexpr int kColChunk = 128;  // columns per bcast CTA
 constexpr int kBcastThreads = 256;
 
 typedef unsigned long long u64;
-// work counters of the last run_nms (diagnostics, bench.py): pairs the sweep consulted, pairs that needed the clip,
-// (pair, i, j) triangle items that ran the three clips -- for the diagonal panels and the broadcast separately
+// work counters of the last run_nms (diagnostics, bench.py): pairs the sweep consulted and pairs that needed the clip,
+// for the diagonal panels and the broadcast separately (slots 2 and 5 are reserved)
 constexpr int kNmsStats = 8;
-enum { kStDiagPairs = 0, kStDiagQueued = 1, kStDiagItems = 2, kStBcastPairs = 3, kStBcastQueued = 4, kStBcastItems = 5 };
+enum { kStDiagPairs = 0, kStDiagQueued = 1, kStBcastPairs = 3, kStBcastQueued = 4 };
 
 static size_t a256n(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -89,153 +89,31 @@ __device__ __forceinline__ void stage_oriented(const float* __restrict__ src, fl
     }
 }
 
-// ------------------------------------------------------------------------------------------------ queued pairs
-// A queued pair needs inter = sum_{i,j} tri_overlap(P_i, P_i+1, Q_j, Q_j+1) (polyiou.cpp:91-103). tri_overlap returns
-// an exact 0 before its three clips when an edge triangle is degenerate (s1 == 0 or s2 == 0) or when both P vertices
-// lie strictly right of the ray O->c (polyiou.cuh); for typical boxes that is most of the 16 terms. So the queue is
-// worked off in chunks of kChunk pairs:
-//   B  one thread per pair: the early-out tests of all 16 terms from 8 + 16 cross products (the very expressions
-//      tri_overlap evaluates) -> the terms that need the clips become ITEMS (pair, i, j) in a second queue
-//   C  one lane per item: tri_overlap, result into vals[term][pair]  (every lane runs the long path: no divergence
-//      between "returns 0 at once" and "clips three times", which is what made one-pair-per-16-lanes slow)
-//   D  one thread per pair: the 16 terms added in the reference's order (i outer, j inner; early-out terms are the
-//      exact +0 the reference adds), union, IoU, decision
-constexpr int kChunk = 256;
-struct EvalSmem {
-    float vals[16][kChunk];
-    unsigned short items[16 * kChunk];
-    int nitems;
-    unsigned stat_items;
-};
-
-// bit (4*i + j) set = term (i, j) needs the clips
-__device__ __forceinline__ unsigned long_path_mask(const float* P, const float* Q) {
-    P2 o;
-    o.x = 0.f;
-    o.y = 0.f;
-    P2 p[4], q[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        p[k].x = P[2 * k];
-        p[k].y = P[2 * k + 1];
-        q[k].x = Q[2 * k];
-        q[k].y = Q[2 * k + 1];
+// One queued pair is evaluated by 16 consecutive lanes, lane k = 4*i + j computing the signed overlap of edge
+// triangle i of P with edge triangle j of Q; the group leader then adds the 16 terms in the reference's order
+// (i outer, j inner) and finishes the IoU with the algorithm's own a1, a2. Returns IoU > thr on the leader lane.
+__device__ __forceinline__ bool pair_suppresses_16(const float* P, const float* Q, float a1, float a2, float thr,
+                                                   bool active, unsigned lane) {
+    float val = 0.f;
+    if (active) {
+        const int i = (lane >> 2) & 3, j = lane & 3;
+        P2 a, b, c, d;
+        a.x = P[2 * i];
+        a.y = P[2 * i + 1];
+        b.x = P[2 * ((i + 1) & 3)];
+        b.y = P[2 * ((i + 1) & 3) + 1];
+        c.x = Q[2 * j];
+        c.y = Q[2 * j + 1];
+        d.x = Q[2 * ((j + 1) & 3)];
+        d.y = Q[2 * ((j + 1) & 3) + 1];
+        val = tri_overlap(a, b, c, d);
     }
-    int s1[4], s2[4];
+    float inter = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        s1[k] = sigf(cross3(o, p[k], p[(k + 1) & 3]));
-        s2[k] = sigf(cross3(o, q[k], q[(k + 1) & 3]));
-    }
-    // right[c] bit v: P vertex v strictly right of the ray O -> Q vertex c
-    unsigned right[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        unsigned m = 0;
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-            if (sigf(q[c].x * p[v].y - p[v].x * q[c].y) < 0) m |= 1u << v;
-        right[c] = m;
-    }
-    unsigned mask = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (s1[i] == 0) continue;
-        const unsigned both = (1u << i) | (1u << ((i + 1) & 3));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (s2[j] == 0) continue;
-            const int c = s2[j] == -1 ? ((j + 1) & 3) : j;  // tri_overlap swaps (c, d) for clockwise triangles
-            if ((right[c] & both) == both) continue;
-            mask |= 1u << (4 * i + j);
-        }
-    }
-    return mask;
-}
-
-// Works off `qn` queued (row, column) pairs; entry e = (row << COLBITS) | column. A hit sets bit `column` of
-// hit_bits[row] (diagonal panels) or newdead[column] (broadcast; a pair whose column is already dead is skipped --
-// any kept row that hits is enough). All threads of the 256-thread CTA must call it.
-template <int COLBITS, bool BCAST>
-__device__ __forceinline__ void eval_queue(EvalSmem& ev, const unsigned short* queue, int qn, const float (*rbox)[8],
-                                           const float (*cbox)[8], const NmsAux* raux, const NmsAux* caux, float thr,
-                                           u64* hit_bits, unsigned char* newdead) {
-    const int t = threadIdx.x;
-    const unsigned lane = t & 31;
-    for (int e0 = 0; e0 < qn; e0 += kChunk) {
-        if (t == 0) ev.nitems = 0;
-        __syncthreads();
-        // ---- B
-        const int e = e0 + t;
-        int r = 0, j = 0;
-        unsigned mask = 0;
-        bool active = e < qn;
-        if (active) {
-            r = queue[e] >> COLBITS;
-            j = queue[e] & ((1 << COLBITS) - 1);
-            if (BCAST && newdead[j]) active = false;
-        }
-        if (active) mask = long_path_mask(rbox[r], cbox[j]);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) ev.vals[k][t] = 0.f;
-        {
-            // warp-aggregated append of popc(mask) items per lane
-            int cnt = __popc(mask), incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int wtot = __shfl_sync(0xffffffffu, incl, 31);
-            int wbase = 0;
-            if (lane == 31 && wtot) wbase = atomicAdd(&ev.nitems, wtot);
-            wbase = __shfl_sync(0xffffffffu, wbase, 31);
-            int pos = wbase + incl - cnt;
-            unsigned m = mask;
-            while (m) {
-                const int k = __ffs(m) - 1;
-                m &= m - 1;
-                ev.items[pos++] = static_cast<unsigned short>((t << 4) | k);
-            }
-        }
-        __syncthreads();
-        // ---- C
-        const int nitems = ev.nitems;
-        for (int it = t; it < nitems; it += kChunk) {
-            const int item = ev.items[it];
-            const int pt = item >> 4, k = item & 15, i = k >> 2, jj = k & 3;
-            const unsigned short qe = queue[e0 + pt];
-            const float* P = rbox[qe >> COLBITS];
-            const float* Q = cbox[qe & ((1 << COLBITS) - 1)];
-            P2 a, b, c, d;
-            a.x = P[2 * i];
-            a.y = P[2 * i + 1];
-            b.x = P[2 * ((i + 1) & 3)];
-            b.y = P[2 * ((i + 1) & 3) + 1];
-            c.x = Q[2 * jj];
-            c.y = Q[2 * jj + 1];
-            d.x = Q[2 * ((jj + 1) & 3)];
-            d.y = Q[2 * ((jj + 1) & 3) + 1];
-            ev.vals[k][pt] = tri_overlap(a, b, c, d);
-        }
-        if (t == 0) ev.stat_items += nitems;
-        __syncthreads();
-        // ---- D
-        if (active) {
-            float inter = 0.f;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) inter += ev.vals[k][t];
-            const float uni = raux[r].area + caux[j].area - inter;
-            const float iou = (uni == 0.f) ? (inter + 1.f) / (uni + 1.f) : inter / uni;
-            if (iou > thr) {
-                if (BCAST)
-                    newdead[j] = 1;
-                else
-                    atomicOr(&hit_bits[r], 1ull << j);
-            }
-        }
-        // the next chunk's B rewrites vals / nitems only after its own barrier; D reads vals[.][t] of its own thread
-    }
+    for (int k = 0; k < 16; ++k) inter += __shfl_sync(0xffffffffu, val, (lane & 16) + k);
+    const float uni = a1 + a2 - inter;
+    const float iou = (uni == 0.f) ? (inter + 1.f) / (uni + 1.f) : inter / uni;
+    return active && iou > thr;
 }
 
 // ------------------------------------------------------------------------------------------------ diagonal panel
@@ -250,7 +128,6 @@ struct DiagSmem {
     int qn;
     int last;
     unsigned stat_pairs;
-    EvalSmem ev;
 };
 
 // Appends `want` lanes' entries to a shared-memory queue with one atomic per warp. All 32 lanes must call it.
@@ -306,7 +183,6 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
         if (t == 0) {
             sm.qn = 0;
             sm.stat_pairs = 0;
-            sm.ev.stat_items = 0;
         }
         __syncthreads();
         const int ncol = min(64, m - c0);
@@ -332,14 +208,20 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
             if (lane == 0 && npairs) atomicAdd(&sm.stat_pairs, npairs);
         }
         __syncthreads();
-        // phase 2: the queued pairs, as (pair, i, j) items
+        // phase 2: 16 lanes per queued pair
         const int qn = sm.qn;
-        eval_queue<6, false>(sm.ev, sm.queue, qn, sm.rbox, sm.cbox, sm.raux, sm.caux, thr, sm.bits, nullptr);
+        const unsigned lane = t & 31;
+        for (int e0 = 0; e0 < qn; e0 += kDiagThreads / 16) {
+            const int e = e0 + (t >> 4);
+            const bool active = e < qn;
+            const int r = active ? sm.queue[e] >> 6 : 0, j = active ? sm.queue[e] & 63 : 0;
+            const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active, lane);
+            if (hit && (lane & 15) == 0) atomicOr(&sm.bits[r], 1ull << j);
+        }
         __syncthreads();
         if (t == 0) {
             atomicAdd(stats + kStDiagPairs, static_cast<u64>(sm.stat_pairs));
             atomicAdd(stats + kStDiagQueued, static_cast<u64>(qn));
-            atomicAdd(stats + kStDiagItems, static_cast<u64>(sm.ev.stat_items));
         }
         if (t < 64) bits_out = sm.bits[t];
     }
@@ -418,7 +300,6 @@ struct BcastSmem {
     int rows[kRowChunk];
     int qn;
     unsigned stat_pairs;
-    EvalSmem ev;
 };
 
 // grid (column chunks after the panel, row chunks of the panel's kept rows, N), 256 threads
@@ -460,7 +341,6 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
     if (t == 0) {
         sm.qn = 0;
         sm.stat_pairs = 0;
-        sm.ev.stat_items = 0;
     }
     __syncthreads();
     if (t < nrows) {
@@ -505,13 +385,20 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
         if (lane == 0 && npairs) atomicAdd(&sm.stat_pairs, npairs);
     }
     __syncthreads();
-    // phase 2: the queued pairs, as (pair, i, j) items
+    // phase 2: 16 lanes per queued pair
     const int qn = sm.qn;
-    eval_queue<7, true>(sm.ev, sm.queue, qn, sm.rbox, sm.cbox, sm.raux, sm.caux, thr, nullptr, sm.newdead);
+    const unsigned lane = t & 31;
+    for (int e0 = 0; e0 < qn; e0 += kBcastThreads / 16) {
+        const int e = e0 + (t >> 4);
+        bool active = e < qn;
+        const int r = active ? sm.queue[e] >> 7 : 0, j = active ? sm.queue[e] & 127 : 0;
+        if (active && sm.newdead[j]) active = false;  // benign race: any kept row that hits is enough
+        const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active, lane);
+        if (hit && (lane & 15) == 0) sm.newdead[j] = 1;
+    }
     if (t == 0) {
         atomicAdd(stats + kStBcastPairs, static_cast<u64>(sm.stat_pairs));
         atomicAdd(stats + kStBcastQueued, static_cast<u64>(qn));
-        atomicAdd(stats + kStBcastItems, static_cast<u64>(sm.ev.stat_items));
     }
     __syncthreads();
     if (t < kColChunk) {

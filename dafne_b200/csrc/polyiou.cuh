@@ -40,20 +40,34 @@ __device__ __forceinline__ int line_cross(P2 a, P2 b, P2 c, P2 d, P2* out) {
     out->y = (c.y * s2 - d.y * s1) / (s2 - s1);
     return 1;
 }
+// polygon_cut (polyiou.cpp:58-71). cross3(a, b, p[i]) is evaluated ONCE per vertex and reused as the `sj` of the
+// previous edge and as the s1 / s2 of lineCross (polyiou.cpp:31-40): the reference recomputes the same expression on
+// the same operands, so the values are identical and no rounding changes.
 __device__ __forceinline__ void clip_left(P2* p, int* n_io, P2 a, P2 b) {
     P2 tmp[24];
     int n = *n_io, m = 0;
     p[n] = p[0];
+    const float s_first = cross3(a, b, p[0]);
+    float s_cur = s_first;
+    int g_cur = sigf(s_cur);
     for (int i = 0; i < n; i++) {
-        const int si = sigf(cross3(a, b, p[i]));
-        const int sj = sigf(cross3(a, b, p[i + 1]));
-        if (si > 0) tmp[m++] = p[i];
-        if (si != sj) {
-            tmp[m].x = 0.f;  // defined where the reference reads an unwritten slot (see oracle header)
-            tmp[m].y = 0.f;
-            line_cross(a, b, p[i], p[i + 1], &tmp[m]);
-            m++;
+        const float s_nxt = (i + 1 == n) ? s_first : cross3(a, b, p[i + 1]);
+        const int g_nxt = sigf(s_nxt);
+        if (g_cur > 0) tmp[m++] = p[i];
+        if (g_cur != g_nxt) {
+            // lineCross(a, b, p[i], p[i+1]): both signs zero cannot happen here; an unwritten slot is (0, 0)
+            P2 x;
+            x.x = 0.f;
+            x.y = 0.f;
+            const float den = s_nxt - s_cur;
+            if (sigf(den) != 0) {
+                x.x = (p[i].x * s_nxt - p[i + 1].x * s_cur) / den;
+                x.y = (p[i].y * s_nxt - p[i + 1].y * s_cur) / den;
+            }
+            tmp[m++] = x;
         }
+        s_cur = s_nxt;
+        g_cur = g_nxt;
     }
     n = 0;
     for (int i = 0; i < m; i++)

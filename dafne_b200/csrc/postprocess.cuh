@@ -41,9 +41,8 @@ int launch_postprocess(const PostParams& p, cudaStream_t stream, int64_t* launch
 int postprocess_debug_counts(const void* scratch, int N, int L, const int* level_hw, int num_classes, int pre_nms_topk,
                              int32_t* host_out, cudaStream_t stream);
 
-// Synchronous diagnostic: work counters of the NMS of the last launch_postprocess, host_out[8] = pairs consulted /
-// pairs that needed the polygon clip / (pair, i, j) triangle items clipped, for the diagonal panels [0..2] and for the
-// broadcast of kept rows [3..5]; [6..7] reserved.
+// Synchronous diagnostic: work counters of the NMS of the last launch_postprocess, host_out[8]: pairs consulted /
+// pairs that needed the polygon clip for the diagonal panels [0], [1] and for the broadcast of kept rows [3], [4].
 int postprocess_debug_nms_stats(const void* scratch, int N, int L, const int* level_hw, int num_classes,
                                 int pre_nms_topk, unsigned long long* host_out, cudaStream_t stream);
 int nms_read_stats(const void* nms_scratch, int N, int max_sel, unsigned long long* host_out, cudaStream_t stream);

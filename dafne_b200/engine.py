@@ -234,8 +234,7 @@ class DafneEngine:
         """Work counters of the rotated NMS of the last post-processing (synchronises), summed over the batch."""
         arr = (C.c_uint64 * 8)()
         _capi.check(self.lib.dafne_debug_nms_stats(self._ctx, arr, _capi.stream_ptr()), "dafne_debug_nms_stats")
-        return dict(diag_pairs=arr[0], diag_clipped_pairs=arr[1], diag_triangle_items=arr[2], bcast_pairs=arr[3],
-                    bcast_clipped_pairs=arr[4], bcast_triangle_items=arr[5])
+        return dict(diag_pairs=arr[0], diag_clipped_pairs=arr[1], bcast_pairs=arr[3], bcast_clipped_pairs=arr[4])
 
     def stats(self, reset: bool = False) -> Tuple[int, float]:
         launches, flops = C.c_int64(), C.c_double()

@@ -130,10 +130,10 @@ int dafne_debug_activation(dafne_ctx* ctx, const char* name, const void** dev_pt
 int dafne_debug_post_counts(dafne_ctx* ctx, int32_t* host_out, void* stream);
 
 /* Work counters of the rotated NMS of the last dafne_postprocess / dafne_detect (synchronises the stream), summed over
- * the batch: host_out[0..2] = box pairs the greedy sweep consulted / pairs that needed the polygon clip / (pair, edge,
- * edge) triangle overlaps that ran the three half-plane clips, inside the 512-box diagonal panels; host_out[3..5] = the
- * same for the kept-rows x later-boxes broadcast; host_out[6..7] reserved. The reference's poly_gpu_nms evaluates
- * n * (n - 1) / 2 pairs x 16 triangle overlaps per image (nms.py:91). */
+ * the batch: host_out[0], [1] = box pairs the greedy sweep consulted / pairs that needed the polygon clip (16 triangle
+ * overlaps each) inside the 512-box diagonal panels; host_out[3], [4] = the same for the kept-rows x later-boxes
+ * broadcast; the other slots are reserved (0). The reference's poly_gpu_nms clips n * (n - 1) / 2 pairs per image
+ * (nms.py:91). */
 int dafne_debug_nms_stats(dafne_ctx* ctx, uint64_t* host_out, void* stream);
 
 /* Per-launch timing of the dense forward with CUDA events on the launching stream (bench.py's roofline numbers).

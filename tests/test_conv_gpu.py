@@ -29,6 +29,15 @@ CASES = [
     ("3x3_512_512", 1, 32, 32, 512, 512, 3, 1, {"scale": True, "shift": True, "relu": True}),
     ("1x1_1024_2048s2", 1, 16, 16, 1024, 2048, 1, 2, {"scale": True, "shift": True}),
     ("3x3_256_256_multiwave", 2, 128, 128, 256, 256, 3, 1, {"shift": True, "gn": True}),
+    # residual through the TMA ring (res_shift 0): ring wrap-around over many tiles per CTA, several n tiles,
+    # both epilogue configurations (K <= 256: two warpgroups; deeper K: one), every tile width, ragged edges
+    ("1x1_128_512_res_multiwave", 4, 128, 128, 128, 512, 1, 1, {"scale": True, "shift": True, "relu": True, "res": 0}),
+    ("1x1_512_2048_res_wgs1", 2, 64, 64, 512, 2048, 1, 1, {"scale": True, "shift": True, "relu": True, "res": 0}),
+    ("1x1_256_128_res_odd50", 2, 50, 50, 256, 128, 1, 1, {"scale": True, "shift": True, "relu": True, "res": 0}),
+    ("3x3_128_64_res_odd40", 1, 40, 40, 128, 64, 3, 1, {"scale": True, "shift": True, "res": 0}),
+    ("1x1_64_64_res_n3_30", 3, 30, 30, 64, 64, 1, 1, {"shift": True, "relu": True, "res": 0}),
+    ("1x1_256_1024_res_multiwave", 8, 64, 64, 256, 1024, 1, 1, {"scale": True, "shift": True, "relu": True, "res": 0}),
+    ("1x1_64_256_shortcut_multiwave", 2, 256, 256, 64, 256, 1, 1, {"scale": True, "shift": True}),
 ]
 
 
