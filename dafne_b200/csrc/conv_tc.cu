@@ -109,10 +109,40 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int lt) {
     return c;
 }
 
-template <int BLOCK_N, int EPI_WGS>
+// out[c], out[c+1] = fp16(relu?(acc * scale + shift (+ residual))) for the 64 channels of one chunk. The ReLU rides on
+// the conversion (cvt.rn.relu.f16x2.f32), the (scale, shift) pairs come as one 128-bit shared-memory broadcast per two
+// channels. Compile-time RELU / HAS_RES: the epilogue of the HBM-bound convolutions is issue-bound, so nothing that is
+// switched off may cost an instruction.
+template <bool RELU, bool HAS_RES>
+__device__ __forceinline__ void epilogue_chunk_math(const uint32_t (&v)[64], const float2* tab, const uint4 (&res)[8],
+                                                    uint32_t (&packed)[32]) {
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(res);
+#pragma unroll
+    for (int c = 0; c < 64; c += 2) {
+        const float4 tb = *reinterpret_cast<const float4*>(&tab[c]);  // (scale, shift) x 2
+        float a0 = fmaf(__uint_as_float(v[c]), tb.x, tb.y);
+        float a1 = fmaf(__uint_as_float(v[c + 1]), tb.z, tb.w);
+        if (HAS_RES) {
+            const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rw[c >> 1]));
+            a0 += rf.x;
+            a1 += rf.y;
+        }
+        uint32_t h;
+        if (RELU)
+            asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(a1), "f"(a0));
+        else
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(a1), "f"(a0));
+        packed[c >> 1] = h;
+    }
+}
+
+// MODE: what the epilogue does besides scale/shift/ReLU -- 0 nothing, 1 residual add (TMA ring when res_tma, else
+// per-thread loads of a nearest-upsampled residual), 2 GroupNorm statistics of the fp16-rounded output.
+template <int BLOCK_N, int EPI_WGS, int MODE>
 __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
     conv_tc_kernel(const ConvProblem* __restrict__ probs, int nprob, int total_tiles, int stages, int ring,
-                   int res_tma) {
+                   int res_tma_arg) {
+    const int res_tma = MODE == 1 ? res_tma_arg : 0;
     using Cfg = ConvCfg<BLOCK_N, EPI_WGS>;
     extern __shared__ __align__(1024) uint8_t smem[];
 
@@ -316,7 +346,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             const int x = x0 + rx, y = y0 + ry, n = n0 + rn;
             const bool valid = x < p.Wout && y < p.Hout && n < p.N;
             // residual read by the threads themselves: only the FPN top-down add (nearest-upsampled, res_shift == 1)
-            const bool res_ldg = BLOCK_N >= 64 && p.residual != nullptr && !res_tma;
+            const bool res_ldg = MODE == 1 && BLOCK_N >= 64 && p.residual != nullptr && !res_tma;
 
             const __half* res_row = nullptr;
             if (res_ldg)
@@ -378,36 +408,31 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                     }
-                    const bool has_res = res_ldg || res_tma;
                     uint32_t packed[32];
+                    if (MODE == 1) {
+                        if (p.relu)
+                            epilogue_chunk_math<true, true>(v, s_tab + chbase, res, packed);
+                        else
+                            epilogue_chunk_math<false, true>(v, s_tab + chbase, res, packed);
+                    } else {
+                        if (p.relu)
+                            epilogue_chunk_math<true, false>(v, s_tab + chbase, res, packed);
+                        else
+                            epilogue_chunk_math<false, false>(v, s_tab + chbase, res, packed);
+                    }
                     float gs[16];
+                    if (MODE == 2) {
+                        // statistics of what the next layer will read: the fp16-rounded values
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) gs[i] = 0.0f;
+                        for (int i = 0; i < 16; ++i) gs[i] = 0.0f;
 #pragma unroll
-                    for (int c = 0; c < 64; c += 2) {
-                        const float4 tb = *reinterpret_cast<const float4*>(&s_tab[chbase + c]);  // (scale, shift) x 2
-                        float a0 = fmaf(__uint_as_float(v[c]), tb.x, tb.y);
-                        float a1 = fmaf(__uint_as_float(v[c + 1]), tb.z, tb.w);
-                        if (has_res) {
-                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(res);
-                            const __half2 rh = *reinterpret_cast<const __half2*>(&rw[c >> 1]);
-                            const float2 rf = __half22float2(rh);
-                            a0 += rf.x;
-                            a1 += rf.y;
-                        }
-                        if (p.relu) {
-                            a0 = fmaxf(a0, 0.0f);
-                            a1 = fmaxf(a1, 0.0f);
-                        }
-                        const __half2 h = __floats2half2_rn(a0, a1);
-                        packed[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-                        if (p.gn_sums != nullptr) {
-                            const float2 f = __half22float2(h);  // statistics of what the next layer will read
+                        for (int c = 0; c < 64; c += 2) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&packed[c >> 1]));
                             gs[(c >> 3) * 2] += f.x + f.y;
                             gs[(c >> 3) * 2 + 1] += f.x * f.x + f.y * f.y;
                         }
                     }
-                    if (p.gn_sums != nullptr) {
+                    if (MODE == 2 && p.gn_sums != nullptr) {
                         // Per-pixel partials (fixed 8-channel order) become 64-bit fixed point BEFORE any cross-thread
                         // reduction: integer addition is associative, so the statistics are bit-identical from run
                         // to run and independent of tiling / batch composition (no float atomics).
@@ -691,6 +716,11 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     }
     plan->prob.tmRes = plan->prob.tmOut;
     plan->res_tma = 0;
+    plan->mode = d.residual != nullptr ? 1 : (d.gn_sums != nullptr ? 2 : 0);
+    if (d.residual != nullptr && d.gn_sums != nullptr) {
+        set_error("conv_tc: residual and GroupNorm statistics in one convolution are not supported");
+        return -1;
+    }
     if (!small && d.residual != nullptr && d.res_shift == 0) {
         if (d.res_H != d.Hout || d.res_W != d.Wout) {
             set_error("conv_tc: residual %dx%d does not match the output %dx%d", d.res_H, d.res_W, d.Hout, d.Wout);
@@ -726,16 +756,16 @@ static void conv_smem_config(int res_tma, int* stages, int* ring) {
     *ring = r;
 }
 
-template <int BN, int WGS>
+template <int BN, int WGS, int MODE>
 static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, int res_tma,
                      cudaStream_t stream) {
     using Cfg = ConvCfg<BN, WGS>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, WGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kMaxSmem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, WGS, MODE>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(conv_tc_kernel<%d,%d>, smem=%d): %s", BN, WGS, kMaxSmem,
+            set_error("cudaFuncSetAttribute(conv_tc_kernel<%d,%d,%d>, smem=%d): %s", BN, WGS, MODE, kMaxSmem,
                       cudaGetErrorString(e));
             return -1;
         }
@@ -749,17 +779,27 @@ static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, i
                   ring, smem);
         return -1;
     }
-    conv_tc_kernel<BN, WGS><<<grid, Cfg::THREADS, smem, stream>>>(dev_probs, nprob, total_tiles, stages, ring, res_tma);
+    conv_tc_kernel<BN, WGS, MODE>
+        <<<grid, Cfg::THREADS, smem, stream>>>(dev_probs, nprob, total_tiles, stages, ring, res_tma);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-        set_error("conv_tc_kernel<%d,%d> launch: %s", BN, WGS, cudaGetErrorString(e));
+        set_error("conv_tc_kernel<%d,%d,%d> launch: %s", BN, WGS, MODE, cudaGetErrorString(e));
         return -1;
     }
     return 0;
 }
 
-int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int epi_wgs, int res_tma,
-                      int num_sms, cudaStream_t stream) {
+template <int BN, int WGS>
+static int launch_mode(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, int mode, int res_tma,
+                       cudaStream_t stream) {
+    if (mode == 1) return launch_bn<BN, WGS, 1>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
+    if (mode == 0) return launch_bn<BN, WGS, 0>(dev_probs, nprob, total_tiles, grid, 0, stream);
+    set_error("conv_tc: epilogue mode %d is not built for tile width %d / %d epilogue warpgroups", mode, BN, WGS);
+    return -1;
+}
+
+int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int epi_wgs, int mode,
+                      int res_tma, int num_sms, cudaStream_t stream) {
     if (total_tiles == 0) return 0;
     if (nprob < 1 || nprob > kMaxConvProblems) {
         set_error("conv_tc: %d problems in one launch (1..%d supported)", nprob, kMaxConvProblems);
@@ -767,15 +807,22 @@ int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, 
     }
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     const int key = block_n * 10 + epi_wgs;
+    if (mode == 2) {
+        // GroupNorm statistics: only the 256-wide tower convolutions produce them
+        if (key == 2561) return launch_bn<256, 1, 2>(dev_probs, nprob, total_tiles, grid, 0, stream);
+        if (key == 2562) return launch_bn<256, 2, 2>(dev_probs, nprob, total_tiles, grid, 0, stream);
+        set_error("conv_tc: GroupNorm statistics need Cout %% 256 == 0 (tile width %d)", block_n);
+        return -1;
+    }
     switch (key) {
-        case 161: return launch_bn<16, 1>(dev_probs, nprob, total_tiles, grid, 0, stream);
-        case 321: return launch_bn<32, 1>(dev_probs, nprob, total_tiles, grid, 0, stream);
-        case 641: return launch_bn<64, 1>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
-        case 642: return launch_bn<64, 2>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
-        case 1281: return launch_bn<128, 1>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
-        case 1282: return launch_bn<128, 2>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
-        case 2561: return launch_bn<256, 1>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
-        case 2562: return launch_bn<256, 2>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
+        case 161: return launch_bn<16, 1, 0>(dev_probs, nprob, total_tiles, grid, 0, stream);
+        case 321: return launch_bn<32, 1, 0>(dev_probs, nprob, total_tiles, grid, 0, stream);
+        case 641: return launch_mode<64, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
+        case 642: return launch_mode<64, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
+        case 1281: return launch_mode<128, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
+        case 1282: return launch_mode<128, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
+        case 2561: return launch_mode<256, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
+        case 2562: return launch_mode<256, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
     }
     set_error("conv_tc: unsupported tile width %d with %d epilogue warpgroups", block_n, epi_wgs);
     return -1;
