@@ -92,8 +92,10 @@ __device__ __forceinline__ void stage_oriented(const float* __restrict__ src, fl
 // One queued pair is evaluated by 16 consecutive lanes, lane k = 4*i + j computing the signed overlap of edge
 // triangle i of P with edge triangle j of Q; the group leader then adds the 16 terms in the reference's order
 // (i outer, j inner) and finishes the IoU with the algorithm's own a1, a2. Returns IoU > thr on the leader lane.
+// (One pair per THREAD with all lanes on the same (i, j) was measured too: lanes agree even less on the clipper's
+// branches across pairs than across a pair's sixteen terms, and the CTA waits for its slowest thread -- 7 % slower.)
 __device__ __forceinline__ bool pair_suppresses_16(const float* P, const float* Q, float a1, float a2, float thr,
-                                                   bool active, unsigned lane) {
+                                                   bool active, unsigned lane, float2* slots, int stride) {
     float val = 0.f;
     if (active) {
         const int i = (lane >> 2) & 3, j = lane & 3;
@@ -106,7 +108,7 @@ __device__ __forceinline__ bool pair_suppresses_16(const float* P, const float* 
         c.y = Q[2 * j + 1];
         d.x = Q[2 * ((j + 1) & 3)];
         d.y = Q[2 * ((j + 1) & 3) + 1];
-        val = tri_overlap(a, b, c, d);
+        val = tri_overlap(a, b, c, d, slots, stride);
     }
     float inter = 0.f;
 #pragma unroll
@@ -128,6 +130,7 @@ struct DiagSmem {
     int qn;
     int last;
     unsigned stat_pairs;
+    float2 poly[9 * kDiagThreads];  // tri_overlap's per-thread polygon columns
 };
 
 // Appends `want` lanes' entries to a shared-memory queue with one atomic per warp. All 32 lanes must call it.
@@ -215,7 +218,8 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
             const int e = e0 + (t >> 4);
             const bool active = e < qn;
             const int r = active ? sm.queue[e] >> 6 : 0, j = active ? sm.queue[e] & 63 : 0;
-            const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active, lane);
+            const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active,
+                                                lane, sm.poly + t, kDiagThreads);
             if (hit && (lane & 15) == 0) atomicOr(&sm.bits[r], 1ull << j);
         }
         __syncthreads();
@@ -300,6 +304,7 @@ struct BcastSmem {
     int rows[kRowChunk];
     int qn;
     unsigned stat_pairs;
+    float2 poly[9 * kBcastThreads];  // tri_overlap's per-thread polygon columns
 };
 
 // grid (column chunks after the panel, row chunks of the panel's kept rows, N), 256 threads
@@ -393,7 +398,8 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
         bool active = e < qn;
         const int r = active ? sm.queue[e] >> 7 : 0, j = active ? sm.queue[e] & 127 : 0;
         if (active && sm.newdead[j]) active = false;  // benign race: any kept row that hits is enough
-        const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active, lane);
+        const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active,
+                                            lane, sm.poly + t, kBcastThreads);
         if (hit && (lane & 15) == 0) sm.newdead[j] = 1;
     }
     if (t == 0) {

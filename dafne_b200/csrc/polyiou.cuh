@@ -31,23 +31,124 @@ __device__ __forceinline__ float signed_area(P2* ps, int n) {
     for (int i = 0; i < n; i++) acc += ps[i].x * ps[i + 1].y - ps[i].y * ps[i + 1].x;
     return acc / 2.0f;
 }
-__device__ __forceinline__ int line_cross(P2 a, P2 b, P2 c, P2 d, P2* out) {
-    const float s1 = cross3(a, b, c);
-    const float s2 = cross3(a, b, d);
-    if (sigf(s1) == 0 && sigf(s2) == 0) return 2;
-    if (sigf(s2 - s1) == 0) return 0;
-    out->x = (c.x * s2 - d.x * s1) / (s2 - s1);
-    out->y = (c.y * s2 - d.y * s1) / (s2 - s1);
-    return 1;
+// ------------------------------------------------------------------------------------------------ polygon_cut
+// polygon_cut (polyiou.cpp:58-71) restated for the GPU without changing one rounding:
+//   * cross3(a, b, p[i]) is evaluated ONCE per vertex and reused as the `sj` of the previous edge and as the s1 / s2
+//     of lineCross (polyiou.cpp:31-40) -- the reference recomputes the same expression on the same operands;
+//   * sizes are static: a polygon of n vertices leaves polygon_cut with at most (#vertices kept) + (#sign changes)
+//     <= n + n/2 points, so the three cuts of a triangle see at most 3 -> 4 -> 6 -> 9 vertices. Every loop is
+//     unrolled over that bound with an `i < n` guard, the input polygon sits in registers, and the de-duplication
+//     (polyiou.cpp:66-70) is streamed: each emitted point is compared with the point emitted before it and, if kept,
+//     stored to the thread's private shared-memory column slots[k * stride] -- the only dynamically indexed access;
+//   * the slot lineCross leaves unwritten when its denominator vanishes is (0, 0) (see oracle header).
+// num / den, correctly rounded like the plain operator (den != 0 here). A ZERO numerator is the common case -- every
+// crossing with an edge that starts or ends in the origin has the form (0 * s2 - v * 0) / (s2 - s1) -- and sends the
+// hardware's division straight into its ~35-instruction slow path; IEEE gives it the value 0 with the sign
+// sign(num) ^ sign(den) (den == den excludes a NaN denominator, for which the quotient is NaN).
+__device__ __forceinline__ float div_exact(float num, float den) {
+    if (num == 0.f && den == den)
+        return __int_as_float((__float_as_int(num) ^ __float_as_int(den)) & static_cast<int>(0x80000000u));
+    return num / den;
 }
-// polygon_cut (polyiou.cpp:58-71). cross3(a, b, p[i]) is evaluated ONCE per vertex and reused as the `sj` of the
-// previous edge and as the s1 / s2 of lineCross (polyiou.cpp:31-40): the reference recomputes the same expression on
-// the same operands, so the values are identical and no rounding changes.
-__device__ __forceinline__ void clip_left(P2* p, int* n_io, P2 a, P2 b) {
-    P2 tmp[24];
-    int n = *n_io, m = 0;
+
+struct PolyEmit {
+    float2* slots;
+    int stride;
+    int cnt, n;
+    P2 prev, first, last;
+    __device__ __forceinline__ void put(P2 e) {
+        const bool keep = cnt == 0 || !same_pt(e, prev);  // tmp[i] vs tmp[i-1]
+        if (keep) {
+            slots[n * stride] = make_float2(e.x, e.y);
+            if (n == 0) first = e;
+            last = e;
+            ++n;
+        }
+        prev = e;
+        ++cnt;
+    }
+};
+
+// Cuts the polygon p[0..n) (n <= NI, in registers) by the left half-plane of a->b; the result (<= NI + NI/2 points)
+// is written to slots[0 .. return) in order.
+template <int NI>
+__device__ __forceinline__ int clip_left_static(const P2 (&p)[NI], int n, P2 a, P2 b, float2* slots, int stride) {
+    float s[NI];
+    int g[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        s[i] = cross3(a, b, p[i]);
+        g[i] = sigf(s[i]);
+    }
+    PolyEmit em;
+    em.slots = slots;
+    em.stride = stride;
+    em.cnt = 0;
+    em.n = 0;
+    em.prev = p[0];
+    em.first = p[0];
+    em.last = p[0];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        if (i < n) {
+            // successor: i + 1, or vertex 0 after the last one (p[n] = p[0], polyiou.cpp:60)
+            const bool wrap = (i + 1 >= NI) || (i + 1 >= n);
+            const float s_nxt = wrap ? s[0] : s[(i + 1) % NI];
+            const int g_nxt = wrap ? g[0] : g[(i + 1) % NI];
+            if (g[i] > 0) em.put(p[i]);
+            if (g[i] != g_nxt) {
+                const P2 q = wrap ? p[0] : p[(i + 1) % NI];
+                P2 x;
+                x.x = 0.f;
+                x.y = 0.f;
+                const float den = s_nxt - s[i];
+                if (sigf(den) != 0) {
+                    x.x = div_exact(p[i].x * s_nxt - q.x * s[i], den);
+                    x.y = div_exact(p[i].y * s_nxt - q.y * s[i], den);
+                }
+                em.put(x);
+            }
+        }
+    }
+    int m = em.n;
+    // while (n > 1 && p[n-1] == p[0]) n--   (polyiou.cpp:70); the first round runs on registers
+    if (m > 1 && same_pt(em.last, em.first)) {
+        --m;
+        while (m > 1) {
+            const float2 l = slots[(m - 1) * stride];
+            P2 lp;
+            lp.x = l.x;
+            lp.y = l.y;
+            if (!same_pt(lp, em.first)) break;
+            --m;
+        }
+    }
+    return m;
+}
+
+template <int NI>
+__device__ __forceinline__ void load_poly(P2 (&p)[NI], int n, const float2* slots, int stride) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        float2 v = make_float2(0.f, 0.f);
+        if (i < n) v = slots[i * stride];
+        p[i].x = v.x;
+        p[i].y = v.y;
+    }
+}
+
+// The same cut for a polygon of any size the algorithm can produce (<= 9 in, <= 13 out), looping over local arrays.
+// Only the rare polygons that outgrow the static bounds chosen in tri_overlap come here.
+static __device__ __noinline__ int clip_left_generic(float2* slots, int stride, int n, P2 a, P2 b) {
+    P2 p[10], tmp[14];
+    for (int i = 0; i < n; ++i) {
+        const float2 v = slots[i * stride];
+        p[i].x = v.x;
+        p[i].y = v.y;
+    }
+    int m = 0;
     p[n] = p[0];
-    const float s_first = cross3(a, b, p[0]);
+    const float s_first = n > 0 ? cross3(a, b, p[0]) : 0.f;
     float s_cur = s_first;
     int g_cur = sigf(s_cur);
     for (int i = 0; i < n; i++) {
@@ -55,14 +156,13 @@ __device__ __forceinline__ void clip_left(P2* p, int* n_io, P2 a, P2 b) {
         const int g_nxt = sigf(s_nxt);
         if (g_cur > 0) tmp[m++] = p[i];
         if (g_cur != g_nxt) {
-            // lineCross(a, b, p[i], p[i+1]): both signs zero cannot happen here; an unwritten slot is (0, 0)
             P2 x;
             x.x = 0.f;
             x.y = 0.f;
             const float den = s_nxt - s_cur;
             if (sigf(den) != 0) {
-                x.x = (p[i].x * s_nxt - p[i + 1].x * s_cur) / den;
-                x.y = (p[i].y * s_nxt - p[i + 1].y * s_cur) / den;
+                x.x = div_exact(p[i].x * s_nxt - p[i + 1].x * s_cur, den);
+                x.y = div_exact(p[i].y * s_nxt - p[i + 1].y * s_cur, den);
             }
             tmp[m++] = x;
         }
@@ -73,9 +173,17 @@ __device__ __forceinline__ void clip_left(P2* p, int* n_io, P2 a, P2 b) {
     for (int i = 0; i < m; i++)
         if (i == 0 || !same_pt(tmp[i], tmp[i - 1])) p[n++] = tmp[i];
     while (n > 1 && same_pt(p[n - 1], p[0])) n--;
-    *n_io = n;
+    for (int i = 0; i < n; ++i) slots[i * stride] = make_float2(p[i].x, p[i].y);
+    return n;
 }
-__device__ __forceinline__ float tri_overlap(P2 a, P2 b, P2 c, P2 d) {
+
+// Signed overlap of triangles (O, a, b) and (O, c, d), O = origin (polyiou.cpp:74-89). `slots` is this thread's
+// private column of >= 9 float2 in shared memory, `stride` elements apart.
+//
+// Static bounds: the first cut leaves [~O, v1, v2] (3 points) unless a vertex lies exactly on the ray, the second 3-4
+// points, the third 3-5; those sizes get fully unrolled code (3 / 3 / 4 input vertices, 5 for the area), anything
+// larger -- still the same arithmetic -- takes the looping fallback.
+__device__ __forceinline__ float tri_overlap(P2 a, P2 b, P2 c, P2 d, float2* slots, int stride) {
     P2 o;
     o.x = 0.f;
     o.y = 0.f;
@@ -96,15 +204,51 @@ __device__ __forceinline__ float tri_overlap(P2 a, P2 b, P2 c, P2 d) {
     // O->c, the first clip keeps no vertex and both intersection points it appends are exactly (0,0)
     // ((0*s2 - v*0)/(s2 - 0)); every later clip then sees a single zero point and the area is exactly 0.
     if (sigf(c.x * a.y - a.x * c.y) < 0 && sigf(c.x * b.y - b.x * c.y) < 0) return 0.f;
-    P2 p[12];
-    int n = 3;
-    p[0] = o;
-    p[1] = a;
-    p[2] = b;
-    clip_left(p, &n, o, c);
-    clip_left(p, &n, c, d);
-    clip_left(p, &n, d, o);
-    float res = fabsf(signed_area(p, n));
+    int n;
+    {
+        P2 p3[3];
+        p3[0] = o;
+        p3[1] = a;
+        p3[2] = b;
+        n = clip_left_static<3>(p3, 3, o, c, slots, stride);
+    }
+    if (n <= 3) {
+        P2 p3[3];
+        load_poly<3>(p3, n, slots, stride);
+        n = clip_left_static<3>(p3, n, c, d, slots, stride);
+    } else {
+        n = clip_left_generic(slots, stride, n, c, d);
+    }
+    if (n <= 4) {
+        P2 p4[4];
+        load_poly<4>(p4, n, slots, stride);
+        n = clip_left_static<4>(p4, n, d, o, slots, stride);
+    } else {
+        n = clip_left_generic(slots, stride, n, d, o);
+    }
+    // shoelace over the closed polygon (polyiou.cpp:23-30)
+    float acc = 0.f;
+    if (n <= 5) {
+        P2 q[5];
+        load_poly<5>(q, n, slots, stride);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            if (i < n) {
+                const bool wrap = (i + 1 >= 5) || (i + 1 >= n);
+                const P2 nx = wrap ? q[0] : q[(i + 1) % 5];
+                acc += q[i].x * nx.y - q[i].y * nx.x;
+            }
+        }
+    } else {
+        const float2 q0 = slots[0];
+        float2 cur = q0;
+        for (int i = 0; i < n; ++i) {
+            const float2 nx = (i + 1 == n) ? q0 : slots[(i + 1) * stride];
+            acc += cur.x * nx.y - cur.y * nx.x;
+            cur = nx;
+        }
+    }
+    float res = fabsf(acc / 2.0f);
     if (s1 * s2 == -1) res = -res;
     return res;
 }
@@ -123,13 +267,13 @@ __device__ __forceinline__ void load_oriented(const float* pa, P2* p) {
     }
     p[4] = p[0];
 }
-static __device__ __noinline__ float iou_poly_f32(const float* pa, const float* qa) {
+static __device__ __noinline__ float iou_poly_f32(const float* pa, const float* qa, float2* slots, int stride) {
     P2 p[6], q[6];
     load_oriented(pa, p);
     load_oriented(qa, q);
     float inter = 0.f;
     for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) inter += tri_overlap(p[i], p[i + 1], q[j], q[j + 1]);
+        for (int j = 0; j < 4; j++) inter += tri_overlap(p[i], p[i + 1], q[j], q[j + 1], slots, stride);
     const float a1 = fabsf(signed_area(p, 4));
     const float a2 = fabsf(signed_area(q, 4));
     const float uni = a1 + a2 - inter;
@@ -236,13 +380,6 @@ __device__ __forceinline__ bool pair_inter_is_zero(const NmsAux& P, const NmsAux
         return lhs > rhs;
     }
     return false;
-}
-
-// Decision IoU(P, Q) > thr with the pre-filter in front (bit-identical decisions to iou_poly_f32(...) > thr).
-__device__ __forceinline__ bool suppresses(const float* pbox, const NmsAux& P, const float* qbox, const NmsAux& Q,
-                                           float thr) {
-    if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) return false;  // IoU = 0 / (a1 + a2) = 0 <= thr
-    return iou_poly_f32(pbox, qbox) > thr;
 }
 
 }  // namespace dafne

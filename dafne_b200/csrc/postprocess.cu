@@ -39,8 +39,9 @@ constexpr int kDet = 20;
 // polygon IoU arithmetic: polyiou.cuh (shared with nms.cu)
 __global__ void poly_iou_kernel(const float* __restrict__ p, const float* __restrict__ q, float* __restrict__ out,
                                 int n) {
+    __shared__ float2 slots[9 * 64];  // launched with 64 threads: one private column of 9 points per thread
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = iou_poly_f32(p + 8 * i, q + 8 * i);
+    if (i < n) out[i] = iou_poly_f32(p + 8 * i, q + 8 * i, slots + threadIdx.x, 64);
 }
 __global__ void pair_filter_kernel(const float* __restrict__ p, const float* __restrict__ q,
                                    unsigned char* __restrict__ fired, int n) {
