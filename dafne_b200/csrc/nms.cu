@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
                 if (want) {
                     ++npairs;
                     const NmsAux& Q = sm.caux[j];
-                    if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) want = false;
+                    if (pair_inter_is_zero(P, Q, sm.rbox[r], sm.cbox[j]) && (P.area + Q.area) != 0.f) want = false;
                 }
                 queue_push(sm.queue, &sm.qn, want, static_cast<unsigned short>((r << 6) | j), lane);
             }
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
             if (want) {
                 ++npairs;
                 const NmsAux& P = sm.raux[r];
-                if (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) want = false;
+                if (pair_inter_is_zero(P, Q, sm.rbox[r], sm.cbox[j]) && (P.area + Q.area) != 0.f) want = false;
             }
             queue_push(sm.queue, &sm.qn, want, static_cast<unsigned short>((r << 7) | j), lane);
         }

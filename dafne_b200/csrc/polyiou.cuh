@@ -368,18 +368,55 @@ __device__ __forceinline__ NmsAux nms_aux_of(const float* box) {
     return a;
 }
 
-// true => the faithful arithmetic gives inter == 0 exactly for IoU(P = higher-scored box, Q = lower-scored box)
-__device__ __forceinline__ bool pair_inter_is_zero(const NmsAux& P, const NmsAux& Q) {
+// true => the faithful arithmetic gives inter == 0 exactly for IoU(P = higher-scored box, Q = lower-scored box).
+// pbox / qbox: the boxes (re)oriented like iou_poly_f32 does (load_oriented), 8 floats each.
+//
+// Case A'' (tight form of A'): the margin `ext` of case A' only pays for intersection points that EXTRAPOLATE an edge
+// of P, and lineCross extrapolates only when it is called for a vertex whose cross3(c, d, v) lies within eps of 0 (sign
+// class 0 next to a sign class +-1 of the same numeric sign). If no vertex of P is within eps of any oriented edge
+// line of Q -- checked below with the very expression polygon_cut evaluates -- every intersection point of the second
+// cut is a convex combination of two consecutive vertices (weights s2/(s2-s1), -s1/(s2-s1) in (0,1), no cancellation
+// in numerator or denominator, relative error <= 4.5 u), stays inside P's t-interval, and the inequality of case A'
+// holds with ext = 0.
+__device__ __forceinline__ bool pair_inter_is_zero(const NmsAux& P, const NmsAux& Q, const float* pbox,
+                                                   const float* qbox) {
     if (P.thi + 1.0e-5f < Q.tlo) return true;  // case A
-    const float gapx = (P.tlo - Q.thi) - 4.0e-6f - P.ext;
-    if (gapx > 0.f) {  // case A'
-        const float kmin = Q.kq / (Q.kq + 1.002f * (P.smax + Q.smax));
-        const float rho = Q.smax / P.sminx;
-        const float lhs = kmin * (0.5f * gapx - 2.4e-7f) * 0.999f;
-        const float rhs = 2.4e-7f * (4.0f * P.smax / P.sminx + rho + 2.0f) + 5.0e-9f;
-        return lhs > rhs;
+    const float gap0 = (P.tlo - Q.thi) - 4.0e-6f;
+    if (!(gap0 > 0.f)) return false;
+    const float kmin = Q.kq / (Q.kq + 1.002f * (P.smax + Q.smax));
+    const float rho = Q.smax / P.sminx;
+    const float rhs = 2.4e-7f * (4.0f * P.smax / P.sminx + rho + 2.0f) + 5.0e-9f;
+    const float gapx = gap0 - P.ext;
+    if (gapx > 0.f && kmin * (0.5f * gapx - 2.4e-7f) * 0.999f > rhs) return true;  // case A'
+    if (!(P.ext < INFINITY)) return false;                                           // sminx is not a bound
+    if (!(kmin * (0.5f * gap0 - 2.4e-7f) * 0.999f > rhs)) return false;
+    // case A'': no vertex of P within eps of an oriented edge line of Q
+    P2 o;
+    o.x = 0.f;
+    o.y = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        P2 c, d;
+        c.x = qbox[2 * j];
+        c.y = qbox[2 * j + 1];
+        d.x = qbox[2 * ((j + 1) & 3)];
+        d.y = qbox[2 * ((j + 1) & 3) + 1];
+        const int s2 = sigf(cross3(o, c, d));
+        if (s2 == 0) continue;  // tri_overlap returns 0 for this edge before any cut
+        if (s2 == -1) {
+            const P2 t = c;
+            c = d;
+            d = t;
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            P2 pv;
+            pv.x = pbox[2 * v];
+            pv.y = pbox[2 * v + 1];
+            if (sigf(cross3(c, d, pv)) == 0) return false;
+        }
     }
-    return false;
+    return true;
 }
 
 }  // namespace dafne

@@ -54,7 +54,18 @@ __global__ void pair_filter_kernel(const float* __restrict__ p, const float* __r
         b[k] = q[8 * i + k];
     }
     const NmsAux P = nms_aux_of(a), Q = nms_aux_of(b);
-    fired[i] = (pair_inter_is_zero(P, Q) && (P.area + Q.area) != 0.f) ? 1 : 0;
+    P2 pp[6], qq[6];
+    load_oriented(a, pp);
+    load_oriented(b, qq);
+    float po[8], qo[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        po[2 * k] = pp[k].x;
+        po[2 * k + 1] = pp[k].y;
+        qo[2 * k] = qq[k].x;
+        qo[2 * k + 1] = qq[k].y;
+    }
+    fired[i] = (pair_inter_is_zero(P, Q, po, qo) && (P.area + Q.area) != 0.f) ? 1 : 0;
 }
 int launch_pair_filter(const float* p, const float* q, unsigned char* fired, int n, cudaStream_t s) {
     if (n <= 0) return 0;

@@ -72,8 +72,8 @@ def _rot_rects_t(gen, n, wmin, wmax, aspect, cx, cy, dev):
     return torch.stack([x, y], 2).reshape(n, 8).float().contiguous()
 
 
-@pytest.mark.parametrize("regime", ["same_class", "cross_class", "near_margin", "integer_grid", "tiny_boxes",
-                                    "huge_boxes", "near_origin", "degenerate"])
+@pytest.mark.parametrize("regime", ["same_class", "cross_class", "near_margin", "angular_touch", "integer_grid",
+                                    "tiny_boxes", "huge_boxes", "near_origin", "degenerate"])
 def test_nms_prefilter_never_skips_a_nonzero_iou(regime):
     """Contract of polyiou.cuh::pair_inter_is_zero: wherever the NMS skips the polygon clip, the faithful fp32
     arithmetic (dafne_poly_iou == the oracle's float instantiation, bit for bit) yields EXACTLY 0 -- including the
@@ -100,6 +100,15 @@ def test_nms_prefilter_never_skips_a_nonzero_iou(regime):
         p = _rot_rects_t(gen, n, 20, 60, 3.0, cx, cy, dev)
         ang, dist = U(0, 6.2832), U(0, 250)
         q = _rot_rects_t(gen, n, 20, 60, 3.0, cx + dist * torch.cos(ang), cy + dist * torch.sin(ang), dev)
+    elif regime == "angular_touch":  # q next to p's cone seen from the origin (tiny angular gaps either side), any radius
+        off = torch.randint(0, 15, (n,), generator=gen, device=dev).float() * span
+        cx, cy = U(0, 1024) + off, U(0, 1024) + off
+        p = _rot_rects_t(gen, n, 20, 100, 3.0, cx, cy, dev)
+        r = torch.sqrt(cx * cx + cy * cy)
+        tang, rad = U(-160, 160), U(-900, 900)  # tangential shift of about one box, radial shift across classes
+        scale = (r + rad).clamp(min=40.0) / r
+        qx, qy = cx * scale - cy / r * tang, cy * scale + cx / r * tang
+        q = _rot_rects_t(gen, n, 20, 100, 3.0, qx.clamp(min=60.0), qy.clamp(min=60.0), dev)
     elif regime == "integer_grid":  # axis-aligned integer boxes: exactly collinear edges, exact zeros in the clips
         off = torch.randint(0, 15, (n,), generator=gen, device=dev).float() * 1024.0
 
