@@ -64,8 +64,63 @@ def ncu(src, dst):
     print(open(dst).read())
 
 
+def tensor_pipe(csv_path, per_launch_json, dst, first_global_index, launches_per_forward=71):
+    """ncu per-launch tensor-pipe utilisation of the conv / stem kernels of one forward, labelled with the layer names
+    of bench.py's per-launch profile (same launch order), FLOP-weighted per group."""
+    import json
+
+    rows = [l for l in open(csv_path) if not l.startswith("==")]
+    by = collections.OrderedDict()
+    for x in csv.DictReader(rows):
+        by.setdefault(int(x["ID"]), {"kernel": x["Kernel Name"]})[x["Metric Name"]] = float(x["Metric Value"].replace(",", ""))
+    ops = [o for o in json.load(open(per_launch_json)) if o["kind"] in (1, 2)]
+    assert len(ops) == launches_per_forward, (len(ops), launches_per_forward)
+    seen = {}
+    for k, m in by.items():
+        op = (first_global_index + k) % launches_per_forward
+        seen.setdefault(op, m)
+    groups = collections.OrderedDict()
+    lines = []
+    for i, o in enumerate(ops):
+        m = seen.get(i)
+        if m is None:
+            continue
+        nm = o["name"]
+        g = ("head towers" if "tower" in nm else "head predictions" if nm.startswith("pred") else
+             "FPN + P6/P7" if ("fpn" in nm or "top_block" in nm) else "stem" if nm == "stem" else "ResNet " + nm.split("bottom_up.")[-1].split(".")[0])
+        tp = m["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+        us = m["gpu__time_duration.sum"] / 1e3
+        dram = (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) / 1e6
+        a = groups.setdefault(g, [0.0, 0.0, 0.0, 0.0, 0])
+        a[0] += o["flops"]
+        a[1] += o["flops"] * tp
+        a[2] += us
+        a[3] += dram
+        a[4] += 1
+        lines.append(f"| `{nm[-40:]}` | {m['kernel'].split('(')[0].replace('void ', '')} | {us:.1f} | {tp:.1f} | "
+                     f"{o['flops'] / us / 1e6:.0f} | {dram:.1f} | {m['dram__throughput.avg.pct_of_peak_sustained_elapsed']:.0f} |")
+    with open(dst, "w") as f:
+        f.write(f"# Tensor-pipe utilisation per convolution launch, one forward (source `{csv_path}`)\n\n"
+                "`ncu --metrics sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum,dram__bytes_*` "
+                "(`--clock-control none`; serialised, cold caches: durations are upper bounds)\n\n"
+                "## FLOP-weighted per group\n\n| group | launches | GFLOP | us (ncu) | tensor pipe % (FLOP-weighted) | TFLOP/s | DRAM MB |\n|---|---|---|---|---|---|---|\n")
+        tot = [0.0, 0.0, 0.0]
+        for g, a in groups.items():
+            f.write(f"| {g} | {a[4]} | {a[0] / 1e9:.1f} | {a[2]:.0f} | {a[1] / a[0]:.1f} | {a[0] / a[2] / 1e6:.0f} | {a[3]:.0f} |\n")
+        bb = [a for g, a in groups.items() if g.startswith("ResNet") or g.startswith("FPN")]
+        if bb:
+            fl = sum(a[0] for a in bb)
+            f.write(f"| **backbone + FPN** | {sum(a[4] for a in bb)} | {fl / 1e9:.1f} | {sum(a[2] for a in bb):.0f} | "
+                    f"**{sum(a[1] for a in bb) / fl:.1f}** | {fl / sum(a[2] for a in bb) / 1e6:.0f} | {sum(a[3] for a in bb):.0f} |\n")
+        f.write("\n## Per launch\n\n| layer | kernel | us | tensor pipe % | TFLOP/s | DRAM MB | DRAM % of peak |\n|---|---|---|---|---|---|---|\n")
+        f.write("\n".join(lines) + "\n")
+    print(open(dst).read()[:3000])
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 3)
+    elif sys.argv[1] == "tensor_pipe":
+        tensor_pipe(sys.argv[2], sys.argv[3], sys.argv[4], int(sys.argv[5]))
     else:
         ncu(sys.argv[2], sys.argv[3])
