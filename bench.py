@@ -5,8 +5,9 @@
 
 A "step" = one pass of the hot path (normalise -> ResNet+FPN -> head -> threshold/top-k/decode/rotated NMS) over one
 batch of synthetic 1024x1024x3 uint8 images. `value` = images/s with the inputs already resident in HBM; `e2e` = the
-same through the reference-facing C-ABI call `dafne_detect_host` with HOST buffers (H2D of the images and D2H of the
-detections inside the timed region). Under torchrun every rank runs its own shard of the batch (weak scaling) and a
+same through the reference-facing C-ABI call with HOST buffers, `dafne_detect_host` in its pipelined form
+(`dafne_detect_host_begin` / `_end`, two batches in flight): H2D of every step's images and D2H of its detections are
+inside the timed region, the copy of step i+1 overlapping the compute of step i. Under torchrun every rank runs its own shard of the batch (weak scaling) and a
 step ends with ONE all-gather of the fixed-shape detections.
 
 `--impl reference` times the reference's CPU implementation of the same path on the host cores. detectron2 / poly_nms
@@ -190,8 +191,9 @@ def run_ours(args):
     host_sets = [torch.randint(0, 256, (batch, 3, H, W), dtype=torch.uint8, generator=g).pin_memory()
                  for _ in range(n_sets)]
     dev_sets = [h.to(dev) for h in host_sets]
-    host_dets = torch.empty(batch, cap, DET, dtype=torch.float32).pin_memory()
-    host_counts = torch.empty(batch, dtype=torch.int32).pin_memory()
+    # two result buffers: the reference-facing host call is used in its pipelined form (two batches in flight)
+    host_dets = [torch.empty(batch, cap, DET, dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_counts = [torch.empty(batch, dtype=torch.int32).pin_memory() for _ in range(2)]
     gathered = gathered_counts = None
     if world > 1:
         gathered = torch.empty(world * batch, cap, DET, dtype=torch.float32, device=dev)
@@ -204,23 +206,37 @@ def run_ours(args):
             dist.all_gather_into_tensor(gathered_counts, counts)
         return dets, counts
 
-    def step_host(i):
-        eng.detect_host(host_sets[i % n_sets], sizes, None, host_dets, host_counts, cap)
+    def host_loop(steps):
+        """K steps through dafne_detect_host_begin / _end with HOST buffers: the H2D copy of step i+1 (copy stream)
+        overlaps the compute of step i; every step's images go H2D and its detections come back D2H."""
+        prev = None
+        for i in range(steps):
+            t = eng.detect_host_begin(host_sets[i % n_sets], sizes, None, host_dets[i % 2], host_counts[i % 2], cap)
+            if prev is not None:
+                finish_host(*prev)
+            prev = (t, (i % 2))
+        finish_host(*prev)
+
+    def finish_host(ticket, k):
+        eng.detect_host_end(ticket)  # detections of that step are now in host_dets[k] / host_counts[k]
         if world > 1:
-            dist.all_gather_into_tensor(gathered, host_dets.to(dev, non_blocking=True))
-            dist.all_gather_into_tensor(gathered_counts, host_counts.to(dev, non_blocking=True))
+            dist.all_gather_into_tensor(gathered, host_dets[k].to(dev, non_blocking=True))
+            dist.all_gather_into_tensor(gathered_counts, host_counts[k].to(dev, non_blocking=True))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, whole_loop=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(steps):
-            fn(i)
+        if whole_loop:
+            fn(steps)
+        else:
+            for i in range(steps):
+                fn(i)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -237,9 +253,8 @@ def run_ours(args):
         sampler.start()
     ms = timed(step_device, args.steps)
     launches, flops = eng.stats(reset=True)
-    for i in range(2):
-        step_host(i)
-    ms_host = timed(step_host, args.steps)
+    host_loop(2)
+    ms_host = timed(host_loop, args.steps, whole_loop=True)
     clocks = sampler.stop() if rank == 0 else None
     dets, counts = step_device(0)
     torch.cuda.synchronize()

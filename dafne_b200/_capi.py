@@ -85,6 +85,9 @@ _SIGNATURES = {
     "dafne_postprocess_scratch_bytes": (_i, [_vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]),
     "dafne_detect": (_i, [_vp, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _i, _vp]),
     "dafne_detect_host": (_i, [_vp, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _i, _vp]),
+    "dafne_detect_host_begin": (_i, [_vp, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _i, _vp,
+                                     C.POINTER(_i)]),
+    "dafne_detect_host_end": (_i, [_vp, _i]),
     "dafne_debug_keep_activations": (_i, [_vp, _i]),
     "dafne_debug_activation": (_i, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "dafne_debug_post_counts": (_i, [_vp, C.POINTER(C.c_int32), _vp]),

@@ -255,6 +255,82 @@ int dafne_detect_host(dafne_ctx* ctx, const void* host_images, int dtype, const 
     return 0;
 }
 
+int dafne_detect_host_begin(dafne_ctx* ctx, const void* host_images, int dtype, const int32_t* image_sizes,
+                            const int32_t* output_sizes, float* host_dets, int32_t* host_counts, int capacity,
+                            void* stream, int* ticket) {
+    NEED_CTX(ctx, "dafne_detect_host_begin");
+    if (!ctx->ws || !ticket) {
+        set_error("dafne_detect_host_begin: %s", ctx->ws ? "null ticket" : "no workspace bound");
+        return -1;
+    }
+    const int k = static_cast<int>(ctx->slot_next & 1u);
+    if (ctx->slot_pending[k]) {
+        set_error("dafne_detect_host_begin: two batches are already in flight (call dafne_detect_host_end first)");
+        return -1;
+    }
+    cudaError_t e = cudaSuccess;
+    if (!ctx->copy_stream) {
+        e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_compute[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_result[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) {
+            set_error("dafne_detect_host_begin: creating the copy stream / events failed: %s", cudaGetErrorString(e));
+            return -1;
+        }
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    void* img = k == 0 ? ctx->images_dev : ctx->images_dev2;
+    float* dets = k == 0 ? ctx->dets_dev : ctx->dets_dev2;
+    int32_t* counts = k == 0 ? ctx->counts_dev : ctx->counts_dev2;
+    const size_t esz = dtype == 0 ? 1 : 4;
+    const size_t bytes = static_cast<size_t>(ctx->N) * 3 * ctx->H * ctx->W * esz;
+    if (capacity > ctx->dets_capacity) capacity = ctx->dets_capacity;
+    // H2D on the copy stream, once the batch that last read this staging buffer has been computed
+    if (ctx->slot_used[k]) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute[k], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(img, host_images, bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_h2d[k], ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ctx->ev_h2d[k], 0);
+    if (e != cudaSuccess) {
+        set_error("dafne_detect_host_begin H2D: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    if (dafne_detect(ctx, img, dtype, image_sizes, output_sizes, dets, counts, capacity, stream)) return -1;
+    e = cudaEventRecord(ctx->ev_compute[k], s);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(host_dets, dets, static_cast<size_t>(ctx->N) * capacity * DAFNE_DET_STRIDE * 4,
+                            cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(host_counts, counts, static_cast<size_t>(ctx->N) * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_result[k], s);
+    if (e != cudaSuccess) {
+        set_error("dafne_detect_host_begin D2H: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    ctx->slot_pending[k] = true;
+    ctx->slot_used[k] = true;
+    ctx->slot_next++;
+    *ticket = k;
+    return 0;
+}
+
+int dafne_detect_host_end(dafne_ctx* ctx, int ticket) {
+    NEED_CTX(ctx, "dafne_detect_host_end");
+    if (ticket < 0 || ticket > 1 || !ctx->slot_pending[ticket]) {
+        set_error("dafne_detect_host_end: ticket %d is not in flight", ticket);
+        return -1;
+    }
+    cudaError_t e = cudaEventSynchronize(ctx->ev_result[ticket]);
+    ctx->slot_pending[ticket] = false;
+    if (e != cudaSuccess) {
+        set_error("dafne_detect_host_end: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
 int dafne_debug_keep_activations(dafne_ctx* ctx, int keep) {
     NEED_CTX(ctx, "dafne_debug_keep_activations");
     ctx->keep_activations = keep != 0;

@@ -195,6 +195,12 @@ void ctx_destroy(dafne_ctx* c) {
     if (c->stem_scale) cudaFree(c->stem_scale);
     if (c->stem_shift) cudaFree(c->stem_shift);
     if (c->scales_dev) cudaFree(c->scales_dev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int k = 0; k < 2; ++k) {
+        if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]);
+        if (c->ev_compute[k]) cudaEventDestroy(c->ev_compute[k]);
+        if (c->ev_result[k]) cudaEventDestroy(c->ev_result[k]);
+    }
     delete c;
 }
 
@@ -529,6 +535,9 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     const int det_cap = 2048;
     float* dets_dev = B.persistent<float>(static_cast<size_t>(N) * det_cap * DAFNE_DET_STRIDE * sizeof(float));
     int32_t* counts_dev = B.persistent<int32_t>(static_cast<size_t>(N) * sizeof(int32_t));
+    void* images_dev2 = B.persistent<uint8_t>(img_bytes);
+    float* dets_dev2 = B.persistent<float>(static_cast<size_t>(N) * det_cap * DAFNE_DET_STRIDE * sizeof(float));
+    int32_t* counts_dev2 = B.persistent<int32_t>(static_cast<size_t>(N) * sizeof(int32_t));
 
     // ---- stem (tensor cores; the preprocess kernel writes the zero-bordered NHWC4 canvas it reads)
     Act x0;
@@ -747,6 +756,11 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     c->dets_dev = dets_dev;
     c->counts_dev = counts_dev;
     c->dets_capacity = det_cap;
+    c->images_dev2 = images_dev2;
+    c->dets_dev2 = dets_dev2;
+    c->counts_dev2 = counts_dev2;
+    c->slot_pending[0] = c->slot_pending[1] = false;
+    c->slot_used[0] = c->slot_used[1] = false;
     c->post_scratch = post_scratch;
     c->post_scratch_bytes = post_bytes;
     for (int l = 0; l < 5; ++l)

@@ -94,11 +94,20 @@ struct dafne_ctx {
     long long* gn_sums_all = nullptr;
     size_t gn_sums_bytes = 0;
     int32_t* sizes_dev = nullptr;  // [N][4]
-    void* images_dev = nullptr;    // staging for dafne_detect_host
+    void* images_dev = nullptr;    // staging for dafne_detect_host (slot 0 of the pipelined form)
     size_t images_dev_bytes = 0;
     float* dets_dev = nullptr;  // staging for dafne_detect_host
     int32_t* counts_dev = nullptr;
     int dets_capacity = 0;
+    // dafne_detect_host_begin / _end: two batches in flight (slot 0 shares the buffers above)
+    void* images_dev2 = nullptr;
+    float* dets_dev2 = nullptr;
+    int32_t* counts_dev2 = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_result[2] = {nullptr, nullptr};
+    bool slot_pending[2] = {false, false};
+    bool slot_used[2] = {false, false};
+    unsigned slot_next = 0;
     dafne::HeadOut head_out[DAFNE_MAX_LEVELS][3];
     void* post_scratch = nullptr;
     size_t post_scratch_bytes = 0;

@@ -167,6 +167,26 @@ class DafneEngine:
                                                _capi.stream_ptr()), "dafne_detect_host")
         return host_dets, host_counts
 
+    def detect_host_begin(self, host_images: torch.Tensor, image_sizes, output_sizes, host_dets: torch.Tensor,
+                          host_counts: torch.Tensor, capacity: Optional[int] = None) -> int:
+        """Pipelined detect_host: enqueue H2D (copy stream) + detect + D2H, return a ticket without synchronising.
+        Up to two batches in flight; `host_dets` / `host_counts` (pinned) are filled when detect_host_end returns."""
+        N, _, H, W = host_images.shape
+        self.bind(N, H, W)
+        cap = min(capacity or (self.spec.post_nms_topk + 64), 2048)
+        assert host_dets.shape[1] >= cap and host_dets.is_contiguous()
+        dtype = {torch.uint8: 0, torch.float32: 1}[host_images.dtype]
+        sizes = _i32_array([v for hw in image_sizes for v in hw])
+        osz = _i32_array([v for hw in (output_sizes or image_sizes) for v in hw])
+        ticket = C.c_int(-1)
+        _capi.check(self.lib.dafne_detect_host_begin(self._ctx, host_images.data_ptr(), dtype, sizes, osz,
+                                                     host_dets.data_ptr(), host_counts.data_ptr(), cap,
+                                                     _capi.stream_ptr(), C.byref(ticket)), "dafne_detect_host_begin")
+        return ticket.value
+
+    def detect_host_end(self, ticket: int) -> None:
+        _capi.check(self.lib.dafne_detect_host_end(self._ctx, int(ticket)), "dafne_detect_host_end")
+
     def postprocess_external(self, logits: List[torch.Tensor], reg: List[torch.Tensor], ctr: List[torch.Tensor],
                              image_sizes, output_sizes=None, do_postprocess=True, capacity: Optional[int] = None):
         """Post-process head outputs given in the reference's own NCHW fp32 form (the bit-exact parity gate)."""

@@ -119,6 +119,17 @@ int dafne_detect_host(dafne_ctx* ctx, const void* host_images, int dtype, const 
                       const int32_t* output_sizes, float* host_dets, int32_t* host_counts, int capacity,
                       void* stream);
 
+/* Pipelined form of dafne_detect_host for serving loops (same arguments, same results). _begin enqueues the H2D copy
+ * of this batch on the context's own copy stream into one of two staging buffers, then detection and the D2H copies
+ * on `stream`, and returns without synchronising; *ticket identifies the batch. _end blocks until that batch's
+ * detections and counts are in the host buffers given to _begin. At most two batches are in flight: calling
+ * _begin(i + 1) before _end(i) overlaps the H2D copy of batch i + 1 with the compute of batch i. The host buffers of
+ * a batch must stay valid and untouched until its _end returns. */
+int dafne_detect_host_begin(dafne_ctx* ctx, const void* host_images, int dtype, const int32_t* image_sizes,
+                            const int32_t* output_sizes, float* host_dets, int32_t* host_counts, int capacity,
+                            void* stream, int* ticket);
+int dafne_detect_host_end(dafne_ctx* ctx, int ticket);
+
 /* Per-layer parity support. keep != 0 (set BEFORE dafne_bind_workspace) disables activation-memory reuse so that
  * every intermediate survives the forward; dafne_debug_activation then returns the NHWC fp16 tensor called `name`:
  * "stem", "pool", "res2.0" ... "res5.2", "p3" ... "p7", "cls_tower.l0" ... "corners_tower.l4". */

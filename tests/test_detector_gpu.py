@@ -102,6 +102,41 @@ def test_detect_host_equals_device_path(model):
     assert torch.equal(hd[0, :n], dets_d[0, :n].cpu())
 
 
+def test_pipelined_host_calls_equal_blocking_call(model):
+    """dafne_detect_host_begin / _end (two batches in flight, H2D on the copy stream) returns what dafne_detect_host
+    returns, batch by batch, and refuses a third batch in flight."""
+    from dafne_b200._capi import DafneError
+    from dafne_b200.engine import DET
+
+    eng = model._engine
+    g = torch.Generator().manual_seed(11)
+    batches = [torch.randint(0, 256, (2, 3, 128, 160), dtype=torch.uint8, generator=g).pin_memory() for _ in range(4)]
+    sizes = [(128, 160), (100, 150)]
+    cap = 1064
+    want = []
+    for b in batches:
+        d, c = eng.detect_host(b, sizes, None, None, None, cap)
+        want.append((d.clone(), c.clone()))
+    bufs = [(torch.empty(2, cap, DET).pin_memory(), torch.empty(2, dtype=torch.int32).pin_memory()) for _ in range(2)]
+    prev = None
+    for i, b in enumerate(batches):
+        t = eng.detect_host_begin(b, sizes, None, bufs[i % 2][0], bufs[i % 2][1], cap)
+        if prev is not None:
+            eng.detect_host_end(prev[0])
+            k = prev[1]
+            n = want[k][1]
+            assert torch.equal(bufs[k % 2][1], n)
+            for j in range(2):
+                assert torch.equal(bufs[k % 2][0][j, : n[j]], want[k][0][j, : n[j]])
+        prev = (t, i)
+    t_extra = eng.detect_host_begin(batches[0], sizes, None, bufs[0][0], bufs[0][1], cap)
+    with pytest.raises(DafneError):  # slots of batch 3 and of the extra batch are both in flight
+        eng.detect_host_begin(batches[1], sizes, None, bufs[1][0], bufs[1][1], cap)
+    eng.detect_host_end(prev[0])
+    eng.detect_host_end(t_extra)
+    torch.cuda.synchronize()
+
+
 def test_unsupported_config_fails_loudly():
     from dafne_b200.config import get_cfg
     from dafne_b200.modeling import build_model
