@@ -74,7 +74,7 @@ int dafne_conv_nhwc(const void* in, int N, int H, int W, int Cin, const void* w,
         set_error("dafne_conv_nhwc: descriptor upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return -1;
     }
-    return conv_group_launch(dev_prob, 1, plan.prob.p.total_tiles, plan.block_n, plan.epi_wgs, plan.mode, plan.res_tma,
+    return conv_group_launch(dev_prob, 1, plan.prob.p.total_tiles, plan.block_n, plan.epi_wgs, plan.mode, plan.res_tma, plan.row_shared,
                              num_sms_cached(), s);
 }
 

@@ -10,6 +10,13 @@
 // input patch lands directly in the canonical K-major SWIZZLE_128B operand layout; out-of-image coordinates are
 // zero-filled by TMA, which is exactly the conv zero padding. Nothing im2col-shaped ever exists in HBM.
 //
+// Row-shared taps (3x3 stride 1 with a narrow N tile, where the kernel is bound by L2 -> shared-memory fills, not by
+// the tensor pipe: the prediction convs, res2's 3x3): the pixel tile is 8 wide x 16 high, so one row of it is exactly
+// one 1024-byte swizzle atom. ONE box of 18 rows (the tile plus a row above and below) per horizontal tap dx then
+// serves all three vertical taps: the operand of tap (dy, dx) is the same shared-memory box read from row 1 + dy on --
+// a descriptor start that moves by whole atoms, so the canonical layout is untouched. Three A loads per channel
+// block instead of nine.
+//
 // Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
 // warp 3 = residual producer, warps 4-7 = epilogue (TMEM -> registers -> scale/shift/residual/ReLU -> fp16 -> swizzled
 // smem -> TMA store). Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
@@ -51,8 +58,13 @@ struct ConvCfg {
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
     static constexpr int THREADS = 128 + 128 * EPI_WGS;
     static constexpr int MAX_STAGES = 8, MAX_RING = 4;
-    static constexpr int smem_bytes(int stages, int ring) {
-        return stages * STAGE_BYTES + (BLOCK_N >= 64 ? EPI_WGS * ring * SLOT_BYTES : 0) + AUX_BYTES;
+    // row-shared taps: A box = 18 rows x 8 px x 64 ch (18 KB, padded to 19 KB so B stays 1024-aligned) + B of 3 taps
+    static constexpr int A_RS_BOX_BYTES = 18 * 1024;
+    static constexpr int A_RS_BYTES = 19 * 1024;
+    static constexpr int STAGE_BYTES_RS = A_RS_BYTES + 3 * B_BYTES;
+    static constexpr int smem_bytes(int stages, int ring, int row_shared = 0) {
+        return stages * (row_shared ? STAGE_BYTES_RS : STAGE_BYTES) +
+               (BLOCK_N >= 64 ? EPI_WGS * ring * SLOT_BYTES : 0) + AUX_BYTES;
     }
 };
 constexpr int kMaxSmem = 232448;  // 227 KB
@@ -141,7 +153,7 @@ __device__ __forceinline__ void epilogue_chunk_math(const uint32_t (&v)[64], con
 template <int BLOCK_N, int EPI_WGS, int MODE>
 __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
     conv_tc_kernel(const ConvProblem* __restrict__ probs, int nprob, int total_tiles, int stages, int ring,
-                   int res_tma_arg) {
+                   int res_tma_arg, int row_shared) {
     const int res_tma = MODE == 1 ? res_tma_arg : 0;
     using Cfg = ConvCfg<BLOCK_N, EPI_WGS>;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -157,9 +169,10 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
     // carve-up: [stages x (A | B)] [EPI_WGS x ring x 16 KB epilogue slots] [512 B header] [(scale, shift) tables]
     const int epi_bytes = BLOCK_N >= 64 ? EPI_WGS * ring * Cfg::SLOT_BYTES : 0;
     const uint32_t s_tiles = smem_base;
-    const uint32_t s_epi = smem_base + stages * Cfg::STAGE_BYTES;
+    const int stage_bytes = row_shared ? Cfg::STAGE_BYTES_RS : Cfg::STAGE_BYTES;
+    const uint32_t s_epi = smem_base + stages * stage_bytes;
     const uint32_t s_aux = s_epi + epi_bytes;
-    uint8_t* aux = smem + stages * Cfg::STAGE_BYTES + epi_bytes;
+    uint8_t* aux = smem + stages * stage_bytes + epi_bytes;
     const uint32_t bar_full = s_aux;             // 8 x 8 B
     const uint32_t bar_empty = s_aux + 64;       // 8 x 8 B
     const uint32_t bar_tfull = s_aux + 128;      // 2 x 8 B
@@ -217,6 +230,27 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                 const ConvParams& p = pr->p;
                 const TileCoord tc = tile_coord(p, t - s_begin[g]);
                 const int num_taps = p.num_taps, cin_blocks = p.cin_blocks, Cin = p.Cin;
+                if (row_shared) {
+                    // one 18-row box per (dx, channel block) + the weights of its three vertical taps
+                    for (int dxi = 0; dxi < 3; ++dxi) {
+                        for (int cb = 0; cb < cin_blocks; ++cb) {
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            const uint32_t full = bar_full + 8 * stage;
+                            mbar_arrive_expect_tx(full, Cfg::A_RS_BOX_BYTES + 3 * Cfg::B_BYTES);
+                            const uint32_t sA = s_tiles + stage * stage_bytes;
+                            tma_load_4d(sA, &pr->tmA[0], full, cb * 64, tc.x0 + dxi - 1, tc.y0 - 1, tc.n0);
+#pragma unroll
+                            for (int dyi = 0; dyi < 3; ++dyi)
+                                tma_load_2d(sA + Cfg::A_RS_BYTES + dyi * Cfg::B_BYTES, &pr->tmB, full,
+                                            (dyi * 3 + dxi) * Cin + cb * 64, tc.nt * BLOCK_N);
+                            if (++stage == stages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    }
+                    continue;
+                }
                 for (int tap = 0; tap < num_taps; ++tap) {
                     const CUtensorMap* mA = &pr->tmA[p.tap_view[tap]];
                     const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
@@ -224,7 +258,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t full = bar_full + 8 * stage;
                         mbar_arrive_expect_tx(full, Cfg::STAGE_BYTES);
-                        const uint32_t sA = s_tiles + stage * Cfg::STAGE_BYTES;
+                        const uint32_t sA = s_tiles + stage * stage_bytes;
                         tma_load_4d(sA, mA, full, cb * 64, cx, cy, tc.n0);
                         tma_load_2d(sA + Cfg::A_BYTES, &pr->tmB, full, tap * Cin + cb * 64, tc.nt * BLOCK_N);
                         if (++stage == stages) {
@@ -246,20 +280,32 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             int g = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 while (t >= s_begin[g + 1]) ++g;
-                const int num_kb = probs[g].p.num_taps * probs[g].p.cin_blocks;
+                const int num_kb = (row_shared ? 3 : probs[g].p.num_taps) * probs[g].p.cin_blocks;
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * BLOCK_N;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t sA = s_tiles + stage * Cfg::STAGE_BYTES;
-                    const uint64_t ad = umma_desc_sw128(sA);
-                    const uint64_t bd = umma_desc_sw128(sA + Cfg::A_BYTES);
+                    const uint32_t sA = s_tiles + stage * stage_bytes;
+                    if (row_shared) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        // +32 B along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
-                        umma_f16(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            // rows dyi .. dyi+15 of the 18-row box: the start moves by whole 1024-byte atoms
+                            const uint64_t ad = umma_desc_sw128(sA + dyi * 1024);
+                            const uint64_t bd = umma_desc_sw128(sA + Cfg::A_RS_BYTES + dyi * Cfg::B_BYTES);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16(d, ad + 2 * k, bd + 2 * k, idesc, (kb | dyi | k) != 0);
+                        }
+                    } else {
+                        const uint64_t ad = umma_desc_sw128(sA);
+                        const uint64_t bd = umma_desc_sw128(sA + Cfg::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // +32 B along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
+                            umma_f16(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                        }
                     }
                     umma_commit(bar_empty + 8 * stage);
                     if (++stage == stages) {
@@ -632,9 +678,19 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     p.Cout = d.Cout;
     p.num_taps = d.ksize * d.ksize;
     p.cin_blocks = d.Cin / 64;
-    p.tw = pow2ceil(d.Wout) < 16 ? pow2ceil(d.Wout) : 16;
-    p.th = pow2ceil(d.Hout) < 128 / p.tw ? pow2ceil(d.Hout) : 128 / p.tw;
-    p.nb = 128 / (p.tw * p.th);
+    // Row-shared taps: worth it where the 9 A loads per channel block are the bottleneck (narrow N tiles); the
+    // three weight tiles of a stage must leave room for a four-stage pipeline (bn <= 64).
+    const bool row_shared = d.ksize == 3 && d.stride == 1 && bn <= 64;
+    plan->row_shared = row_shared ? 1 : 0;
+    if (row_shared) {
+        p.tw = 8;
+        p.th = 16;
+        p.nb = 1;
+    } else {
+        p.tw = pow2ceil(d.Wout) < 16 ? pow2ceil(d.Wout) : 16;
+        p.th = pow2ceil(d.Hout) < 128 / p.tw ? pow2ceil(d.Hout) : 128 / p.tw;
+        p.nb = 128 / (p.tw * p.th);
+    }
     p.tiles_x = (d.Wout + p.tw - 1) / p.tw;
     p.tiles_y = (d.Hout + p.th - 1) / p.th;
     p.tiles_n = (d.N + p.nb - 1) / p.nb;
@@ -658,11 +714,14 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
 
     const uint64_t C = d.Cin, W = d.Win, H = d.Hin;
     const uint32_t boxA[4] = {64u, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.nb};
+    const uint32_t boxA_rs[4] = {64u, 8u, 18u, 1u};  // the tile plus one row above and below
     bool view_empty[4] = {false, false, false, false};
     if (d.stride == 1) {
         const uint64_t dims[4] = {C, W, H, (uint64_t)d.N};
         const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
-        if (encode_map(&plan->prob.tmA[0], d.in, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A")) return -1;
+        if (encode_map(&plan->prob.tmA[0], d.in, 4, dims, str, row_shared ? boxA_rs : boxA,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A"))
+            return -1;
         for (int v = 1; v < 4; ++v) plan->prob.tmA[v] = plan->prob.tmA[0];
         for (int t = 0; t < p.num_taps; ++t) {
             p.tap_view[t] = 0;
@@ -741,23 +800,18 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
 // Operand stages / epilogue ring slots per warpgroup for a launch: as deep as 227 KB allows. With a TMA residual the
 // ring is the prefetch depth of the residual stream, so it gets four slots at the price of operand stages.
 template <int BN, int WGS>
-static void conv_smem_config(int res_tma, int* stages, int* ring) {
+static void conv_smem_config(int res_tma, int row_shared, int* stages, int* ring) {
     using Cfg = ConvCfg<BN, WGS>;
-    if (BN < 64) {
-        *ring = 2;
-        *stages = Cfg::MAX_STAGES;
-        return;
-    }
-    int r = res_tma ? 4 : (WGS == 2 ? 3 : 2);
+    int r = BN < 64 ? 2 : (res_tma ? 4 : (WGS == 2 ? 3 : 2));
     int st = Cfg::MAX_STAGES;
-    while (st > 2 && Cfg::smem_bytes(st, r) > kMaxSmem) --st;
-    while (r > 2 && Cfg::smem_bytes(st, r) > kMaxSmem) --r;
+    while (st > 2 && Cfg::smem_bytes(st, r, row_shared) > kMaxSmem) --st;
+    while (r > 2 && Cfg::smem_bytes(st, r, row_shared) > kMaxSmem) --r;
     *stages = st;
     *ring = r;
 }
 
 template <int BN, int WGS, int MODE>
-static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, int res_tma,
+static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, int res_tma, int row_shared,
                      cudaStream_t stream) {
     using Cfg = ConvCfg<BN, WGS>;
     static bool configured = false;
@@ -772,15 +826,15 @@ static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, i
         configured = true;
     }
     int stages, ring;
-    conv_smem_config<BN, WGS>(res_tma, &stages, &ring);
-    const int smem = Cfg::smem_bytes(stages, ring);
+    conv_smem_config<BN, WGS>(res_tma, row_shared, &stages, &ring);
+    const int smem = Cfg::smem_bytes(stages, ring, row_shared);
     if (smem > kMaxSmem) {
         set_error("conv_tc_kernel<%d,%d>: %d stages + %d ring slots need %d bytes of shared memory", BN, WGS, stages,
                   ring, smem);
         return -1;
     }
     conv_tc_kernel<BN, WGS, MODE>
-        <<<grid, Cfg::THREADS, smem, stream>>>(dev_probs, nprob, total_tiles, stages, ring, res_tma);
+        <<<grid, Cfg::THREADS, smem, stream>>>(dev_probs, nprob, total_tiles, stages, ring, res_tma, row_shared);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("conv_tc_kernel<%d,%d,%d> launch: %s", BN, WGS, MODE, cudaGetErrorString(e));
@@ -791,15 +845,15 @@ static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, i
 
 template <int BN, int WGS>
 static int launch_mode(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, int mode, int res_tma,
-                       cudaStream_t stream) {
-    if (mode == 1) return launch_bn<BN, WGS, 1>(dev_probs, nprob, total_tiles, grid, res_tma, stream);
-    if (mode == 0) return launch_bn<BN, WGS, 0>(dev_probs, nprob, total_tiles, grid, 0, stream);
+                       int row_shared, cudaStream_t stream) {
+    if (mode == 1) return launch_bn<BN, WGS, 1>(dev_probs, nprob, total_tiles, grid, res_tma, row_shared, stream);
+    if (mode == 0) return launch_bn<BN, WGS, 0>(dev_probs, nprob, total_tiles, grid, 0, row_shared, stream);
     set_error("conv_tc: epilogue mode %d is not built for tile width %d / %d epilogue warpgroups", mode, BN, WGS);
     return -1;
 }
 
 int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int epi_wgs, int mode,
-                      int res_tma, int num_sms, cudaStream_t stream) {
+                      int res_tma, int row_shared, int num_sms, cudaStream_t stream) {
     if (total_tiles == 0) return 0;
     if (nprob < 1 || nprob > kMaxConvProblems) {
         set_error("conv_tc: %d problems in one launch (1..%d supported)", nprob, kMaxConvProblems);
@@ -809,20 +863,20 @@ int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, 
     const int key = block_n * 10 + epi_wgs;
     if (mode == 2) {
         // GroupNorm statistics: only the 256-wide tower convolutions produce them
-        if (key == 2561) return launch_bn<256, 1, 2>(dev_probs, nprob, total_tiles, grid, 0, stream);
-        if (key == 2562) return launch_bn<256, 2, 2>(dev_probs, nprob, total_tiles, grid, 0, stream);
+        if (key == 2561) return launch_bn<256, 1, 2>(dev_probs, nprob, total_tiles, grid, 0, 0, stream);
+        if (key == 2562) return launch_bn<256, 2, 2>(dev_probs, nprob, total_tiles, grid, 0, 0, stream);
         set_error("conv_tc: GroupNorm statistics need Cout %% 256 == 0 (tile width %d)", block_n);
         return -1;
     }
     switch (key) {
-        case 161: return launch_bn<16, 1, 0>(dev_probs, nprob, total_tiles, grid, 0, stream);
-        case 321: return launch_bn<32, 1, 0>(dev_probs, nprob, total_tiles, grid, 0, stream);
-        case 641: return launch_mode<64, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
-        case 642: return launch_mode<64, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
-        case 1281: return launch_mode<128, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
-        case 1282: return launch_mode<128, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
-        case 2561: return launch_mode<256, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
-        case 2562: return launch_mode<256, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, stream);
+        case 161: return launch_bn<16, 1, 0>(dev_probs, nprob, total_tiles, grid, 0, row_shared, stream);
+        case 321: return launch_bn<32, 1, 0>(dev_probs, nprob, total_tiles, grid, 0, row_shared, stream);
+        case 641: return launch_mode<64, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, stream);
+        case 642: return launch_mode<64, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, stream);
+        case 1281: return launch_mode<128, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, stream);
+        case 1282: return launch_mode<128, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, stream);
+        case 2561: return launch_mode<256, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, 0, stream);
+        case 2562: return launch_mode<256, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, 0, stream);
     }
     set_error("conv_tc: unsupported tile width %d with %d epilogue warpgroups", block_n, epi_wgs);
     return -1;

@@ -299,7 +299,7 @@ struct Builder {
     ConvProblem* dev_probs = nullptr;
     bool grouping = false;
     size_t group_first = 0;
-    int group_bn = 0, group_wgs = 0, group_res = -1, group_mode = -1;
+    int group_bn = 0, group_wgs = 0, group_res = -1, group_mode = -1, group_rs = -1;
     double group_flops = 0, group_bytes = 0;
     std::string group_name;
     OpInfo group_info;
@@ -311,6 +311,7 @@ struct Builder {
         group_wgs = 0;
         group_res = -1;
         group_mode = -1;
+        group_rs = -1;
         group_flops = group_bytes = 0;
         group_name = name;
     }
@@ -330,9 +331,10 @@ struct Builder {
             total += probs[i].p.total_tiles;
         }
         const ConvProblem* dp = dev_probs + first;
-        const int bn = group_bn, wgs = group_wgs, res = group_res, mode = group_mode, sms = c->num_sms,
+        const int bn = group_bn, wgs = group_wgs, res = group_res, mode = group_mode, rs = group_rs, sms = c->num_sms,
                   n = static_cast<int>(cnt);
-        c->ops.push_back([=](cudaStream_t s) { return conv_group_launch(dp, n, total, bn, wgs, mode, res, sms, s); });
+        c->ops.push_back(
+            [=](cudaStream_t s) { return conv_group_launch(dp, n, total, bn, wgs, mode, res, rs, sms, s); });
         OpInfo o = group_info;
         snprintf(o.name, sizeof(o.name), "%s", group_name.size() > 46 ? group_name.substr(group_name.size() - 46).c_str()
                                                                       : group_name.c_str());
@@ -445,13 +447,15 @@ struct Builder {
                 failed = true;
                 return out;
             }
-            if ((group_res >= 0 && group_res != plan.res_tma) || (group_mode >= 0 && group_mode != plan.mode)) {
+            if ((group_res >= 0 && group_res != plan.res_tma) || (group_mode >= 0 && group_mode != plan.mode) ||
+                (group_rs >= 0 && group_rs != plan.row_shared)) {
                 set_error("plan: group '%s' mixes TMA-residual and other convolutions", group_name.c_str());
                 failed = true;
                 return out;
             }
             group_res = plan.res_tma;
             group_mode = plan.mode;
+            group_rs = plan.row_shared;
             group_bn = plan.block_n;
             group_wgs = group_wgs == 0 ? plan.epi_wgs : (group_wgs < plan.epi_wgs ? group_wgs : plan.epi_wgs);
             probs.push_back(plan.prob);

@@ -38,6 +38,12 @@ CASES = [
     ("1x1_64_64_res_n3_30", 3, 30, 30, 64, 64, 1, 1, {"shift": True, "relu": True, "res": 0}),
     ("1x1_256_1024_res_multiwave", 8, 64, 64, 256, 1024, 1, 1, {"scale": True, "shift": True, "relu": True, "res": 0}),
     ("1x1_64_256_shortcut_multiwave", 2, 256, 256, 64, 256, 1, 1, {"scale": True, "shift": True}),
+    # row-shared taps (3x3 stride 1, N tile <= 64): 8 x 16 pixel tiles, ragged sizes, several images, many tiles per CTA
+    ("3x3_64_64_rowshared_multiwave", 2, 256, 256, 64, 64, 3, 1, {"scale": True, "shift": True, "relu": True}),
+    ("3x3_256_15_pred_odd_n3", 3, 25, 42, 256, 15, 3, 1, {"shift": True, "f32": 16}),
+    ("3x3_256_2_pred_7x11", 2, 7, 11, 256, 2, 3, 1, {"shift": True, "f32": 16}),
+    ("3x3_256_32_pred_f32_ld32", 1, 40, 24, 256, 32, 3, 1, {"shift": True, "f32": 32}),
+    ("3x3_64_64_res_rowshared", 1, 50, 70, 64, 64, 3, 1, {"scale": True, "shift": True, "relu": True, "res": 0}),
 ]
 
 
