@@ -3,6 +3,8 @@
 //   normalise + pad          dafne/modeling/one_stage_detector.py:100-107 (ImageList.from_tensors pads with 0 AFTER normalising)
 //   stem conv+BN+ReLU, pool  detectron2 v0.5 BasicStem via dafne/modeling/backbone/fpn.py:72
 //   GroupNorm(32) + ReLU     dafne/modeling/dafne/dafne.py:326-345
+#include <stdint.h>
+
 #include "conv_tc.cuh"
 #include "elementwise.cuh"
 
@@ -20,38 +22,64 @@ namespace dafne {
 // ------------------------------------------------------------------------------------------------ preprocess
 // Output canvas: fp16 [N][H+6][W+8][4] with the image at row 3 / pixel 4 and zeros around it (stem_tc.cu reads
 // 64-byte runs of it through TMA); every canvas position is written on every call.
+// One thread = 4 consecutive canvas pixels (the canvas row pitch W + 8 and the image's left edge at pixel 4 are
+// multiples of 4, so a group is either entirely left / right of the image columns or aligned with 4 image pixels):
+// three 4-pixel loads (one per plane; 4 B for uint8, 16 B for float) and one 32-byte store per thread.
+template <typename T>
+struct alignas(4 * sizeof(T)) Px4 {
+    T v[4];
+};
 template <typename T>
 __global__ void preprocess_kernel(const T* __restrict__ img, const int32_t* __restrict__ sizes, int N, int H, int W,
                                   float m0, float m1, float m2, float s0, float s1, float s2,
                                   __half* __restrict__ out) {
-    const int PW = W + 8, PH = H + 6;
-    const size_t total = static_cast<size_t>(N) * PH * PW;
+    const int PW = W + 8, PH = H + 6, PW4 = PW / 4;
+    const size_t total = static_cast<size_t>(N) * PH * PW4;
+    const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int x = static_cast<int>(i % PW) - 4;
-        const int y = static_cast<int>((i / PW) % PH) - 3;
-        const int n = i / (static_cast<size_t>(PW) * PH);
+        const int x = static_cast<int>(i % PW4) * 4 - 4;
+        const int y = static_cast<int>((i / PW4) % PH) - 3;
+        const int n = i / (static_cast<size_t>(PW4) * PH);
         const int h = sizes[4 * n], w = sizes[4 * n + 1];  // rows of [h, w, out_h, out_w]
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-        if (y >= 0 && x >= 0 && y < h && x < w) {
+        float v[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[c][k] = 0.f;
+        if (y >= 0 && y < h && x >= 0 && x < w) {
             const size_t plane = static_cast<size_t>(H) * W;
             const size_t base = static_cast<size_t>(n) * 3 * plane + static_cast<size_t>(y) * W + x;
-            v0 = (static_cast<float>(img[base]) - m0) / s0;
-            v1 = (static_cast<float>(img[base + plane]) - m1) / s1;
-            v2 = (static_cast<float>(img[base + 2 * plane]) - m2) / s2;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const Px4<T> q = *reinterpret_cast<const Px4<T>*>(img + base + c * plane);  // x % 4 == 0, W % 32 == 0
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (x + k < w) v[c][k] = (static_cast<float>(q.v[k]) - mean[c]) / sd[c];
+            }
         }
-        const __half2 a = __floats2half2_rn(v0, v1);
-        const __half2 b = __floats2half2_rn(v2, 0.f);
-        uint2 o;
-        o.x = *reinterpret_cast<const uint32_t*>(&a);
-        o.y = *reinterpret_cast<const uint32_t*>(&b);
-        reinterpret_cast<uint2*>(out)[i] = o;
+        uint4 o[2];
+        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __half2 a = __floats2half2_rn(v[0][k], v[1][k]);
+            const __half2 b = __floats2half2_rn(v[2][k], 0.f);
+            ow[2 * k] = *reinterpret_cast<const uint32_t*>(&a);
+            ow[2 * k + 1] = *reinterpret_cast<const uint32_t*>(&b);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out) + i * 2;
+        dst[0] = o[0];
+        dst[1] = o[1];
     }
 }
 
 int launch_preprocess(const void* images, int dtype, const int32_t* sizes_dev, int N, int H, int W, const float* mean3,
                       const float* std3, __half* out, cudaStream_t s) {
-    const size_t total = static_cast<size_t>(N) * (H + 6) * (W + 8);
+    if (W % 4 != 0 || (reinterpret_cast<uintptr_t>(images) & 15) != 0) {
+        set_error("preprocess: needs W %% 4 == 0 and 16-byte aligned images (W=%d)", W);
+        return -1;
+    }
+    const size_t total = static_cast<size_t>(N) * (H + 6) * ((W + 8) / 4);
     const int threads = 256;
     const int blocks = static_cast<int>((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads
                                                                                    : 148 * 16);

@@ -19,10 +19,15 @@
 namespace dafne {
 
 namespace {
-constexpr int kStages = 8;
-constexpr int kABytes = 128 * 64;  // 128 pixels x 32 fp16
-constexpr int kBBytes = 64 * 64;   // 64 couts x 32 fp16
-constexpr int kStageBytes = kABytes + kBBytes;
+// One stage = one row PARITY of the 7 kernel rows: padded row 2*oy + ky = 2*(oy + ky/2) + (ky & 1), so the taps
+// ky = 0, 2, 4, 6 read the even-row view from row-pair oy + 0..3 and ky = 1, 3, 5 the odd-row view from oy + 0..2.
+// ONE box of th + 3 = 11 row pairs per parity therefore serves all of its taps: tap ky's operand is that box read
+// from row ky/2 on -- the descriptor start moves by whole 1024-byte rows (two SWIZZLE_64B atoms), the layout is
+// untouched. Two A loads per tile instead of seven (the kernel was bound by L2 -> shared-memory fills).
+constexpr int kStages = 6;
+constexpr int kABytes = 11 * 1024;  // 11 row pairs x 16 pixels x 32 fp16
+constexpr int kBBytes = 64 * 64;    // 64 couts x 32 fp16, per kernel row
+constexpr int kStageBytes = kABytes + 4 * kBBytes;
 constexpr int kEpiBytes = 2 * 16384;
 constexpr int kAuxBytes = 256 + 2 * 64 * 4;
 constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kAuxBytes;
@@ -98,14 +103,15 @@ __global__ void __launch_bounds__(256, 1)
                 const int r = t / p.tiles_x;
                 const int ty = r % p.tiles_y, tn = r / p.tiles_y;
                 const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tn * p.nb;
-                for (int ky = 0; ky < 7; ++ky) {
+                for (int par = 0; par < 2; ++par) {
+                    const int nky = 4 - par;
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
-                    mbar_arrive_expect_tx(full, kStageBytes);
+                    mbar_arrive_expect_tx(full, kABytes + nky * kBBytes);
                     const uint32_t sA = s_tiles + stage * kStageBytes;
-                    // padded row 2*oy + ky = 2 * (oy + ky/2) + (ky & 1)
-                    tma_load_5d(sA, &tmA, full, 0, x0, ky & 1, y0 + (ky >> 1), n0);
-                    tma_load_2d(sA + kABytes, &tmB, full, ky * 32, 0);
+                    tma_load_5d(sA, &tmA, full, 0, x0, par, y0, n0);
+                    for (int j = 0; j < nky; ++j)
+                        tma_load_2d(sA + kABytes + j * kBBytes, &tmB, full, (2 * j + par) * 32, 0);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -124,14 +130,16 @@ __global__ void __launch_bounds__(256, 1)
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * 64;
-                for (int kb = 0; kb < 7; ++kb) {
+                for (int par = 0; par < 2; ++par) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sA = s_tiles + stage * kStageBytes;
-                    const uint64_t ad = umma_desc_sw64(sA);
-                    const uint64_t bd = umma_desc_sw64(sA + kABytes);
+                    for (int j = 0; j < 4 - par; ++j) {
+                        const uint64_t ad = umma_desc_sw64(sA + j * 1024);  // row pairs j .. j+7 of the box
+                        const uint64_t bd = umma_desc_sw64(sA + kABytes + j * kBBytes);
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_f16(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < 2; ++k) umma_f16(d, ad + 2 * k, bd + 2 * k, idesc, (par | j | k) != 0);
+                    }
                     umma_commit(bar_empty + 8 * stage);
                     if (++stage == kStages) {
                         stage = 0;
@@ -167,11 +175,16 @@ __global__ void __launch_bounds__(256, 1)
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
             uint32_t packed[32];
 #pragma unroll
-            for (int c = 0; c < 64; c += 2) {
-                const float a0 = fmaxf(fmaf(__uint_as_float(v[c]), s_scale[c], s_shift[c]), 0.f);
-                const float a1 = fmaxf(fmaf(__uint_as_float(v[c + 1]), s_scale[c + 1], s_shift[c + 1]), 0.f);
-                const __half2 h = __floats2half2_rn(a0, a1);
-                packed[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            for (int c = 0; c < 64; c += 4) {
+                const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
+                const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+                const float a0 = fmaf(__uint_as_float(v[c]), sc.x, sh.x);
+                const float a1 = fmaf(__uint_as_float(v[c + 1]), sc.y, sh.y);
+                const float a2 = fmaf(__uint_as_float(v[c + 2]), sc.z, sh.z);
+                const float a3 = fmaf(__uint_as_float(v[c + 3]), sc.w, sh.w);
+                // ReLU on the conversion
+                asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(packed[c >> 1]) : "f"(a1), "f"(a0));
+                asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(packed[(c >> 1) + 1]) : "f"(a3), "f"(a2));
             }
             const uint32_t buf = s_epi + store_buf * 16384;
             if (et == 0) tma_store_wait_read<1>();
@@ -253,7 +266,7 @@ int stem_plan_build(const __half* canvas, int N, int H, int W, const __half* w_p
         // {32 elements (64 B run), output x (16 B = 2 pixels per step), row parity, row pair, image}
         const cuuint64_t dims[5] = {32, (cuuint64_t)Wo, 2, (cuuint64_t)(Ho + 3), (cuuint64_t)N};
         const cuuint64_t str[4] = {16, row_bytes, 2 * row_bytes, (cuuint64_t)(H + 6) * row_bytes};
-        const cuuint32_t box[5] = {32, (cuuint32_t)p.tw, 1, (cuuint32_t)p.th, 1};
+        const cuuint32_t box[5] = {32, (cuuint32_t)p.tw, 1, (cuuint32_t)p.th + 3, 1};  // + 3 row pairs: all taps of a parity
         if (encode(&plan->tmA, canvas, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, "A")) return -1;
     }
     {
