@@ -27,6 +27,7 @@
 // a whole ring ahead of the epilogue; nothing on that path is an uncoalesced per-thread global load.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_tc.cuh"
@@ -794,6 +795,10 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     }
     // K <= 256 (every 1x1 of res2-res4, the 3x3 of res2): HBM-bound, the epilogue is the critical path
     plan->epi_wgs = (!small && p.num_taps * d.Cin <= 256) ? 2 : 1;
+    if (const char* ov = getenv("DAFNE_CONV_WGS")) {  // tuning aid (scripts/prof_conv.py): force 1 | 2
+        const int v = atoi(ov);
+        if (!small && (v == 1 || v == 2)) plan->epi_wgs = v;
+    }
     return 0;
 }
 

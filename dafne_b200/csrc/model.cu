@@ -609,19 +609,20 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     }
     feats[2] = x;
 
-    // ---- FPN (top-down), P6, P7
-    Act prev, P[5];
+    // ---- FPN (top-down), P6, P7. The lateral convs form a chain (each adds the upsampled previous one); the three
+    // output convs only depend on their own lateral sum, so they run as ONE grouped launch afterwards.
+    Act inner[3], P[5];
     for (int i = 2; i >= 0; --i) {
         const std::string lat = "backbone.fpn_lateral" + std::to_string(3 + i);
-        const std::string outn = "backbone.fpn_output" + std::to_string(3 + i);
-        Act inner = (i == 2) ? B.conv(B.layer(lat), feats[i], false) : B.conv(B.layer(lat), feats[i], false, &prev, 1);
+        inner[i] = (i == 2) ? B.conv(B.layer(lat), feats[i], false) : B.conv(B.layer(lat), feats[i], false, &inner[i + 1], 1);
         B.free_act(feats[i]);
-        if (i != 2) B.free_act(prev);
-        P[i] = B.conv(B.layer(outn), inner, false);
-        prev = inner;
         if (B.failed) return -1;
     }
-    B.free_act(prev);
+    B.begin_group("backbone.fpn_output3+4+5");
+    for (int i = 0; i < 3; ++i) P[i] = B.conv(B.layer("backbone.fpn_output" + std::to_string(3 + i)), inner[i], false);
+    B.end_group();
+    if (B.failed) return -1;
+    for (int i = 0; i < 3; ++i) B.free_act(inner[i]);
     for (int i = 0; i < 3; ++i) B.name("p" + std::to_string(3 + i), P[i]);
     P[3] = B.conv(B.layer("backbone.top_block.p6"), P[2], false);
     Act p6r = B.new_act(P[3].N, P[3].H, P[3].W, 256);
