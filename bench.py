@@ -33,7 +33,22 @@ WORKLOADS = {
     "r101_b32": ("configs/dota10_r101_ms.yaml", 32, 1024, 1024, "configs[2]: ResNet-101 DAFNe dota-1.0_r101_ms, batch 32"),
     "r101_b16": ("configs/dota10_r101_ms.yaml", 16, 1024, 1024, "configs[3]: ResNet-101 DAFNe, 16 images per GPU"),
     "hrsc_r50_b8": ("configs/hrsc_r50_ms.yaml", 8, 1024, 1024, "configs[4] (single size): HRSC r50_ms, batch 8"),
+    # configs[4] as the reference runs it: images of 512^2 / 800^2 / 1024^2 in ONE batch, zero-padded to the largest
+    # (ImageList.from_tensors) -- the padded area is computed like the reference computes it, images/s counts images
+    "hrsc_r50_mixed": ("configs/hrsc_r50_ms.yaml", 24, 1024, 1024,
+                       "configs[4]: HRSC r50_ms, mixed 512/800/1024 batch of 24 padded to 1024x1024"),
 }
+MIXED_SIZES = [(512, 512), (800, 800), (1024, 1024)]
+# HRSC (one class) stress recipe: denser candidates (about 10 % of the locations above the threshold instead
+# of 1 % of the (location, class) pairs) and 8:1 elongated base quads, so the rotated NMS sees thousands of overlapping
+# slender boxes per image even with C = 1.
+HRSC_SYNTH = dict(cls_bias=-3.6, base_quad=(-4.0, -0.5, 4.0, -0.5, 4.0, 0.5, -4.0, 0.5))
+
+
+def synth_weights(workload, spec):
+    from dafne_b200.weights import synthetic_state_dict
+
+    return synthetic_state_dict(spec, 0, **(HRSC_SYNTH if workload.startswith("hrsc") else {}))
 GFLOP_PER_IMAGE = {"r50": 505.97, "r101": 661.13}  # BASELINE.md section 2 (C = 15, 1024^2)
 
 
@@ -134,7 +149,7 @@ def run_reference(args):
 
     cfg, spec, batch, H, W, what = load_spec(args.workload)
     cores = os.cpu_count() or 1
-    sd = synthetic_state_dict(spec, 0)
+    sd = synth_weights(args.workload, spec)
     g = torch.Generator().manual_seed(1234)
     imgs = torch.randint(0, 256, (1, 3, H, W), dtype=torch.uint8, generator=g)
     for _ in range(min(args.warmup, 1)):
@@ -181,8 +196,10 @@ def run_ours(args):
     if args.batch:
         batch = args.batch
     eng = DafneEngine(spec, dev)
-    eng.load_state_dict(synthetic_state_dict(spec, 0))
+    eng.load_state_dict(synth_weights(args.workload, spec))
     sizes = [(H, W)] * batch
+    if args.workload.endswith("_mixed"):
+        sizes = [MIXED_SIZES[i % len(MIXED_SIZES)] for i in range(batch)]
     cap = spec.post_nms_topk + 24
 
     # inputs: several distinct batches so the input stream (not only the ~GB of activations) exceeds the 126 MB L2
@@ -294,7 +311,8 @@ def run_ours(args):
             "config": {
                 "workload": args.workload, "what": what, "per_gpu_batch": batch, "global_batch": world * batch,
                 "image": [3, H, W], "resnet_depth": spec.resnet_depth, "num_classes": spec.num_classes,
-                "weights": "seeded random init (dafne_b200.weights.synthetic_state_dict)",
+                "weights": "seeded random init (dafne_b200.weights.synthetic_state_dict"
+                           + (", HRSC stress recipe)" if args.workload.startswith("hrsc") else ")"),
                 "parallelism": f"batch-sharded x{world}, one all-gather of detections" if world > 1 else "single GPU",
                 "l2": f"{n_sets} distinct input batches ({n_sets * batch * 3 * H * W / 2**20:.0f} MiB) rotate; "
                       f"activation workspace {eng.workspace_bytes / 2**20:.0f} MiB >> 126 MiB L2",
@@ -325,7 +343,7 @@ def run_ours(args):
     # CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sd = synthetic_state_dict(spec, 0)
+        sd = synth_weights(args.workload, spec)
         n_img = args.cpu_images
         t0 = time.perf_counter()
         for k in range(n_img):

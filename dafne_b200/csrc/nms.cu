@@ -25,9 +25,13 @@ namespace dafne {
 constexpr int kPanel = 512;
 constexpr int kPanelWords = kPanel / 64;  // 8
 constexpr int kDiagBlocks = kPanelWords * (kPanelWords + 1) / 2;  // 36 (rb <= cb)
-constexpr int kRowChunk = 32;   // kept rows per bcast CTA
-constexpr int kColChunk = 128;  // columns per bcast CTA
+// Work items are deliberately small (16 x 64 pairs): the clips a CTA ends up with vary by an order of magnitude with
+// the local box density, and the hardware's dynamic CTA dispatch balances many small CTAs far better than few big
+// ones (32 x 128 tiles left the SMs idle half of the time behind the densest tiles).
+constexpr int kRowChunk = 16;  // kept rows per bcast CTA
+constexpr int kColChunk = 64;  // columns per bcast CTA
 constexpr int kBcastThreads = 256;
+constexpr int kDiagSplit = 4;  // a 64 x 64 diagonal-panel block is worked on by 4 CTAs of 16 rows each
 
 typedef unsigned long long u64;
 // work counters of the last run_nms (diagnostics, bench.py): pairs the sweep consulted and pairs that needed the clip,
@@ -126,7 +130,7 @@ struct DiagSmem {
     NmsAux raux[64];
     NmsAux caux[64];
     u64 bits[64];
-    unsigned short queue[64 * 64];
+    unsigned short queue[(64 / kDiagSplit) * 64];
     int qn;
     int last;
     unsigned stat_pairs;
@@ -145,7 +149,7 @@ __device__ __forceinline__ void queue_push(unsigned short* queue, int* qn, bool 
     if (want) queue[base + __popc(m & ((1u << lane) - 1u))] = entry;
 }
 
-// grid (36, N), 256 threads. Block b -> (rb, cb), rb <= cb, both 64-box blocks of panel `panel`.
+// grid (36 * kDiagSplit, N), 256 threads. Block b / kDiagSplit -> (rb, cb), rb <= cb, both 64-box blocks of panel `panel`.
 __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __restrict__ boxes, const NmsAux* __restrict__ aux,
                                                       const int* __restrict__ counts, int max_sel, int nblk,
                                                       int panel, float thr, u64* __restrict__ removed,
@@ -157,8 +161,9 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
     const int base = panel * kPanel;
     if (base >= m) return;  // uniform for the whole image: nobody counts, nothing to resolve
     __shared__ DiagSmem sm;
-    // decode (rb, cb) from the linear upper-triangle index
-    int rb = 0, rem = blockIdx.x;
+    // decode (rb, cb) from the linear upper-triangle index; `sub` = which 16 rows of the 64-row block
+    const int sub = blockIdx.x % kDiagSplit;
+    int rb = 0, rem = blockIdx.x / kDiagSplit;
     while (rem >= kPanelWords - rb) {
         rem -= kPanelWords - rb;
         ++rb;
@@ -189,15 +194,16 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
         }
         __syncthreads();
         const int ncol = min(64, m - c0);
-        // phase 1: 4 threads per row, 16 columns each; pre-filter against the alive columns, queue what needs the clip
+        // phase 1: 16 threads per row, 4 columns each; pre-filter against the alive columns, queue what needs the clip
         {
-            const int r = t >> 2, jq = (t & 3) * 16;
+            constexpr int kCols = 64 / (kDiagThreads / (64 / kDiagSplit));  // columns per thread
+            const int r = sub * (64 / kDiagSplit) + t / (64 / kCols), jq = (t % (64 / kCols)) * kCols;
             const unsigned lane = t & 31;
             const bool row_on = r0 + r < m && !((rdead >> r) & 1ull);
             const NmsAux P = sm.raux[row_on ? r : 0];
-            const int jlo = max(jq, (cb == rb) ? r + 1 : 0), jhi = min(jq + 16, ncol);
+            const int jlo = max(jq, (cb == rb) ? r + 1 : 0), jhi = min(jq + kCols, ncol);
             unsigned npairs = 0;
-            for (int u = 0; u < 16; ++u) {
+            for (int u = 0; u < kCols; ++u) {
                 const int j = jq + u;
                 bool want = row_on && j >= jlo && j < jhi && !((cdead >> j) & 1ull);
                 if (want) {
@@ -229,10 +235,11 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
         }
         if (t < 64) bits_out = sm.bits[t];
     }
-    if (t < 64)     diag[(static_cast<size_t>(n) * kPanel + rb * 64 + t) * kPanelWords + cb] = bits_out;
+    if (t >= sub * (64 / kDiagSplit) && t < (sub + 1) * (64 / kDiagSplit))  // this CTA's 16 rows of the block
+        diag[(static_cast<size_t>(n) * kPanel + rb * 64 + t) * kPanelWords + cb] = bits_out;
     __threadfence();
     __syncthreads();
-    if (t == 0) sm.last = (atomicAdd(&ctr[n], 1) == kDiagBlocks - 1);
+    if (t == 0) sm.last = (atomicAdd(&ctr[n], 1) == kDiagBlocks * kDiagSplit - 1);
     __syncthreads();
     if (!sm.last) return;
     __threadfence();
@@ -367,18 +374,17 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
         sm.newdead[t] = 0;
     }
     __syncthreads();
-    // phase 1: 2 threads per column, half of the rows each
+    // phase 1: kBcastThreads / kColChunk threads per column, a slice of the rows each
     {
-        const int j = t & (kColChunk - 1), half = t >> 7;
+        constexpr int kTpc = kBcastThreads / kColChunk, kRpt = (kRowChunk + kTpc - 1) / kTpc;
+        const int j = t % kColChunk, part = t / kColChunk;
         const unsigned lane = t & 31;
         const bool col_on = !sm.dead[j];
         const NmsAux Q = sm.caux[col_on ? j : 0];
-        const int rmid = (nrows + 1) >> 1;
-        const int rlo = half ? rmid : 0, rhi = half ? nrows : rmid;
         unsigned npairs = 0;
-        for (int u = 0; u < (kRowChunk + 1) / 2; ++u) {
-            const int r = rlo + u;
-            bool want = col_on && r < rhi;
+        for (int u = 0; u < kRpt; ++u) {
+            const int r = part * kRpt + u;
+            bool want = col_on && r < nrows;
             if (want) {
                 ++npairs;
                 const NmsAux& P = sm.raux[r];
@@ -453,7 +459,7 @@ int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float th
     const int panels = (max_sel + kPanel - 1) / kPanel;
     int nl = 1;
     for (int p = 0; p < panels; ++p) {
-        nms_diag_kernel<<<dim3(kDiagBlocks, N), kDiagThreads, 0, s>>>(nmsbox, aux, counts, max_sel, y.nblk, p, thr, removed, diag,
+        nms_diag_kernel<<<dim3(kDiagBlocks * kDiagSplit, N), kDiagThreads, 0, s>>>(nmsbox, aux, counts, max_sel, y.nblk, p, thr, removed, diag,
                                                             pk, ctr, keep, nkeep, stats);
         NMS_CHECK_LAUNCH("nms_diag_kernel");
         ++nl;
