@@ -6,6 +6,7 @@
 
 #include "conv_tc.cuh"
 #include "elementwise.cuh"
+#include "merge_nms.cuh"
 #include "model.cuh"
 #include "postprocess.cuh"
 #include <string.h>
@@ -329,6 +330,23 @@ int dafne_detect_host_end(dafne_ctx* ctx, int ticket) {
         return -1;
     }
     return 0;
+}
+
+int dafne_poly_nms_f64_batch_host(const double* dets_host, const int32_t* offsets, int nproblems, double thresh,
+                                  int device_id, int32_t* keep_out, int32_t* nkeep_out) {
+    return merge_nms_f64_batch_host(dets_host, offsets, nproblems, thresh, device_id, keep_out, nkeep_out);
+}
+
+int dafne_poly_nms_f64_host(const double* dets_host, int n, double thresh, int device_id, int32_t* keep_out,
+                            int32_t* num_out) {
+    if (n < 0 || !num_out) {
+        set_error("dafne_poly_nms_f64_host: bad arguments");
+        return -1;
+    }
+    *num_out = 0;
+    if (n == 0) return 0;
+    const int32_t offsets[2] = {0, n};
+    return merge_nms_f64_batch_host(dets_host, offsets, 1, thresh, device_id, keep_out, num_out);
 }
 
 int dafne_debug_keep_activations(dafne_ctx* ctx, int keep) {

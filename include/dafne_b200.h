@@ -17,6 +17,7 @@
  *   dafne/modeling/nms/nms.py:10-92                ml_nms / batched_nms_poly                    -> dafne_poly_nms
  *   dafne/modeling/nms/nms.py:91                   poly_gpu_nms(dets[n,9] host, thr, device_id) -> dafne_poly_nms_host
  *   tools/prepare_dota/polyiou.cpp:108-133         iou_poly                                     -> dafne_poly_iou
+ *   dafne/utils/ResultMerge_multi_process.py:61-122  py_cpu_nms_poly_fast (patch merge, double) -> dafne_poly_nms_f64_host
  */
 #ifndef DAFNE_B200_H
 #define DAFNE_B200_H
@@ -204,6 +205,21 @@ int dafne_poly_nms_scratch_bytes(int n, size_t* bytes);
  * score, class offsets already applied by the caller), synchronous. */
 int dafne_poly_nms_host(int* keep_out, int* num_out, const float* polys_host, int polys_num, int polys_dim,
                         float nms_overlap_thresh, int device_id);
+
+/* ------------------------------------------------------------------ next to the path: patch-merge NMS */
+/* Device implementation of the reference's py_cpu_nms_poly_fast(dets, thresh)
+ * (dafne/utils/ResultMerge_multi_process.py:61-122), the polygon NMS that merges per-patch detections back into full
+ * DOTA images: DOUBLE precision, polyiou.iou_poly arithmetic (tools/prepare_dota/polyiou.cpp:108-133) evaluated only
+ * for pairs whose horizontal boxes overlap, a box dropped unless ovr <= thresh. Host pointers in and out, synchronous.
+ * dets_host = [n][9] doubles (8 coordinates + score); keep_out[n] receives the kept input indices in descending score
+ * order (equal scores: ascending index), *num_out their number. */
+int dafne_poly_nms_f64_host(const double* dets_host, int n, double thresh, int device_id, int32_t* keep_out,
+                            int32_t* num_out);
+/* The same for many (class, image) lists in one call -- what nmsbynamedict / mergesingle loop over on a 16-process
+ * host pool (ResultMerge_multi_process.py:155-232): list p = rows offsets[p] .. offsets[p+1] of dets_host; its kept
+ * LOCAL indices land at keep_out[offsets[p] .. offsets[p] + nkeep_out[p]). */
+int dafne_poly_nms_f64_batch_host(const double* dets_host, const int32_t* offsets, int nproblems, double thresh,
+                                  int device_id, int32_t* keep_out, int32_t* nkeep_out);
 
 #ifdef __cplusplus
 }
