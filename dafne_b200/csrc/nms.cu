@@ -307,7 +307,7 @@ struct BcastSmem {
     NmsAux caux[kColChunk];
     unsigned short queue[kRowChunk * kColChunk];
     unsigned char dead[kColChunk];
-    unsigned char newdead[kColChunk];
+    unsigned int newdead[kColChunk];  // 0 -> 1 flags, touched with atomics while phase 2 runs
     int rows[kRowChunk];
     int qn;
     unsigned stat_pairs;
@@ -403,10 +403,12 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
         const int e = e0 + (t >> 4);
         bool active = e < qn;
         const int r = active ? sm.queue[e] >> 7 : 0, j = active ? sm.queue[e] & 127 : 0;
-        if (active && sm.newdead[j]) active = false;  // benign race: any kept row that hits is enough
+        // a column some kept row already hit needs no further clip (any hit is enough); atomic read / write of the
+        // 0 -> 1 flag so that concurrent warps are race-free by construction (compute-sanitizer racecheck clean)
+        if (active && atomicOr(&sm.newdead[j], 0u)) active = false;
         const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active,
                                             lane, sm.poly + t, kBcastThreads);
-        if (hit && (lane & 15) == 0) sm.newdead[j] = 1;
+        if (hit && (lane & 15) == 0) atomicExch(&sm.newdead[j], 1u);
     }
     if (t == 0) {
         atomicAdd(stats + kStBcastPairs, static_cast<u64>(sm.stat_pairs));

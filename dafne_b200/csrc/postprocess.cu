@@ -869,9 +869,93 @@ __global__ void nms_gather_kernel(const int* __restrict__ order, const int* __re
     if (blockIdx.x == 0 && threadIdx.x == 0) *nkeep_out = nk;
 }
 
+// ---- more than kMaxSorted boxes (the TTA union of up to 27 augmented copies x 1000 detections, tta.py:264-268):
+// chunks of kMaxSorted keys are sorted in shared memory, merged pairwise by rank (all keys are distinct: score bits
+// above, inverted input index below), and one CTA then derives the class offsets and writes the NMS boxes.
+constexpr int kMaxNmsBoxes = 65536;
+
+__global__ void __launch_bounds__(1024) nms_sort_chunk_kernel(const float* __restrict__ scores, int n,
+                                                              unsigned long long* __restrict__ keys) {
+    extern __shared__ unsigned long long s_keys[];
+    const int base = blockIdx.x * kMaxSorted;
+    const int cnt = min(kMaxSorted, n - base);
+    int np2 = 1;
+    while (np2 < cnt) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x)
+        s_keys[i] = i < cnt ? ((static_cast<unsigned long long>(__float_as_uint(scores[base + i])) << 32) |
+                               (0xFFFFFFFFu - static_cast<unsigned>(base + i)))
+                            : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(s_keys, np2);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) keys[base + i] = s_keys[i];
+}
+
+// merges descending runs [2r*len, 2r*len + len) and [2r*len + len, 2r*len + 2*len) of `in` (clipped to n) into `out`
+__global__ void nms_merge_runs_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out,
+                                      int n, int len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int pair0 = (i / (2 * len)) * (2 * len);
+    const int a0 = pair0, a1 = min(pair0 + len, n), b0 = a1, b1 = min(pair0 + 2 * len, n);
+    const unsigned long long key = in[i];
+    const bool in_a = i < a1;
+    // number of elements of the OTHER run that come before `key` in descending order (keys are distinct)
+    int lo = in_a ? b0 : a0, hi = in_a ? b1 : a1;
+    const int other0 = lo;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (in[mid] > key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    out[pair0 + (i - (in_a ? a0 : b0)) + (lo - other0)] = key;
+}
+
+// the tail of nms_prepare_kernel for keys that are already sorted (one CTA)
+__global__ void __launch_bounds__(1024) nms_prepare_sorted_kernel(const float* __restrict__ polys,
+                                                                  const int* __restrict__ classes,
+                                                                  const unsigned long long* __restrict__ keys, int n,
+                                                                  int vehicle_merge, float* __restrict__ nmsbox,
+                                                                  int* __restrict__ order, int* __restrict__ count) {
+    __shared__ float s_min[32], s_max[32];
+    float vmin = INFINITY, vmax = -INFINITY;
+    for (int i = threadIdx.x; i < n * 8; i += blockDim.x) {
+        vmin = fminf(vmin, polys[i]);
+        vmax = fmaxf(vmax, polys[i]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_min[threadIdx.x >> 5] = vmin;
+        s_max[threadIdx.x >> 5] = vmax;
+    }
+    __syncthreads();
+    vmin = s_min[0];
+    vmax = s_max[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) {
+        vmin = fminf(vmin, s_min[w]);
+        vmax = fmaxf(vmax, s_max[w]);
+    }
+    const float span = vmax - vmin + 1.0f;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const int src = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(keys[r] & 0xFFFFFFFFu));
+        order[r] = src;
+        int c = classes ? classes[src] : 0;
+        if (vehicle_merge && c == 5) c = 4;
+        const float off = static_cast<float>(c) * span;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nmsbox[r * 8 + k] = polys[src * 8 + k] + off;
+    }
+    if (threadIdx.x == 0) *count = n;
+}
+
 size_t poly_nms_scratch_bytes(int n) {
     const size_t ms = n < 1 ? 1 : n;
-    return a256(ms * 32) + a256(ms * 4) + a256(4) + a256(nms_scratch_bytes(1, static_cast<int>(ms))) + a256(ms * 4) + a256(4);
+    return a256(ms * 32) + a256(ms * 4) + a256(4) + a256(nms_scratch_bytes(1, static_cast<int>(ms))) + a256(ms * 4) +
+           a256(4) + (n > kMaxSorted ? 2 * a256(ms * 8) : 0);
 }
 
 int launch_poly_nms(const float* polys, const float* scores, const int32_t* classes, int n, float thresh,
@@ -890,8 +974,8 @@ int launch_poly_nms(const float* polys, const float* scores, const int32_t* clas
         }
         return 0;
     }
-    if (n > kMaxSorted) {
-        set_error("poly_nms: n=%d exceeds the supported %d boxes per image", n, kMaxSorted);
+    if (n > kMaxNmsBoxes) {
+        set_error("poly_nms: n=%d exceeds the supported %d boxes per image", n, kMaxNmsBoxes);
         return -1;
     }
     if (poly_nms_scratch_bytes(n) > scratch_bytes) {
@@ -912,21 +996,51 @@ int launch_poly_nms(const float* polys, const float* scores, const int32_t* clas
     int* keep_pos = reinterpret_cast<int*>(b);
     b += a256(ms * 4);
     int* nk = reinterpret_cast<int*>(b);
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    const size_t smem = static_cast<size_t>(np2) * 8;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(nms_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) {
-            set_error("nms_prepare_kernel smem attribute: %s", cudaGetErrorString(e));
-            return -1;
+    b += a256(4);
+    if (n <= kMaxSorted) {
+        int np2 = 1;
+        while (np2 < n) np2 <<= 1;
+        const size_t smem = static_cast<size_t>(np2) * 8;
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(nms_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(smem));
+            if (e != cudaSuccess) {
+                set_error("nms_prepare_kernel smem attribute: %s", cudaGetErrorString(e));
+                return -1;
+            }
+            configured = smem;
         }
-        configured = smem;
+        nms_prepare_kernel<<<1, 1024, smem, s>>>(polys, scores, classes, n, vehicle_merge, nmsbox, order, count);
+        POST_CHECK_LAUNCH("nms_prepare_kernel");
+    } else {
+        unsigned long long* keys_a = reinterpret_cast<unsigned long long*>(b);
+        b += a256(ms * 8);
+        unsigned long long* keys_b = reinterpret_cast<unsigned long long*>(b);
+        const size_t smem = static_cast<size_t>(kMaxSorted) * 8;
+        static bool configured_chunk = false;
+        if (!configured_chunk) {
+            cudaError_t e = cudaFuncSetAttribute(nms_sort_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(smem));
+            if (e != cudaSuccess) {
+                set_error("nms_sort_chunk_kernel smem attribute: %s", cudaGetErrorString(e));
+                return -1;
+            }
+            configured_chunk = true;
+        }
+        const int chunks = (n + kMaxSorted - 1) / kMaxSorted;
+        nms_sort_chunk_kernel<<<chunks, 1024, smem, s>>>(scores, n, keys_a);
+        POST_CHECK_LAUNCH("nms_sort_chunk_kernel");
+        for (int len = kMaxSorted; len < n; len *= 2) {
+            nms_merge_runs_kernel<<<(n + 255) / 256, 256, 0, s>>>(keys_a, keys_b, n, len);
+            POST_CHECK_LAUNCH("nms_merge_runs_kernel");
+            unsigned long long* t = keys_a;
+            keys_a = keys_b;
+            keys_b = t;
+        }
+        nms_prepare_sorted_kernel<<<1, 1024, 0, s>>>(polys, classes, keys_a, n, vehicle_merge, nmsbox, order, count);
+        POST_CHECK_LAUNCH("nms_prepare_sorted_kernel");
     }
-    nms_prepare_kernel<<<1, 1024, smem, s>>>(polys, scores, classes, n, vehicle_merge, nmsbox, order, count);
-    POST_CHECK_LAUNCH("nms_prepare_kernel");
     if (run_nms(nmsbox, count, 1, n, thresh, nms_scratch, nms_bytes, keep_pos, nk, s, nullptr)) return -1;
     nms_gather_kernel<<<8, 256, 0, s>>>(order, keep_pos, nk, keep_out, nkeep_out);
     POST_CHECK_LAUNCH("nms_gather_kernel");

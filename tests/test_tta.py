@@ -1,0 +1,119 @@
+"""Test-time augmentation: the mapper's transforms on the CPU, the device wrapper against the oracle's
+restatement of the merge (tta.py:232-268) on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from dafne_b200 import tta
+from dafne_b200.config import get_cfg
+
+
+def _cfg(min_sizes=(96, 128), max_size=160, hflip=True, vflip=True):
+    cfg = get_cfg()
+    cfg.TEST.AUG.MIN_SIZES = list(min_sizes)
+    cfg.TEST.AUG.MAX_SIZE = max_size
+    cfg.TEST.AUG.HFLIP = hflip
+    cfg.TEST.AUG.VFLIP = vflip
+    return cfg
+
+
+def test_resize_shortest_edge_sizes_like_detectron2():
+    t = tta.resize_shortest_edge_transform(480, 640, 800, 1333)
+    assert (t.new_h, t.new_w) == (800, 1067)
+    t = tta.resize_shortest_edge_transform(500, 2000, 800, 1333)  # capped by max_size
+    assert (t.new_h, t.new_w) == (333, 1333)
+    t = tta.resize_shortest_edge_transform(1024, 1024, 1200, 1200)
+    assert (t.new_h, t.new_w) == (1200, 1200)
+
+
+def test_transform_inverse_round_trip_and_device_free_math():
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0, 300, (50, 2)).astype(np.float32)
+    tl = tta.ResizeTransform(300, 400, 150, 260) + tta.TransformList([tta.HFlipTransform(260), tta.VFlipTransform(150)])
+    fwd = tl.apply_coords(pts.copy())
+    back = tl.inverse().apply_coords(fwd.copy())
+    assert np.abs(back - pts).max() < 1e-3
+    img = rng.integers(0, 256, (300, 400, 3), dtype=np.uint8)
+    out = tl.apply_image(img)
+    assert out.shape == (150, 260, 3) and out.dtype == np.uint8
+    # flips are exact pixel permutations of the resized image
+    res = tta.ResizeTransform(300, 400, 150, 260).apply_image(img)
+    assert np.array_equal(out, res[::-1, ::-1])
+
+
+def test_mapper_builds_the_reference_s_copies():
+    cfg = _cfg()
+    g = torch.Generator().manual_seed(0)
+    image = torch.randint(0, 256, (3, 100, 140), dtype=torch.uint8, generator=g)
+    copies = tta.DotaDatasetMapperTTA(cfg)({"image": image, "height": 200, "width": 280})
+    assert len(copies) == 2 * 3  # len(MIN_SIZES) x (plain, hflip, vflip)   (tta.py:69-135)
+    shapes = [tuple(c["image"].shape) for c in copies]
+    assert shapes[0] == shapes[1] == shapes[2] == (3, 96, 134)
+    assert shapes[3] == shapes[4] == shapes[5] == (3, 114, 160)  # capped by MAX_SIZE
+    for c in copies:
+        # the transform chain maps original-image coordinates to this copy's coordinates
+        h, w = c["image"].shape[1:]
+        corner = c["transforms"].apply_coords(np.array([[280.0, 200.0]], np.float32))
+        assert abs(abs(corner[0, 0] - w / 2) - w / 2) < 1e-2 and abs(abs(corner[0, 1] - h / 2) - h / 2) < 1e-2
+    assert torch.equal(copies[1]["image"], copies[0]["image"].flip(2))
+    assert torch.equal(copies[2]["image"], copies[0]["image"].flip(1))
+    with pytest.raises(NotImplementedError):
+        cfg.TEST.AUG.ROTATION_ANGLES = [90]
+        tta.DotaDatasetMapperTTA(cfg)
+
+
+@pytest.mark.gpu
+def test_tta_wrapper_equals_oracle_merge_of_the_copies():
+    from dafne_b200.modeling import build_model
+    from oracle import tta as otta
+
+    cfg = _cfg(min_sizes=(160, 192, 256), max_size=320)
+    cfg.MODEL.DEVICE = "cuda:0"
+    model = build_model(cfg)
+    wrapper = tta.OneStageRCNNWithTTA(cfg, model)
+    g = torch.Generator().manual_seed(4)
+    image = torch.randint(0, 256, (3, 200, 256), dtype=torch.uint8, generator=g)
+    inp = {"image": image, "height": 400, "width": 512}
+    out = wrapper([inp])[0]["instances"]
+    # the oracle merges what the SAME model returns for each augmented copy
+    copies = wrapper.tta_mapper(inp)
+    tfms = [c.pop("transforms") for c in copies]
+    per_copy = wrapper._batch_inference(copies)
+    corners = [o["instances"].pred_corners.cpu().numpy() for o in per_copy]
+    scores = [o["instances"].scores.cpu().numpy() for o in per_copy]
+    classes = [o["instances"].pred_classes.cpu().numpy() for o in per_copy]
+    assert sum(len(s) for s in scores) > 50, "the synthetic model should detect something in every copy"
+    spec = model.spec
+    want_c, want_s, want_k, _ = otta.merge_detections(corners, scores, classes, tfms, spec.nms_thresh,
+                                                      spec.post_nms_topk, spec.vehicle_merge)
+    assert len(out) == len(want_s)
+    assert np.array_equal(out.scores.cpu().numpy(), want_s)
+    assert np.array_equal(out.pred_classes.cpu().numpy(), want_k)
+    assert np.array_equal(out.pred_corners.cpu().numpy(), want_c)
+    # corners are in the coordinates of the ORIGINAL image (height / width), not of the input tensor
+    assert out.pred_corners[:, 0::2].max() > 256
+
+
+@pytest.mark.gpu
+def test_poly_nms_beyond_the_shared_memory_sort():
+    """The TTA union can hold 27 copies x 1000 boxes: more than the 16 384 keys one CTA sorts in shared memory."""
+    from dafne_b200.modeling import batched_nms_poly
+    from oracle import postprocess as opost
+
+    rng = np.random.default_rng(2)
+    n = 20000
+    cx, cy = rng.uniform(0, 1500, n), rng.uniform(0, 1500, n)
+    w, h, a = rng.uniform(20, 60, n), rng.uniform(8, 20, n), rng.uniform(0, np.pi, n)
+    dx = np.stack([-w, w, w, -w], 1) / 2
+    dy = np.stack([-h, -h, h, h], 1) / 2
+    boxes = np.stack([cx[:, None] + dx * np.cos(a)[:, None] - dy * np.sin(a)[:, None],
+                      cy[:, None] + dx * np.sin(a)[:, None] + dy * np.cos(a)[:, None]], 2).reshape(n, 8).astype(np.float32)
+    scores = (rng.permutation(n) / n).astype(np.float32)
+    classes = rng.integers(0, 3, n)
+    keep = batched_nms_poly(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(),
+                            torch.from_numpy(classes).cuda(), 0.1).cpu().numpy()
+    order = np.lexsort((np.arange(n), -scores.astype(np.float64)))
+    span = (boxes.max() - boxes.min()) + np.float32(1.0)
+    shifted = boxes + (classes.astype(np.float32) * span)[:, None]
+    want = order[opost.greedy_nms(shifted[order], 0.1)]
+    assert np.array_equal(keep, want)
