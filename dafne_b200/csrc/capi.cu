@@ -76,6 +76,7 @@ int dafne_conv_nhwc(const void* in, int N, int H, int W, int Cin, const void* w,
         return -1;
     }
     return conv_group_launch(dev_prob, 1, plan.prob.p.total_tiles, plan.block_n, plan.epi_wgs, plan.mode, plan.res_tma, plan.row_shared,
+                             plan.breg_bytes,
                              num_sms_cached(), s);
 }
 

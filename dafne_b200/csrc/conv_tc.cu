@@ -10,12 +10,15 @@
 // input patch lands directly in the canonical K-major SWIZZLE_128B operand layout; out-of-image coordinates are
 // zero-filled by TMA, which is exactly the conv zero padding. Nothing im2col-shaped ever exists in HBM.
 //
-// Row-shared taps (3x3 stride 1 with a narrow N tile, where the kernel is bound by L2 -> shared-memory fills, not by
-// the tensor pipe: the prediction convs, res2's 3x3): the pixel tile is 8 wide x 16 high, so one row of it is exactly
-// one 1024-byte swizzle atom. ONE box of 18 rows (the tile plus a row above and below) per horizontal tap dx then
-// serves all three vertical taps: the operand of tap (dy, dx) is the same shared-memory box read from row 1 + dy on --
-// a descriptor start that moves by whole atoms, so the canonical layout is untouched. Three A loads per channel
-// block instead of nine.
+// Halo box (3x3 stride 1 with a narrow N tile, where the kernel is bound by L2 -> shared-memory fills, not by the
+// tensor pipe: the prediction convs, res2's 3x3): the pixel tile is 8 wide x 16 high and ONE box of 18 rows x 10
+// pixels (the tile plus a one-pixel border) per channel block serves all nine taps: the operand of tap (dy, dx) is
+// that box read from pixel (1 + dy) * 10 + (1 + dx) on, eight consecutive pixels per 8-row group, groups 10 pixels
+// (1280 B) apart. Such a descriptor start is not on a 1024-byte atom boundary; it works because both TMA and the
+// tensor core derive the 128-byte swizzle from the shared-memory ADDRESS bits [7, 10) (measured: results bit-equal to
+// the atom-aligned forms with base_offset = 0, wrong with base_offset = start >> 7). One A load per channel block
+// instead of nine. (The "row-shared" predecessor -- 8-pixel-wide boxes, one per dx, starts moving by whole atoms --
+// is kept for A/B runs, DAFNE_CONV_TAPS=rows.)
 //
 // Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
 // warp 3 = residual producer, warps 4-7 = epilogue (TMEM -> registers -> scale/shift/residual/ReLU -> fp16 -> swizzled
@@ -63,12 +66,24 @@ struct ConvCfg {
     static constexpr int A_RS_BOX_BYTES = 18 * 1024;
     static constexpr int A_RS_BYTES = 19 * 1024;
     static constexpr int STAGE_BYTES_RS = A_RS_BYTES + 3 * B_BYTES;
-    static constexpr int smem_bytes(int stages, int ring, int row_shared = 0) {
-        return stages * (row_shared ? STAGE_BYTES_RS : STAGE_BYTES) +
+    // halo box: one 18-row x 10-pixel box per channel block serves all nine taps through descriptor starts that are
+    // NOT atom-aligned (stride between 8-row groups = 10 pixels = 1280 B)
+    static constexpr int A_HALO_BOX_BYTES = 18 * 10 * 128;
+    static constexpr int A_HALO_BYTES = 23 * 1024;
+    static constexpr int STAGE_BYTES_HALO = A_HALO_BYTES + 9 * B_BYTES;
+    // mode 3 = halo box with the whole weight tensor of the problem RESIDENT in shared memory (all taps x channel
+    // blocks, <= kMaxResidentB bytes): it is loaded once per run of tiles that share it, a stage is the A box alone
+    __host__ __device__ static constexpr int stage_bytes(int row_shared) {
+        return row_shared == 3 ? A_HALO_BYTES
+                               : (row_shared == 2 ? STAGE_BYTES_HALO : (row_shared ? STAGE_BYTES_RS : STAGE_BYTES));
+    }
+    static constexpr int smem_bytes(int stages, int ring, int row_shared = 0, int breg_bytes = 0) {
+        return breg_bytes + stages * stage_bytes(row_shared) +
                (BLOCK_N >= 64 ? EPI_WGS * ring * SLOT_BYTES : 0) + AUX_BYTES;
     }
 };
 constexpr int kMaxSmem = 232448;  // 227 KB
+constexpr int kMaxResidentB = 72 * 1024;
 
 // Sum 16 per-lane values across the warp; lane l returns the total of value index
 // 8*b4 + 4*b3 + 2*b2 + b1 (b_i = bit i of l). 16 shuffles instead of 80.
@@ -154,7 +169,7 @@ __device__ __forceinline__ void epilogue_chunk_math(const uint32_t (&v)[64], con
 template <int BLOCK_N, int EPI_WGS, int MODE>
 __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
     conv_tc_kernel(const ConvProblem* __restrict__ probs, int nprob, int total_tiles, int stages, int ring,
-                   int res_tma_arg, int row_shared) {
+                   int res_tma_arg, int row_shared, int breg_bytes) {
     const int res_tma = MODE == 1 ? res_tma_arg : 0;
     using Cfg = ConvCfg<BLOCK_N, EPI_WGS>;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -167,13 +182,15 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
         __trap();
     }
 
-    // carve-up: [stages x (A | B)] [EPI_WGS x ring x 16 KB epilogue slots] [512 B header] [(scale, shift) tables]
+    // carve-up: [resident weights (mode 3)] [stages x (A | B)] [EPI_WGS x ring x 16 KB epilogue slots] [512 B header]
+    // [(scale, shift) tables]
     const int epi_bytes = BLOCK_N >= 64 ? EPI_WGS * ring * Cfg::SLOT_BYTES : 0;
-    const uint32_t s_tiles = smem_base;
-    const int stage_bytes = row_shared ? Cfg::STAGE_BYTES_RS : Cfg::STAGE_BYTES;
-    const uint32_t s_epi = smem_base + stages * stage_bytes;
+    const uint32_t s_bres = smem_base;
+    const uint32_t s_tiles = smem_base + breg_bytes;
+    const int stage_bytes = Cfg::stage_bytes(row_shared);
+    const uint32_t s_epi = s_tiles + stages * stage_bytes;
     const uint32_t s_aux = s_epi + epi_bytes;
-    uint8_t* aux = smem + stages * stage_bytes + epi_bytes;
+    uint8_t* aux = smem + breg_bytes + stages * stage_bytes + epi_bytes;
     const uint32_t bar_full = s_aux;             // 8 x 8 B
     const uint32_t bar_empty = s_aux + 64;       // 8 x 8 B
     const uint32_t bar_tfull = s_aux + 128;      // 2 x 8 B
@@ -182,6 +199,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
     int* s_begin = reinterpret_cast<int*>(aux + 168);  // nprob + 1 tile offsets (<= 17 ints)
     const uint32_t bar_rfull = s_aux + 256;      // [EPI_WGS][4] x 8 B: residual chunk landed in the slot
     const uint32_t bar_rempty = s_aux + 320;     // [EPI_WGS][4] x 8 B: the slot's output store has been read out
+    const uint32_t bar_bfull = s_aux + 384;      // resident weights landed
     float2* s_tab_all = reinterpret_cast<float2*>(aux + Cfg::AUX_HDR);
 
     if (warp == 0 && lane < nprob) {
@@ -204,6 +222,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             mbar_init(bar_rfull + 8 * i, 1);
             mbar_init(bar_rempty + 8 * i, 1);
         }
+        mbar_init(bar_bfull, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -225,12 +244,61 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             int stage = 0;
             uint32_t phase = 0;
             int g = 0;
+            long long bkey = -1;  // mode 3: which weights are resident
+            int last_stage = -1;
+            uint32_t last_phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 while (t >= s_begin[g + 1]) ++g;
                 const ConvProblem* pr = probs + g;
                 const ConvParams& p = pr->p;
                 const TileCoord tc = tile_coord(p, t - s_begin[g]);
                 const int num_taps = p.num_taps, cin_blocks = p.cin_blocks, Cin = p.Cin;
+                if (row_shared == 3) {
+                    // weights of this (problem, n tile): resident, reloaded only when they change -- after the MMAs
+                    // that still read the old ones have drained (the last stage filled has been consumed)
+                    const long long key = (static_cast<long long>(reinterpret_cast<uintptr_t>(p.w_id)) << 8) | tc.nt;
+                    if (key != bkey) {
+                        if (last_stage >= 0) mbar_wait(bar_empty + 8 * last_stage, last_phase);
+                        mbar_arrive_expect_tx(bar_bfull, 9 * cin_blocks * Cfg::B_BYTES);
+                        for (int cb = 0; cb < cin_blocks; ++cb)
+                            for (int tap = 0; tap < 9; ++tap)
+                                tma_load_2d(s_bres + (cb * 9 + tap) * Cfg::B_BYTES, &pr->tmB, bar_bfull,
+                                            tap * Cin + cb * 64, tc.nt * BLOCK_N);
+                        bkey = key;
+                    }
+                    for (int cb = 0; cb < cin_blocks; ++cb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t full = bar_full + 8 * stage;
+                        mbar_arrive_expect_tx(full, Cfg::A_HALO_BOX_BYTES);
+                        tma_load_4d(s_tiles + stage * stage_bytes, &pr->tmA[0], full, cb * 64, tc.x0 - 1, tc.y0 - 1,
+                                    tc.n0);
+                        last_stage = stage;
+                        last_phase = phase;
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    continue;
+                }
+                if (row_shared == 2) {
+                    for (int cb = 0; cb < cin_blocks; ++cb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t full = bar_full + 8 * stage;
+                        mbar_arrive_expect_tx(full, Cfg::A_HALO_BOX_BYTES + 9 * Cfg::B_BYTES);
+                        const uint32_t sA = s_tiles + stage * stage_bytes;
+                        tma_load_4d(sA, &pr->tmA[0], full, cb * 64, tc.x0 - 1, tc.y0 - 1, tc.n0);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap)
+                            tma_load_2d(sA + Cfg::A_HALO_BYTES + tap * Cfg::B_BYTES, &pr->tmB, full, tap * Cin + cb * 64,
+                                        tc.nt * BLOCK_N);
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    continue;
+                }
                 if (row_shared) {
                     // one 18-row box per (dx, channel block) + the weights of its three vertical taps
                     for (int dxi = 0; dxi < 3; ++dxi) {
@@ -279,9 +347,21 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             int acc = 0;
             uint32_t acc_phase = 0;
             int g = 0;
+            long long bkey = -1;
+            uint32_t bphase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 while (t >= s_begin[g + 1]) ++g;
-                const int num_kb = (row_shared ? 3 : probs[g].p.num_taps) * probs[g].p.cin_blocks;
+                const int num_kb =
+                    (row_shared >= 2 ? 1 : (row_shared ? 3 : probs[g].p.num_taps)) * probs[g].p.cin_blocks;
+                if (row_shared == 3) {
+                    const long long key = (static_cast<long long>(reinterpret_cast<uintptr_t>(probs[g].p.w_id)) << 8) |
+                                          ((t - s_begin[g]) % probs[g].p.n_tiles);
+                    if (key != bkey) {
+                        mbar_wait(bar_bfull, bphase);
+                        bphase ^= 1;
+                        bkey = key;
+                    }
+                }
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * BLOCK_N;
@@ -289,7 +369,22 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sA = s_tiles + stage * stage_bytes;
-                    if (row_shared) {
+                    if (row_shared >= 2) {
+                        // The issuing thread is the bottleneck of these narrow-N convolutions (a 128 x 16 x 16 MMA
+                        // is done in a few dozen cycles): both base descriptors are built once per stage and the 36
+                        // MMAs differ by compile-time constants only. In the halo modes kb is the channel block.
+                        const uint64_t a_base = umma_desc_sw128_ex(sA, 1280, 0);
+                        const uint64_t b_base = umma_desc_sw128(row_shared == 3 ? s_bres + kb * 9 * Cfg::B_BYTES
+                                                                                : sA + Cfg::A_HALO_BYTES);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint64_t ad = a_base + (((tap / 3) * 10 + (tap % 3)) * 128 >> 4);
+                            const uint64_t bd = b_base + (tap * Cfg::B_BYTES >> 4);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16(d, ad + 2 * k, bd + 2 * k, idesc, (tap | k) != 0 ? 1u : (kb != 0));
+                        }
+                    } else if (row_shared) {
 #pragma unroll
                         for (int dyi = 0; dyi < 3; ++dyi) {
                             // rows dyi .. dyi+15 of the 18-row box: the start moves by whole 1024-byte atoms
@@ -683,6 +778,22 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     // three weight tiles of a stage must leave room for a four-stage pipeline (bn <= 64).
     const bool row_shared = d.ksize == 3 && d.stride == 1 && bn <= 64;
     plan->row_shared = row_shared ? 1 : 0;
+    // 2 = halo box (one A load per channel block serves all nine taps); DAFNE_CONV_TAPS=rows selects the older
+    // row-shared form (three loads, atom-aligned descriptor starts only) for A/B measurements
+    bool halo = row_shared;
+    if (const char* hv = getenv("DAFNE_CONV_TAPS"))
+        if (strcmp(hv, "rows") == 0) halo = false;
+    if (halo) plan->row_shared = 2;
+    plan->breg_bytes = 0;
+    if (halo && 9 * (d.Cin / 64) * bn * 128 <= kMaxResidentB) {
+        // weights resident in shared memory: measured equal to streaming them per stage (both end up bound by the
+        // tensor core's ~76 cycles per 128 x 16 x 16 MMA), so it stays an A/B option
+        if (const char* hv = getenv("DAFNE_CONV_TAPS"))
+            if (strcmp(hv, "resident") == 0) {
+                plan->row_shared = 3;
+                plan->breg_bytes = 9 * (d.Cin / 64) * bn * 128;
+            }
+    }
     if (row_shared) {
         p.tw = 8;
         p.th = 16;
@@ -709,13 +820,14 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     p.gn_sums = d.gn_sums;
     p.out_f32 = d.out_f32;
     p.out_ld = d.out_ld;
+    p.w_id = d.w;
     plan->block_n = bn;
     plan->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     plan->flops = 2.0 * d.N * d.Hout * d.Wout * (double)d.Cout * p.num_taps * d.Cin;
 
     const uint64_t C = d.Cin, W = d.Win, H = d.Hin;
     const uint32_t boxA[4] = {64u, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.nb};
-    const uint32_t boxA_rs[4] = {64u, 8u, 18u, 1u};  // the tile plus one row above and below
+    const uint32_t boxA_rs[4] = {64u, halo ? 10u : 8u, 18u, 1u};  // the tile plus one row above and below
     bool view_empty[4] = {false, false, false, false};
     if (d.stride == 1) {
         const uint64_t dims[4] = {C, W, H, (uint64_t)d.N};
@@ -805,19 +917,19 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
 // Operand stages / epilogue ring slots per warpgroup for a launch: as deep as 227 KB allows. With a TMA residual the
 // ring is the prefetch depth of the residual stream, so it gets four slots at the price of operand stages.
 template <int BN, int WGS>
-static void conv_smem_config(int res_tma, int row_shared, int* stages, int* ring) {
+static void conv_smem_config(int res_tma, int row_shared, int breg, int* stages, int* ring) {
     using Cfg = ConvCfg<BN, WGS>;
     int r = BN < 64 ? 2 : (res_tma ? 4 : (WGS == 2 ? 3 : 2));
     int st = Cfg::MAX_STAGES;
-    while (st > 2 && Cfg::smem_bytes(st, r, row_shared) > kMaxSmem) --st;
-    while (r > 2 && Cfg::smem_bytes(st, r, row_shared) > kMaxSmem) --r;
+    while (st > 2 && Cfg::smem_bytes(st, r, row_shared, breg) > kMaxSmem) --st;
+    while (r > 2 && Cfg::smem_bytes(st, r, row_shared, breg) > kMaxSmem) --r;
     *stages = st;
     *ring = r;
 }
 
 template <int BN, int WGS, int MODE>
 static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, int res_tma, int row_shared,
-                     cudaStream_t stream) {
+                     int breg, cudaStream_t stream) {
     using Cfg = ConvCfg<BN, WGS>;
     static bool configured = false;
     if (!configured) {
@@ -831,15 +943,15 @@ static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, i
         configured = true;
     }
     int stages, ring;
-    conv_smem_config<BN, WGS>(res_tma, row_shared, &stages, &ring);
-    const int smem = Cfg::smem_bytes(stages, ring, row_shared);
+    conv_smem_config<BN, WGS>(res_tma, row_shared, breg, &stages, &ring);
+    const int smem = Cfg::smem_bytes(stages, ring, row_shared, breg);
     if (smem > kMaxSmem) {
         set_error("conv_tc_kernel<%d,%d>: %d stages + %d ring slots need %d bytes of shared memory", BN, WGS, stages,
                   ring, smem);
         return -1;
     }
     conv_tc_kernel<BN, WGS, MODE>
-        <<<grid, Cfg::THREADS, smem, stream>>>(dev_probs, nprob, total_tiles, stages, ring, res_tma, row_shared);
+        <<<grid, Cfg::THREADS, smem, stream>>>(dev_probs, nprob, total_tiles, stages, ring, res_tma, row_shared, breg);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("conv_tc_kernel<%d,%d,%d> launch: %s", BN, WGS, MODE, cudaGetErrorString(e));
@@ -850,15 +962,15 @@ static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, i
 
 template <int BN, int WGS>
 static int launch_mode(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, int mode, int res_tma,
-                       int row_shared, cudaStream_t stream) {
-    if (mode == 1) return launch_bn<BN, WGS, 1>(dev_probs, nprob, total_tiles, grid, res_tma, row_shared, stream);
-    if (mode == 0) return launch_bn<BN, WGS, 0>(dev_probs, nprob, total_tiles, grid, 0, row_shared, stream);
+                       int row_shared, int breg, cudaStream_t stream) {
+    if (mode == 1) return launch_bn<BN, WGS, 1>(dev_probs, nprob, total_tiles, grid, res_tma, row_shared, breg, stream);
+    if (mode == 0) return launch_bn<BN, WGS, 0>(dev_probs, nprob, total_tiles, grid, 0, row_shared, breg, stream);
     set_error("conv_tc: epilogue mode %d is not built for tile width %d / %d epilogue warpgroups", mode, BN, WGS);
     return -1;
 }
 
 int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int epi_wgs, int mode,
-                      int res_tma, int row_shared, int num_sms, cudaStream_t stream) {
+                      int res_tma, int row_shared, int breg, int num_sms, cudaStream_t stream) {
     if (total_tiles == 0) return 0;
     if (nprob < 1 || nprob > kMaxConvProblems) {
         set_error("conv_tc: %d problems in one launch (1..%d supported)", nprob, kMaxConvProblems);
@@ -868,20 +980,20 @@ int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, 
     const int key = block_n * 10 + epi_wgs;
     if (mode == 2) {
         // GroupNorm statistics: only the 256-wide tower convolutions produce them
-        if (key == 2561) return launch_bn<256, 1, 2>(dev_probs, nprob, total_tiles, grid, 0, 0, stream);
-        if (key == 2562) return launch_bn<256, 2, 2>(dev_probs, nprob, total_tiles, grid, 0, 0, stream);
+        if (key == 2561) return launch_bn<256, 1, 2>(dev_probs, nprob, total_tiles, grid, 0, 0, 0, stream);
+        if (key == 2562) return launch_bn<256, 2, 2>(dev_probs, nprob, total_tiles, grid, 0, 0, 0, stream);
         set_error("conv_tc: GroupNorm statistics need Cout %% 256 == 0 (tile width %d)", block_n);
         return -1;
     }
     switch (key) {
-        case 161: return launch_bn<16, 1, 0>(dev_probs, nprob, total_tiles, grid, 0, row_shared, stream);
-        case 321: return launch_bn<32, 1, 0>(dev_probs, nprob, total_tiles, grid, 0, row_shared, stream);
-        case 641: return launch_mode<64, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, stream);
-        case 642: return launch_mode<64, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, stream);
-        case 1281: return launch_mode<128, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, stream);
-        case 1282: return launch_mode<128, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, stream);
-        case 2561: return launch_mode<256, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, 0, stream);
-        case 2562: return launch_mode<256, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, 0, stream);
+        case 161: return launch_bn<16, 1, 0>(dev_probs, nprob, total_tiles, grid, 0, row_shared, breg, stream);
+        case 321: return launch_bn<32, 1, 0>(dev_probs, nprob, total_tiles, grid, 0, row_shared, breg, stream);
+        case 641: return launch_mode<64, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, breg, stream);
+        case 642: return launch_mode<64, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, breg, stream);
+        case 1281: return launch_mode<128, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, 0, stream);
+        case 1282: return launch_mode<128, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, row_shared, 0, stream);
+        case 2561: return launch_mode<256, 1>(dev_probs, nprob, total_tiles, grid, mode, res_tma, 0, 0, stream);
+        case 2562: return launch_mode<256, 2>(dev_probs, nprob, total_tiles, grid, mode, res_tma, 0, 0, stream);
     }
     set_error("conv_tc: unsupported tile width %d with %d epilogue warpgroups", block_n, epi_wgs);
     return -1;

@@ -46,6 +46,7 @@ struct ConvParams {
     long long* gn_sums;
     float* out_f32;
     int out_ld;
+    const void* w_id;  // identity of the weight tensor (its device pointer): tiles with equal w_id share resident weights
 };
 
 // One convolution as the kernel sees it. A launch works through an array of these in device memory (tiles of all
@@ -65,7 +66,9 @@ struct ConvPlan {
     int epi_wgs;  // epilogue warpgroups the shape wants (1 | 2, see ConvCfg)
     int mode;     // epilogue variant: 0 plain, 1 residual add, 2 GroupNorm statistics
     int res_tma;  // residual at the output's resolution: loaded by TMA into the epilogue ring
-    int row_shared;  // 3x3 stride 1, narrow N tile: one 18-row A box per horizontal tap serves the three vertical taps
+    int row_shared;  // 3x3 stride 1, narrow N tile: 0 one A load per tap; 1 one per horizontal tap (18-row box);
+                     // 2 one halo box for all nine taps; 3 the same with the weights resident in shared memory
+    int breg_bytes;  // mode 3: bytes of the resident weight region (9 x Cin/64 x BLOCK_N x 128)
     int grid;     // CTAs for a stand-alone launch
     double flops;  // 2*MACs, algorithmic (unpadded)
 };
@@ -80,9 +83,9 @@ inline void conv_out_dims(ConvDesc& d) {
 int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms);
 // Launch over `nprob` (<= kMaxConvProblems) problems with the same block_n, stored contiguously in DEVICE memory with
 // p.tile_begin already assigned (prefix sums of p.total_tiles).
-// mode, res_tma and row_shared must be the same for every problem of the launch.
+// mode, res_tma, row_shared and breg_bytes must be the same for every problem of the launch.
 int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, int block_n, int epi_wgs, int mode,
-                      int res_tma, int row_shared, int num_sms, cudaStream_t stream);
+                      int res_tma, int row_shared, int breg_bytes, int num_sms, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
 const char* get_error();

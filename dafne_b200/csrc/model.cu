@@ -299,7 +299,7 @@ struct Builder {
     ConvProblem* dev_probs = nullptr;
     bool grouping = false;
     size_t group_first = 0;
-    int group_bn = 0, group_wgs = 0, group_res = -1, group_mode = -1, group_rs = -1;
+    int group_bn = 0, group_wgs = 0, group_res = -1, group_mode = -1, group_rs = -1, group_breg = -1;
     double group_flops = 0, group_bytes = 0;
     std::string group_name;
     OpInfo group_info;
@@ -312,6 +312,7 @@ struct Builder {
         group_res = -1;
         group_mode = -1;
         group_rs = -1;
+        group_breg = -1;
         group_flops = group_bytes = 0;
         group_name = name;
     }
@@ -331,10 +332,10 @@ struct Builder {
             total += probs[i].p.total_tiles;
         }
         const ConvProblem* dp = dev_probs + first;
-        const int bn = group_bn, wgs = group_wgs, res = group_res, mode = group_mode, rs = group_rs, sms = c->num_sms,
-                  n = static_cast<int>(cnt);
+        const int bn = group_bn, wgs = group_wgs, res = group_res, mode = group_mode, rs = group_rs,
+                  breg = group_breg, sms = c->num_sms, n = static_cast<int>(cnt);
         c->ops.push_back(
-            [=](cudaStream_t s) { return conv_group_launch(dp, n, total, bn, wgs, mode, res, rs, sms, s); });
+            [=](cudaStream_t s) { return conv_group_launch(dp, n, total, bn, wgs, mode, res, rs, breg, sms, s); });
         OpInfo o = group_info;
         snprintf(o.name, sizeof(o.name), "%s", group_name.size() > 46 ? group_name.substr(group_name.size() - 46).c_str()
                                                                       : group_name.c_str());
@@ -448,7 +449,7 @@ struct Builder {
                 return out;
             }
             if ((group_res >= 0 && group_res != plan.res_tma) || (group_mode >= 0 && group_mode != plan.mode) ||
-                (group_rs >= 0 && group_rs != plan.row_shared)) {
+                (group_rs >= 0 && group_rs != plan.row_shared) || (group_breg >= 0 && group_breg != plan.breg_bytes)) {
                 set_error("plan: group '%s' mixes TMA-residual and other convolutions", group_name.c_str());
                 failed = true;
                 return out;
@@ -456,6 +457,7 @@ struct Builder {
             group_res = plan.res_tma;
             group_mode = plan.mode;
             group_rs = plan.row_shared;
+            group_breg = plan.breg_bytes;
             group_bn = plan.block_n;
             group_wgs = group_wgs == 0 ? plan.epi_wgs : (group_wgs < plan.epi_wgs ? group_wgs : plan.epi_wgs);
             probs.push_back(plan.prob);
@@ -716,13 +718,14 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     }
     for (int t = 0; t < 3; ++t)
         for (int l = 0; l < 5; ++l) B.name(std::string(kTowers[t]) + ".l" + std::to_string(l), cur[t][l]);
+    // all levels of one prediction conv next to each other: its weights stay resident in shared memory across them
     B.begin_group("pred.cls_logits+center_pred");
-    for (int l = 0; l < 5; ++l) {
+    for (int l = 0; l < 5; ++l)
         B.conv(B.layer(kHead + "cls_logits"), cur[0][l], false, nullptr, 0, nullptr,
                base ? ho[l][0].p : reinterpret_cast<float*>(1), ho[l][0].ld);
+    for (int l = 0; l < 5; ++l)
         B.conv(B.layer(kHead + "center_pred"), cur[1][l], false, nullptr, 0, nullptr,
                base ? ho[l][2].p : reinterpret_cast<float*>(1), ho[l][2].ld);
-    }
     B.end_group();
     B.begin_group("pred.ctrness+corners_pred");
     for (int l = 0; l < 5; ++l)

@@ -143,6 +143,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// The same with an explicit stride between 8-row groups. The start need not sit on a 1024-byte atom boundary as long
+// as the data was written with an address-based swizzle too (TMA): measured on B200, base_offset must stay 0 then.
+__device__ __forceinline__ uint64_t umma_desc_sw128_ex(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(base_offset & 7) << 49;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
 // kind::f16 instruction descriptor: fp32 accumulator, fp16 A/B, both K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
     return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
