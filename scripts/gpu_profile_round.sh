@@ -12,7 +12,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
 # 3. tensor-pipe utilisation of every conv launch of one forward (step 4 of 4: skip the 3 warm-up forwards)
 timeout 400 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed \
-    --clock-control none -k regex:'conv_tc|stem_tc' -s 195 -c 65 --csv --log-file gpurun_out/${TAG}_conv_tensor_pipe.csv \
+    --clock-control none -k regex:'conv_tc|stem_tc' -s 207 -c 69 --csv --log-file gpurun_out/${TAG}_conv_tensor_pipe.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_pipe.log 2>&1
 # 4. full captures: the dominant kernel (tower conv, GN-statistics epilogue) and the NMS broadcast of panel 0
 timeout 400 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \

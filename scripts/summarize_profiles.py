@@ -64,7 +64,7 @@ def ncu(src, dst):
     print(open(dst).read())
 
 
-def tensor_pipe(csv_path, per_launch_json, dst, first_global_index, launches_per_forward=71):
+def tensor_pipe(csv_path, per_launch_json, dst, first_global_index, launches_per_forward=69):
     """ncu per-launch tensor-pipe utilisation of the conv / stem kernels of one forward, labelled with the layer names
     of bench.py's per-launch profile (same launch order), FLOP-weighted per group."""
     import json
