@@ -203,9 +203,48 @@ __device__ __forceinline__ float tri_overlap(P2 a, P2 b, P2 c, P2 d, float2* slo
     // Exact shortcut (same result bits as the generic path below): if a and b are both strictly right of the ray
     // O->c, the first clip keeps no vertex and both intersection points it appends are exactly (0,0)
     // ((0*s2 - v*0)/(s2 - 0)); every later clip then sees a single zero point and the area is exactly 0.
-    if (sigf(c.x * a.y - a.x * c.y) < 0 && sigf(c.x * b.y - b.x * c.y) < 0) return 0.f;
+    const float sa = c.x * a.y - a.x * c.y;  // == cross3(O, c, a): x - 0 is exact
+    const float sb = c.x * b.y - b.x * c.y;
+    const int ga = sigf(sa), gb = sigf(sb);
+    if (ga < 0 && gb < 0) return 0.f;
     int n;
-    {
+    // First cut (left of O -> c) of [O, a, b]. O lies on the line (sign class 0), so whenever a and b are off the
+    // line the cut is one of three fixed shapes, and the intersection points with an edge through O are zero points
+    // ((0 * s2 - v * 0) / (s2 - 0)); the sign of such a zero never reaches the result (it only meets +-0 products,
+    // x - c with c != 0, and same_pt / sig, which treat +-0 alike):
+    //   a, b left:   tmp = [z, a, b, z']    -> [z, a, b]       a left, b right:  tmp = [z, a, x, z'] -> [z, a, x]
+    //   a right, b left:  tmp = [z, x, b, z'] -> [z, x, b]      (x = lineCross(a, b), z' dropped by the closing check)
+    // provided the de-duplication (polyiou.cpp:66-70) finds the three points distinct -- checked; anything else
+    // (a vertex on the line, coincident points) takes the generic cut.
+    bool fast = false;
+    // (non-finite coordinates would turn v * 0 into NaN: generic cut)
+    if (ga != 0 && gb != 0 && fabsf(a.x) + fabsf(a.y) + fabsf(b.x) + fabsf(b.y) < INFINITY) {
+        P2 z, p1 = a, p2 = b;
+        z.x = 0.f;
+        z.y = 0.f;
+        if (ga != gb) {
+            P2 x;
+            x.x = 0.f;
+            x.y = 0.f;
+            const float den = sb - sa;
+            if (sigf(den) != 0) {
+                x.x = div_exact(a.x * sb - b.x * sa, den);
+                x.y = div_exact(a.y * sb - b.y * sa, den);
+            }
+            if (ga > 0)
+                p2 = x;
+            else
+                p1 = x;
+        }
+        if (!same_pt(p1, z) && !same_pt(p2, p1) && !same_pt(p2, z)) {
+            slots[0] = make_float2(0.f, 0.f);
+            slots[stride] = make_float2(p1.x, p1.y);
+            slots[2 * stride] = make_float2(p2.x, p2.y);
+            n = 3;
+            fast = true;
+        }
+    }
+    if (!fast) {
         P2 p3[3];
         p3[0] = o;
         p3[1] = a;
