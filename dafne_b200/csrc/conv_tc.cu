@@ -58,7 +58,9 @@ struct ConvCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SLOT_BYTES = 16384;  // 128 pixels x 64 ch fp16, one epilogue chunk
     static constexpr int AUX_HDR = 512;       // barriers, tmem pointer, tile offsets
-    static constexpr int AUX_BYTES = AUX_HDR + EPI_WGS * BLOCK_N * 8;  // + (scale, shift) pairs per warpgroup
+    // + (scale, shift) pairs per warpgroup; MODE 2 (tower convs: bias only) keeps the shifts alone
+    static constexpr int aux_bytes(int mode) { return AUX_HDR + EPI_WGS * BLOCK_N * (mode == 2 ? 4 : 8); }
+    static constexpr int AUX_BYTES = AUX_HDR + EPI_WGS * BLOCK_N * 8;
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
     static constexpr int THREADS = 128 + 128 * EPI_WGS;
     static constexpr int MAX_STAGES = 8, MAX_RING = 4;
@@ -77,9 +79,9 @@ struct ConvCfg {
         return row_shared == 3 ? A_HALO_BYTES
                                : (row_shared == 2 ? STAGE_BYTES_HALO : (row_shared ? STAGE_BYTES_RS : STAGE_BYTES));
     }
-    static constexpr int smem_bytes(int stages, int ring, int row_shared = 0, int breg_bytes = 0) {
+    static constexpr int smem_bytes(int stages, int ring, int row_shared = 0, int breg_bytes = 0, int mode = 0) {
         return breg_bytes + stages * stage_bytes(row_shared) +
-               (BLOCK_N >= 64 ? EPI_WGS * ring * SLOT_BYTES : 0) + AUX_BYTES;
+               (BLOCK_N >= 64 ? EPI_WGS * ring * SLOT_BYTES : 0) + aux_bytes(mode);
     }
 };
 constexpr int kMaxSmem = 232448;  // 227 KB
@@ -161,6 +163,19 @@ __device__ __forceinline__ void epilogue_chunk_math(const uint32_t (&v)[64], con
         else
             asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(a1), "f"(a0));
         packed[c >> 1] = h;
+    }
+}
+
+// Bias-only variant for the tower convolutions (MODE 2: no scale, no residual, no ReLU -- GroupNorm follows): the table
+// holds the 64 shifts of the chunk.
+__device__ __forceinline__ void epilogue_chunk_bias(const uint32_t (&v)[64], const float* tab, uint32_t (&packed)[32]) {
+#pragma unroll
+    for (int c = 0; c < 64; c += 4) {
+        const float4 sh = *reinterpret_cast<const float4*>(&tab[c]);
+        const float a0 = __uint_as_float(v[c]) + sh.x, a1 = __uint_as_float(v[c + 1]) + sh.y;
+        const float a2 = __uint_as_float(v[c + 2]) + sh.z, a3 = __uint_as_float(v[c + 3]) + sh.w;
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(packed[c >> 1]) : "f"(a1), "f"(a0));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(packed[(c >> 1) + 1]) : "f"(a3), "f"(a2));
     }
 }
 
@@ -445,7 +460,8 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
         const int et = (threadIdx.x - 128) & 127;
         const int row = wi * 32 + lane;
         const uint32_t bar_id = 1 + wg;
-        float2* s_tab = s_tab_all + wg * BLOCK_N;
+        float2* s_tab = s_tab_all + wg * BLOCK_N;  // MODE 2: BLOCK_N floats (shift only) at the same place
+        float* s_bias = reinterpret_cast<float*>(s_tab_all) + wg * BLOCK_N;
         const uint32_t s_epi_wg = s_epi + wg * ring * Cfg::SLOT_BYTES;
         uint32_t acc_phase = 0;  // EPI_WGS == 2: this warpgroup always drains accumulator stage `wg`
         int acc = EPI_WGS == 2 ? wg : 0;
@@ -505,7 +521,10 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                     float2 v;
                     v.x = (p.scale != nullptr && ch < p.Cout) ? __ldg(p.scale + ch) : 1.0f;
                     v.y = (p.shift != nullptr && ch < p.Cout) ? __ldg(p.shift + ch) : 0.0f;
-                    s_tab[i] = v;
+                    if (MODE == 2)
+                        s_bias[i] = v.y;
+                    else
+                        s_tab[i] = v;
                 }
                 named_bar_sync(bar_id, 128);
             }
@@ -551,7 +570,9 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                     }
                     uint32_t packed[32];
-                    if (MODE == 1) {
+                    if (MODE == 2) {
+                        epilogue_chunk_bias(v, s_bias + chbase, packed);
+                    } else if (MODE == 1) {
                         if (p.relu)
                             epilogue_chunk_math<true, true>(v, s_tab + chbase, res, packed);
                         else
@@ -889,8 +910,8 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     plan->prob.tmRes = plan->prob.tmOut;
     plan->res_tma = 0;
     plan->mode = d.residual != nullptr ? 1 : (d.gn_sums != nullptr ? 2 : 0);
-    if (d.residual != nullptr && d.gn_sums != nullptr) {
-        set_error("conv_tc: residual and GroupNorm statistics in one convolution are not supported");
+    if (d.gn_sums != nullptr && (d.residual != nullptr || d.scale != nullptr || d.relu)) {
+        set_error("conv_tc: GroupNorm statistics go with a bias-only convolution (no scale, residual or ReLU)");
         return -1;
     }
     if (!small && d.residual != nullptr && d.res_shift == 0) {
@@ -917,12 +938,12 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
 // Operand stages / epilogue ring slots per warpgroup for a launch: as deep as 227 KB allows. With a TMA residual the
 // ring is the prefetch depth of the residual stream, so it gets four slots at the price of operand stages.
 template <int BN, int WGS>
-static void conv_smem_config(int res_tma, int row_shared, int breg, int* stages, int* ring) {
+static void conv_smem_config(int res_tma, int row_shared, int breg, int mode, int* stages, int* ring) {
     using Cfg = ConvCfg<BN, WGS>;
     int r = BN < 64 ? 2 : (res_tma ? 4 : (WGS == 2 ? 3 : 2));
     int st = Cfg::MAX_STAGES;
-    while (st > 2 && Cfg::smem_bytes(st, r, row_shared, breg) > kMaxSmem) --st;
-    while (r > 2 && Cfg::smem_bytes(st, r, row_shared, breg) > kMaxSmem) --r;
+    while (st > 2 && Cfg::smem_bytes(st, r, row_shared, breg, mode) > kMaxSmem) --st;
+    while (r > 2 && Cfg::smem_bytes(st, r, row_shared, breg, mode) > kMaxSmem) --r;
     *stages = st;
     *ring = r;
 }
@@ -943,8 +964,8 @@ static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, i
         configured = true;
     }
     int stages, ring;
-    conv_smem_config<BN, WGS>(res_tma, row_shared, breg, &stages, &ring);
-    const int smem = Cfg::smem_bytes(stages, ring, row_shared, breg);
+    conv_smem_config<BN, WGS>(res_tma, row_shared, breg, MODE, &stages, &ring);
+    const int smem = Cfg::smem_bytes(stages, ring, row_shared, breg, MODE);
     if (smem > kMaxSmem) {
         set_error("conv_tc_kernel<%d,%d>: %d stages + %d ring slots need %d bytes of shared memory", BN, WGS, stages,
                   ring, smem);

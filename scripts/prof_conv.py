@@ -36,7 +36,7 @@ def main():
         flush.zero_()  # evict the 126 MB L2 between launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        st = lib.dafne_conv_nhwc(x.data_ptr(), N, H, W, Cin, w.data_ptr(), Cout, k, stride, scale.data_ptr(),
+        st = lib.dafne_conv_nhwc(x.data_ptr(), N, H, W, Cin, w.data_ptr(), Cout, k, stride, None if use_gn else scale.data_ptr(),
                                  shift.data_ptr(), 1 if use_res else 0, res.data_ptr() if use_res else None,
                                  Ho if use_res else 0, Wo if use_res else 0, 0, sums.data_ptr() if use_gn else None,
                                  out.data_ptr(), None, 0, s)

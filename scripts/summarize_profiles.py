@@ -64,7 +64,7 @@ def ncu(src, dst):
     print(open(dst).read())
 
 
-def tensor_pipe(csv_path, per_launch_json, dst, first_global_index, launches_per_forward=69):
+def tensor_pipe(csv_path, per_launch_json, dst, first_global_index):
     """ncu per-launch tensor-pipe utilisation of the conv / stem kernels of one forward, labelled with the layer names
     of bench.py's per-launch profile (same launch order), FLOP-weighted per group."""
     import json
@@ -74,7 +74,7 @@ def tensor_pipe(csv_path, per_launch_json, dst, first_global_index, launches_per
     for x in csv.DictReader(rows):
         by.setdefault(int(x["ID"]), {"kernel": x["Kernel Name"]})[x["Metric Name"]] = float(x["Metric Value"].replace(",", ""))
     ops = [o for o in json.load(open(per_launch_json)) if o["kind"] in (1, 2)]
-    assert len(ops) == launches_per_forward, (len(ops), launches_per_forward)
+    launches_per_forward = len(ops)
     seen = {}
     for k, m in by.items():
         op = (first_global_index + k) % launches_per_forward
