@@ -7,6 +7,7 @@
 #include "conv_tc.cuh"
 #include "elementwise.cuh"
 #include "merge_nms.cuh"
+#include "resize.cuh"
 #include "model.cuh"
 #include "postprocess.cuh"
 #include <string.h>
@@ -331,6 +332,12 @@ int dafne_detect_host_end(dafne_ctx* ctx, int ticket) {
         return -1;
     }
     return 0;
+}
+
+int dafne_resize_bilinear_u8(const uint8_t* dev_in, int planes, int h, int w, uint8_t* dev_out, int new_h, int new_w,
+                             uint8_t* dev_tmp, void* stream) {
+    return launch_resize_bilinear_u8(dev_in, planes, h, w, dev_out, new_h, new_w, dev_tmp,
+                                     static_cast<cudaStream_t>(stream));
 }
 
 int dafne_poly_nms_f64_batch_host(const double* dets_host, const int32_t* offsets, int nproblems, double thresh,

@@ -98,6 +98,24 @@ def poly_iou(p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def resize_bilinear_u8(image: torch.Tensor, new_h: int, new_w: int) -> torch.Tensor:
+    """[C, H, W] (or [N, C, H, W]) uint8 CUDA tensor -> same layout at new_h x new_w, bit-identical to
+    PIL.Image.resize((new_w, new_h), Image.BILINEAR) -- what detectron2's ResizeTransform runs on the host
+    (tools/plain_train_net.py:293-298, dafne/modeling/tta.py:76-93)."""
+    if not image.is_cuda or image.dtype != torch.uint8:
+        raise _capi.DafneError("resize_bilinear_u8: uint8 CUDA tensor required (no CPU fallback in this package)")
+    x = image.contiguous()
+    h, w = int(x.shape[-2]), int(x.shape[-1])
+    planes = x.numel() // (h * w)
+    out = torch.empty(tuple(x.shape[:-2]) + (int(new_h), int(new_w)), dtype=torch.uint8, device=x.device)
+    tmp = torch.empty(planes * h * int(new_w), dtype=torch.uint8, device=x.device) if (new_h != h and new_w != w) else None
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib().dafne_resize_bilinear_u8(x.data_ptr(), planes, h, w, out.data_ptr(), int(new_h),
+                                                         int(new_w), tmp.data_ptr() if tmp is not None else None,
+                                                         _capi.stream_ptr()), "dafne_resize_bilinear_u8")
+    return out
+
+
 def batched_nms_poly(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float,
                      vehicle_merge: bool = True) -> torch.Tensor:
     """Class-aware polygon NMS (nms.py:37-92): int64 indices of kept boxes, in decreasing score order."""
@@ -326,19 +344,28 @@ def build_model(cfg) -> nn.Module:
 
 class DefaultPredictor:
     """detectron2.engine.DefaultPredictor for this model (call shape of tools/vis/feature_maps.py:171-194):
-    predictor(bgr_hwc_uint8) -> {"instances": Instances}. Resizing (ResizeShortestEdge) is not part of the hot path;
-    the image is used at its own resolution."""
+    predictor(bgr_hwc_uint8) -> {"instances": Instances} in the coordinates of the original image. Like detectron2's,
+    it resizes with ResizeShortestEdge(INPUT.MIN_SIZE_TEST, INPUT.MAX_SIZE_TEST) first -- here on the device, with the
+    Pillow-exact bilinear kernel (`resize=False` feeds the image at its own resolution)."""
 
-    def __init__(self, cfg, state_dict: Optional[Dict[str, torch.Tensor]] = None):
+    def __init__(self, cfg, state_dict: Optional[Dict[str, torch.Tensor]] = None, resize: bool = True):
         self.cfg = cfg
         self.model = build_model(cfg)
         if state_dict is not None:
             self.model.load_state_dict(state_dict)
         self.input_format = cfg.INPUT.FORMAT
+        self.resize = resize
+        self.min_size_test, self.max_size_test = int(cfg.INPUT.MIN_SIZE_TEST), int(cfg.INPUT.MAX_SIZE_TEST)
 
     def __call__(self, original_image: np.ndarray):
+        from .tta import NoOpTransform, resize_shortest_edge_transform
+
         if self.input_format == "RGB":
             original_image = original_image[:, :, ::-1]
         h, w = original_image.shape[:2]
         image = torch.as_tensor(np.ascontiguousarray(original_image.transpose(2, 0, 1)))
+        if self.resize and image.dtype == torch.uint8:
+            t = resize_shortest_edge_transform(h, w, self.min_size_test, self.max_size_test)
+            if not isinstance(t, NoOpTransform):
+                image = resize_bilinear_u8(image.to(self.model.device), t.new_h, t.new_w)
         return self.model([{"image": image, "height": h, "width": w}])[0]

@@ -53,6 +53,9 @@ class NoOpTransform(Transform):
     def apply_image(self, img):
         return img
 
+    def apply_image_device(self, img):
+        return img
+
     def apply_coords(self, coords):
         return coords
 
@@ -69,6 +72,9 @@ class HFlipTransform(Transform):
 
     def apply_image(self, img):
         return np.flip(img, axis=1)
+
+    def apply_image_device(self, img):
+        return img.flip(-1)
 
     def apply_coords(self, coords):
         coords[:, 0] = self.width - coords[:, 0]
@@ -88,6 +94,9 @@ class VFlipTransform(Transform):
 
     def apply_image(self, img):
         return np.flip(img, axis=0)
+
+    def apply_image_device(self, img):
+        return img.flip(-2)
 
     def apply_coords(self, coords):
         coords[:, 1] = self.height - coords[:, 1]
@@ -117,6 +126,13 @@ class ResizeTransform(Transform):
         pil = pil.resize((self.new_w, self.new_h), Image.BILINEAR if self.interp is None else self.interp)
         ret = np.asarray(pil)
         return ret if ret.ndim == 3 else ret[:, :, None]
+
+    def apply_image_device(self, img: torch.Tensor) -> torch.Tensor:
+        """[C, H, W] uint8 CUDA tensor: the same Pillow bilinear resize, on the device (dafne_resize_bilinear_u8)."""
+        from .modeling import resize_bilinear_u8
+
+        assert tuple(img.shape[-2:]) == (self.h, self.w), (tuple(img.shape), self.h, self.w)
+        return resize_bilinear_u8(img, self.new_h, self.new_w)
 
     def apply_coords(self, coords):
         coords[:, 0] = coords[:, 0] * (self.new_w * 1.0 / self.w)
@@ -173,7 +189,11 @@ def resize_shortest_edge_transform(h: int, w: int, size: int, max_size: int) -> 
 
 # ------------------------------------------------------------------------------------------------ mapper (tta.py:29-135)
 class DotaDatasetMapperTTA:
-    def __init__(self, cfg):
+    """`device` (not in the reference): build the copies on that CUDA device -- one H2D copy of the image, the
+    Pillow-exact resize kernel and flips there -- instead of on the host; the copies are bit-identical either way."""
+
+    def __init__(self, cfg, device=None):
+        self.device = torch.device(device) if device is not None else None
         self.min_sizes = list(cfg.TEST.AUG.MIN_SIZES)
         self.max_size = cfg.TEST.AUG.MAX_SIZE
         self.resize_type = cfg.INPUT.RESIZE_TYPE
@@ -213,16 +233,24 @@ class DotaDatasetMapperTTA:
             if self.vflip:
                 candidates.append([resize, lambda img: VFlipTransform(img.shape[0])])
         ret = []
+        on_device = self.device is not None and dataset_dict["image"].dtype == torch.uint8
+        dev_image = dataset_dict["image"].to(self.device) if on_device else None
         for aug in candidates:
-            img = np.copy(numpy_image)
+            img = np.copy(numpy_image) if not on_device else None
+            cur = dev_image
+            shape_hw = numpy_image.shape[:2]
             tfms = []
             for make in aug:  # detectron2 apply_augmentations: each transform is built from the current image
-                t = make(img)
-                img = t.apply_image(img)
+                t = make(np.empty(shape_hw + (0,), np.uint8) if on_device else img)
+                if on_device:
+                    cur = t.apply_image_device(cur)
+                    shape_hw = tuple(cur.shape[-2:])
+                else:
+                    img = t.apply_image(img)
                 tfms.append(t)
             dic = copy.copy(dataset_dict)
             dic["transforms"] = pre_tfm + TransformList(tfms)
-            dic["image"] = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1)))
+            dic["image"] = cur.contiguous() if on_device else torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1)))
             ret.append(dic)
         return ret
 

@@ -221,6 +221,15 @@ int dafne_poly_nms_f64_host(const double* dets_host, int n, double thresh, int d
 int dafne_poly_nms_f64_batch_host(const double* dets_host, const int32_t* offsets, int nproblems, double thresh,
                                   int device_id, int32_t* keep_out, int32_t* nkeep_out);
 
+/* ------------------------------------------------------------------ next to the path: the input resize */
+/* Bilinear resize of uint8 image planes on device, bit-identical to PIL.Image.resize((new_w, new_h), BILINEAR), which is
+ * what detectron2's ResizeShortestEdge / ResizeTransform run on the host before the reference's model sees an image
+ * (tools/plain_train_net.py:293-298, dafne/modeling/tta.py:76-93). dev_in [planes][h][w] (a CHW image has planes = 3),
+ * dev_out [planes][new_h][new_w]; dev_tmp: planes * h * new_w bytes, needed when both sizes change (may be NULL
+ * otherwise). No host synchronisation. */
+int dafne_resize_bilinear_u8(const uint8_t* dev_in, int planes, int h, int w, uint8_t* dev_out, int new_h, int new_w,
+                             uint8_t* dev_tmp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
