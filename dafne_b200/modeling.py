@@ -13,6 +13,7 @@ gives the model a detectron2-compatible state dict.
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 import ctypes as C
 from typing import Dict, List, Optional, Sequence
 
@@ -230,7 +231,14 @@ class OneStageDetector(nn.Module):
         self.proposal_generator = DAFNe(self.spec)
         self.backbone = build_dafne_resnet_fpn_backbone(cfg)
         self.top_module = None  # MODEL.TOP_MODULE.NAME == "" in every shipped config (defaults.py:34)
+        # One engine (context + bound workspace + launch plan) per batch shape, most recently used first: a caller
+        # that cycles through shapes -- TTA runs 9 scales per image -- must not re-plan on every call. `_engine` is
+        # the one used last.
         self._engine: Optional[DafneEngine] = None
+        self._engines: "OrderedDict[tuple, DafneEngine]" = OrderedDict()
+        self._engine_versions: Dict[int, int] = {}
+        self._weights_version = 0
+        self.max_cached_shapes = 12
         self._weights_dirty = True
         self.eval()
 
@@ -258,16 +266,34 @@ class OneStageDetector(nn.Module):
     def device(self) -> torch.device:
         return self.pixel_mean.device
 
-    def _get_engine(self) -> DafneEngine:
+    def _get_engine(self, shape: Optional[tuple] = None) -> DafneEngine:
+        """The engine bound (or to be bound) to batch shape (N, H, W); None = the one used last."""
         if not self.device.type == "cuda":
             raise _capi.DafneError("OneStageDetector must live on a CUDA device: call model.to('cuda') first")
-        if self._engine is None or self._engine.device != self.device:
-            self._engine = DafneEngine(self.spec, self.device)
-            self._weights_dirty = True
         if self._weights_dirty:
-            self._engine.load_state_dict(self.params.state_dict())
+            self._weights_version += 1
             self._weights_dirty = False
-        return self._engine
+        if any(e.device != self.device for e in self._engines.values()):
+            for e in self._engines.values():
+                e.close()
+            self._engines.clear()
+            self._engine = None
+        if shape is None:
+            shape = next(reversed(self._engines)) if self._engines else ("default",)
+        eng = self._engines.get(shape)
+        if eng is None:
+            if len(self._engines) >= self.max_cached_shapes:
+                _, old = self._engines.popitem(last=False)
+                self._engine_versions.pop(id(old), None)
+                old.close()
+            eng = DafneEngine(self.spec, self.device)
+            self._engines[shape] = eng
+        self._engines.move_to_end(shape)
+        if self._engine_versions.get(id(eng)) != self._weights_version:
+            eng.load_state_dict(self.params.state_dict())
+            self._engine_versions[id(eng)] = self._weights_version
+        self._engine = eng
+        return eng
 
     # -- the reference's methods -----------------------------------------------------------------------
     def preprocess_image(self, batched_inputs: Sequence[dict]):
@@ -288,8 +314,8 @@ class OneStageDetector(nn.Module):
     def forward(self, batched_inputs: Sequence[dict], do_postprocess: bool = True):
         if self.training:
             raise NotImplementedError("training is outside the hot-path scope")
-        eng = self._get_engine()
         batch, sizes = self.preprocess_image(batched_inputs)
+        eng = self._get_engine((int(batch.shape[0]), int(batch.shape[2]), int(batch.shape[3])))
         out_sizes = [
             (int(inp.get("height", s[0])), int(inp.get("width", s[1]))) for inp, s in zip(batched_inputs, sizes)
         ]
