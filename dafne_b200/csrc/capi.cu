@@ -334,6 +334,12 @@ int dafne_detect_host_end(dafne_ctx* ctx, int ticket) {
     return 0;
 }
 
+int dafne_voc_match_f64_host(const double* dets_host, const int32_t* det_image, int nd, const double* gts_host,
+                             const int32_t* gt_offsets, int nimages, int device_id, double* ovmax_out,
+                             int32_t* jmax_out) {
+    return voc_match_f64_host(dets_host, det_image, nd, gts_host, gt_offsets, nimages, device_id, ovmax_out, jmax_out);
+}
+
 int dafne_resize_bilinear_u8(const uint8_t* dev_in, int planes, int h, int w, uint8_t* dev_out, int new_h, int new_w,
                              uint8_t* dev_tmp, void* stream) {
     return launch_resize_bilinear_u8(dev_in, planes, h, w, dev_out, new_h, new_w, dev_tmp,

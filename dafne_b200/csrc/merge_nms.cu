@@ -224,3 +224,100 @@ done:
 }
 
 }  // namespace dafne
+
+// ================================================================================================ VOC matching (8f-4)
+// The IoU-heavy inner loop of the reference's voc_eval (dafne/evaluation/voc_eval.py:133-186): for every detection the
+// best polygon IoU against the ground truths of ITS image and the index of that ground truth. As in the reference the
+// polygon IoU (double, iou_poly(GT, detection)) is evaluated only where the "+1" horizontal-box overlap is positive; the
+// maximum keeps the FIRST of equal values (np.argmax). One thread per detection.
+namespace dafne {
+
+__global__ void voc_match_kernel(const double* __restrict__ dets, const int* __restrict__ det_image,
+                                 const double* __restrict__ gts, const int* __restrict__ gt_offsets, int nd,
+                                 double* __restrict__ ovmax_out, int* __restrict__ jmax_out) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= nd) return;
+    double bb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bb[k] = dets[static_cast<size_t>(d) * 8 + k];
+    double bx0 = bb[0], bx1 = bb[0], by0 = bb[1], by1 = bb[1];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        bx0 = fmin(bx0, bb[2 * k]);
+        bx1 = fmax(bx1, bb[2 * k]);
+        by0 = fmin(by0, bb[2 * k + 1]);
+        by1 = fmax(by1, bb[2 * k + 1]);
+    }
+    const int img = det_image[d];
+    double ovmax = -INFINITY;
+    int jmax = -1;
+    for (int j = gt_offsets[img]; j < gt_offsets[img + 1]; ++j) {
+        double g[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = gts[static_cast<size_t>(j) * 8 + k];
+        double gx0 = g[0], gx1 = g[0], gy0 = g[1], gy1 = g[1];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            gx0 = fmin(gx0, g[2 * k]);
+            gx1 = fmax(gx1, g[2 * k]);
+            gy0 = fmin(gy0, g[2 * k + 1]);
+            gy1 = fmax(gy1, g[2 * k + 1]);
+        }
+        // voc_eval.py:150-166
+        const double iw = fmax(fmin(gx1, bx1) - fmax(gx0, bx0) + 1.0, 0.0);
+        const double ih = fmax(fmin(gy1, by1) - fmax(gy0, by0) + 1.0, 0.0);
+        const double inters = iw * ih;
+        const double uni = (bx1 - bx0 + 1.0) * (by1 - by0 + 1.0) + (gx1 - gx0 + 1.0) * (gy1 - gy0 + 1.0) - inters;
+        if (!(inters / uni > 0.0)) continue;
+        const double ov = f64::iou_poly(g, bb);  // voc_eval.py:177-179: iou_poly(GT, bb)
+        if (jmax < 0 || ov > ovmax) {            // np.max / np.argmax over the kept ones: first maximum
+            ovmax = ov;
+            jmax = j - gt_offsets[img];
+        }
+    }
+    ovmax_out[d] = ovmax;
+    jmax_out[d] = jmax;
+}
+
+int voc_match_f64_host(const double* dets, const int* det_image, int nd, const double* gts, const int* gt_offsets,
+                       int nimages, int device, double* ovmax_out, int* jmax_out) {
+    if (nd <= 0) return 0;
+    if (!dets || !det_image || !gt_offsets || !ovmax_out || !jmax_out || nimages < 1) {
+        set_error("voc match: bad arguments");
+        return -1;
+    }
+    const int ng = gt_offsets[nimages];
+    for (int i = 0; i < nd; ++i)
+        if (det_image[i] < 0 || det_image[i] >= nimages) {
+            set_error("voc match: detection %d refers to image %d of %d", i, det_image[i], nimages);
+            return -1;
+        }
+    int rc = 0;
+    double *d_dets = nullptr, *d_gts = nullptr, *d_ov = nullptr;
+    int *d_img = nullptr, *d_off = nullptr, *d_j = nullptr;
+    MERGE_CUDA(cudaSetDevice(device));
+    MERGE_CUDA(cudaMalloc(&d_dets, static_cast<size_t>(nd) * 64));
+    MERGE_CUDA(cudaMalloc(&d_gts, static_cast<size_t>(ng > 0 ? ng : 1) * 64));
+    MERGE_CUDA(cudaMalloc(&d_ov, static_cast<size_t>(nd) * 8));
+    MERGE_CUDA(cudaMalloc(&d_img, static_cast<size_t>(nd) * 4));
+    MERGE_CUDA(cudaMalloc(&d_off, static_cast<size_t>(nimages + 1) * 4));
+    MERGE_CUDA(cudaMalloc(&d_j, static_cast<size_t>(nd) * 4));
+    MERGE_CUDA(cudaMemcpy(d_dets, dets, static_cast<size_t>(nd) * 64, cudaMemcpyHostToDevice));
+    if (ng > 0) MERGE_CUDA(cudaMemcpy(d_gts, gts, static_cast<size_t>(ng) * 64, cudaMemcpyHostToDevice));
+    MERGE_CUDA(cudaMemcpy(d_img, det_image, static_cast<size_t>(nd) * 4, cudaMemcpyHostToDevice));
+    MERGE_CUDA(cudaMemcpy(d_off, gt_offsets, static_cast<size_t>(nimages + 1) * 4, cudaMemcpyHostToDevice));
+    voc_match_kernel<<<(nd + 63) / 64, 64>>>(d_dets, d_img, d_gts, d_off, nd, d_ov, d_j);
+    MERGE_CUDA(cudaGetLastError());
+    MERGE_CUDA(cudaMemcpy(ovmax_out, d_ov, static_cast<size_t>(nd) * 8, cudaMemcpyDeviceToHost));
+    MERGE_CUDA(cudaMemcpy(jmax_out, d_j, static_cast<size_t>(nd) * 4, cudaMemcpyDeviceToHost));
+done:
+    cudaFree(d_dets);
+    cudaFree(d_gts);
+    cudaFree(d_ov);
+    cudaFree(d_img);
+    cudaFree(d_off);
+    cudaFree(d_j);
+    return rc;
+}
+
+}  // namespace dafne

@@ -221,6 +221,17 @@ int dafne_poly_nms_f64_host(const double* dets_host, int n, double thresh, int d
 int dafne_poly_nms_f64_batch_host(const double* dets_host, const int32_t* offsets, int nproblems, double thresh,
                                   int device_id, int32_t* keep_out, int32_t* nkeep_out);
 
+/* ------------------------------------------------------------------ next to the path: VOC AP with polygon IoU */
+/* The matching step of the reference's voc_eval (dafne/evaluation/voc_eval.py:133-186) for one class: for every
+ * detection (dets_host [nd][8] doubles, already sorted by descending confidence; det_image[d] = index of its image) the
+ * best polygon IoU -- polyiou.iou_poly(GT, detection) in double, evaluated only where the "+1" horizontal-box overlap is
+ * positive -- against the ground truths of that image (gts_host rows gt_offsets[i] .. gt_offsets[i+1]) and the local
+ * index of that ground truth (first maximum); -inf / -1 when nothing overlaps. Host pointers, synchronous. The
+ * sequential true/false-positive assignment and the AP integral stay with the caller (dafne_b200/voc_eval.py). */
+int dafne_voc_match_f64_host(const double* dets_host, const int32_t* det_image, int nd, const double* gts_host,
+                             const int32_t* gt_offsets, int nimages, int device_id, double* ovmax_out,
+                             int32_t* jmax_out);
+
 /* ------------------------------------------------------------------ next to the path: the input resize */
 /* Bilinear resize of uint8 image planes on device, bit-identical to PIL.Image.resize((new_w, new_h), BILINEAR), which is
  * what detectron2's ResizeShortestEdge / ResizeTransform run on the host before the reference's model sees an image
