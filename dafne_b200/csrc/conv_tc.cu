@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
     }
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (operands)
-        if (lane == 0) {
+        if (DAFNE_ONE_THREAD(2, lane)) {
             int stage = 0;
             uint32_t phase = 0;
             int g = 0;
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (DAFNE_ONE_THREAD(1, lane)) {
             constexpr uint32_t idesc = umma_idesc_f16(128, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
         }
     } else if (warp == 3) {
         // ------------------------------------------------------------ residual producer
-        if (BLOCK_N >= 64 && res_tma && lane == 0) {
+        if (BLOCK_N >= 64 && res_tma && DAFNE_ONE_THREAD(4, lane)) {
             constexpr int CHUNKS = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;
             int cnt[2] = {0, 0};  // chunks issued per epilogue warpgroup
             int g = 0, it = 0;

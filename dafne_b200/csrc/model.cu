@@ -555,30 +555,20 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     x0.off = B.arena.alloc(x0.bytes);
     x0.p = base ? reinterpret_cast<__half*>(base + x0.off) : nullptr;
     __half* x0p_saved = x0.p;
-    Act s1 = B.new_act(N, H / 2, W / 2, 64);
+    // stem conv + FrozenBN + ReLU + max-pool in one launch: the H/2 x W/2 conv output never reaches HBM
+    Act x = B.new_act(N, (H / 2 - 1) / 2 + 1, (W / 2 - 1) / 2 + 1, 64);
     B.launches += 2;
     B.flops += 2.0 * N * (H / 2) * (W / 2) * 64.0 * 49 * 3;
     if (base) {
         // op 0 (preprocess) is issued by ctx_forward because it takes the per-call image pointer
         StemPlan sp_;
-        if (stem_plan_build(x0.p, N, H, W, c->stem_w, c->stem_scale, c->stem_shift, s1.p, &sp_, c->num_sms)) return -1;
+        if (stem_plan_build(x0.p, N, H, W, c->stem_w, c->stem_scale, c->stem_shift, x.p, &sp_, c->num_sms)) return -1;
         c->ops.push_back([sp_](cudaStream_t s) { return stem_plan_launch(sp_, s); });
-        B.info("stem", 2, 2.0 * N * (H / 2) * (W / 2) * 64.0 * 147,
-               (double)x0.bytes + (double)N * (H / 2) * (W / 2) * 128);
-    }
-    Act x = B.new_act(N, H / 4, W / 4, 64);
-    B.launches += 1;
-    if (base) {
-        __half* s1p = s1.p;
-        __half* xp = x.p;
-        c->ops.push_back([=](cudaStream_t s) { return launch_maxpool3x3s2(s1p, N, H / 2, W / 2, 64, xp, s); });
-        B.info("maxpool", 0, 0, (double)N * (H / 2) * (W / 2) * 128 * 1.25);
+        B.info("stem+pool", 2, 2.0 * N * (H / 2) * (W / 2) * 64.0 * 147, (double)x0.bytes + (double)x.bytes);
     }
     // x0 is needed until the stem ran; releasing at plan time is safe because ops execute in plan order
-    B.name("stem", s1);
     B.name("pool", x);
     B.free_act(x0);
-    B.free_act(s1);
 
     // ---- bottlenecks
     const int* nb = stage_blocks(sp.resnet_depth);
@@ -753,7 +743,7 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     c->W = W;
     c->ws = base;
     c->ws_bytes = bytes;
-    c->launches_per_forward = B.launches;  // preprocess + stem + pool + convs + GN applies + relu copy
+    c->launches_per_forward = B.launches;  // preprocess + stem (with pool) + convs + GN applies + relu copy
     c->x0 = x0p_saved;
     c->flops_per_forward = B.flops;
     c->gn_sums_all = sums_all;

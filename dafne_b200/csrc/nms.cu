@@ -31,6 +31,7 @@ constexpr int kDiagBlocks = kPanelWords * (kPanelWords + 1) / 2;  // 36 (rb <= c
 constexpr int kRowChunk = 16;  // kept rows per bcast CTA
 constexpr int kColChunk = 64;  // columns per bcast CTA
 constexpr int kBcastThreads = 256;
+constexpr int kBcastImages = 256;  // images one broadcast launch can index (larger batches: one launch per group)
 constexpr int kDiagSplit = 4;  // a 64 x 64 diagonal-panel block is worked on by 4 CTAs of 16 rows each
 
 typedef unsigned long long u64;
@@ -42,7 +43,7 @@ enum { kStDiagPairs = 0, kStDiagQueued = 1, kStBcastPairs = 3, kStBcastQueued = 
 static size_t a256n(size_t v) { return (v + 255) / 256 * 256; }
 
 struct NmsLayout {
-    size_t o_aux, o_removed, o_diag, o_pk, o_ctr, o_stats, total;
+    size_t o_aux, o_removed, o_diag, o_pk, o_ctr, o_stats, o_work, total;
     int nblk;
 };
 static NmsLayout nms_layout(int N, int max_sel) {
@@ -59,6 +60,8 @@ static NmsLayout nms_layout(int N, int max_sel) {
     o = a256n(o + static_cast<size_t>(N) * 4);
     y.o_stats = o;
     o = a256n(o + kNmsStats * 8);
+    y.o_work = o;  // one work-item counter per (panel, image group) of the broadcast
+    o = a256n(o + static_cast<size_t>((max_sel + kPanel - 1) / kPanel) * ((N + kBcastImages - 1) / kBcastImages) * 4);
     y.o_diag = o;
     o = a256n(o + static_cast<size_t>(N) * kPanel * kPanelWords * 8);
     y.total = o;
@@ -314,114 +317,149 @@ struct BcastSmem {
     float2 poly[9 * kBcastThreads];  // tri_overlap's per-thread polygon columns
 };
 
-// grid (column chunks after the panel, row chunks of the panel's kept rows, N), 256 threads
+// Work item = (column chunk after the panel, row chunk of the panel's kept rows, image). How many there are is only
+// known on the device (it depends on every image's box count and on how many rows of the panel survived), so the grid
+// is a fixed number of resident CTAs that pull items from a global counter: a panel past the last box of every image
+// costs one wave of CTAs that find zero items instead of tens of thousands of CTAs launched to exit (the capacity bound
+// is 8 960 boxes per image, a typical image has a quarter of that), and the dynamic pull keeps the load balance the
+// hardware's CTA dispatcher gave the one-CTA-per-item version.
 __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* __restrict__ boxes,
                                                               const NmsAux* __restrict__ aux,
-                                                              const int* __restrict__ counts, int max_sel, int nblk,
-                                                              int panel, float thr, const u64* __restrict__ pk,
-                                                              u64* __restrict__ removed, u64* __restrict__ stats) {
-    const int n = blockIdx.z;
-    const int m = counts[n];
-    const int c0 = (panel + 1) * kPanel + blockIdx.x * kColChunk;
-    if (c0 >= m) return;
-    // the row chunk: kept rows number [rc*32, rc*32+32) of the panel
-    const u64* pkn = pk + static_cast<size_t>(n) * kPanelWords;
-    int total = 0;
-    u64 kw[kPanelWords];
-#pragma unroll
-    for (int w = 0; w < kPanelWords; ++w) {
-        kw[w] = pkn[w];
-        total += __popcll(kw[w]);
-    }
-    const int k0 = blockIdx.y * kRowChunk;
-    if (k0 >= total) return;
-    const int nrows = min(kRowChunk, total - k0);
+                                                              const int* __restrict__ counts, int N, int max_sel,
+                                                              int nblk, int panel, float thr,
+                                                              const u64* __restrict__ pk, u64* __restrict__ removed,
+                                                              u64* __restrict__ stats, int* __restrict__ work_ctr) {
     __shared__ BcastSmem sm;
+    __shared__ int s_pref[kBcastImages + 1];  // exclusive prefix of the per-image item counts
+    __shared__ int s_next;
     const int t = threadIdx.x;
-    const size_t ibase = static_cast<size_t>(n) * max_sel;
-    if (t < nrows) {
-        // the (k0 + t)-th set bit of the 512-bit kept mask
-        int want = k0 + t, w = 0;
-        while (want >= __popcll(kw[w])) {
-            want -= __popcll(kw[w]);
-            ++w;
+    for (int n = t; n < N; n += kBcastThreads) {
+        const int after = counts[n] - (panel + 1) * kPanel;
+        int items = 0;
+        if (after > 0) {
+            int kept = 0;
+#pragma unroll
+            for (int w = 0; w < kPanelWords; ++w) kept += __popcll(pk[static_cast<size_t>(n) * kPanelWords + w]);
+            items = ((after + kColChunk - 1) / kColChunk) * ((kept + kRowChunk - 1) / kRowChunk);
         }
-        u64 v = kw[w];
-        for (int i = 0; i < want; ++i) v &= v - 1;
-        sm.rows[t] = panel * kPanel + w * 64 + (__ffsll(static_cast<long long>(v)) - 1);
+        s_pref[n + 1] = items;
     }
+    __syncthreads();
     if (t == 0) {
-        sm.qn = 0;
-        sm.stat_pairs = 0;
+        s_pref[0] = 0;
+        for (int n = 0; n < N; ++n) s_pref[n + 1] += s_pref[n];
     }
     __syncthreads();
-    if (t < nrows) {
-        stage_oriented(boxes + (ibase + sm.rows[t]) * 8, sm.rbox[t]);
-        sm.raux[t] = aux[ibase + sm.rows[t]];
-    }
-    u64* rmv = removed + static_cast<size_t>(n) * nblk;
-    bool alive = false;
-    if (t < kColChunk) {
-        const int col = c0 + t;
-        if (col < m) {
-            alive = !((__ldcg(rmv + (col >> 6)) >> (col & 63)) & 1ull);
-            if (alive) {
-                stage_oriented(boxes + (ibase + col) * 8, sm.cbox[t]);
-                sm.caux[t] = aux[ibase + col];
-            }
+    const int total_items = s_pref[N];
+    int item = blockIdx.x;
+    int n = 0;
+    while (item < total_items) {
+        while (item >= s_pref[n + 1]) ++n;  // items are handed out in increasing order
+        const int m = counts[n];
+        const int col_chunks = (m - (panel + 1) * kPanel + kColChunk - 1) / kColChunk;
+        const int local = item - s_pref[n];
+        const int c0 = (panel + 1) * kPanel + (local % col_chunks) * kColChunk;
+        // the row chunk: kept rows number [k0, k0 + kRowChunk) of the panel
+        const u64* pkn = pk + static_cast<size_t>(n) * kPanelWords;
+        int total = 0;
+        u64 kw[kPanelWords];
+#pragma unroll
+        for (int w = 0; w < kPanelWords; ++w) {
+            kw[w] = pkn[w];
+            total += __popcll(kw[w]);
         }
-        sm.dead[t] = alive ? 0 : 1;
-        sm.newdead[t] = 0;
-    }
-    __syncthreads();
-    // phase 1: kBcastThreads / kColChunk threads per column, a slice of the rows each
-    {
-        constexpr int kTpc = kBcastThreads / kColChunk, kRpt = (kRowChunk + kTpc - 1) / kTpc;
-        const int j = t % kColChunk, part = t / kColChunk;
+        const int k0 = (local / col_chunks) * kRowChunk;
+        const int nrows = min(kRowChunk, total - k0);
+        const size_t ibase = static_cast<size_t>(n) * max_sel;
+        if (t < nrows) {
+            // the (k0 + t)-th set bit of the 512-bit kept mask
+            int want = k0 + t, w = 0;
+            while (want >= __popcll(kw[w])) {
+                want -= __popcll(kw[w]);
+                ++w;
+            }
+            u64 v = kw[w];
+            for (int i = 0; i < want; ++i) v &= v - 1;
+            sm.rows[t] = panel * kPanel + w * 64 + (__ffsll(static_cast<long long>(v)) - 1);
+        }
+        if (t == 0) {
+            sm.qn = 0;
+            sm.stat_pairs = 0;
+        }
+        __syncthreads();
+        if (t < nrows) {
+            stage_oriented(boxes + (ibase + sm.rows[t]) * 8, sm.rbox[t]);
+            sm.raux[t] = aux[ibase + sm.rows[t]];
+        }
+        u64* rmv = removed + static_cast<size_t>(n) * nblk;
+        bool alive = false;
+        if (t < kColChunk) {
+            const int col = c0 + t;
+            if (col < m) {
+                alive = !((__ldcg(rmv + (col >> 6)) >> (col & 63)) & 1ull);
+                if (alive) {
+                    stage_oriented(boxes + (ibase + col) * 8, sm.cbox[t]);
+                    sm.caux[t] = aux[ibase + col];
+                }
+            }
+            sm.dead[t] = alive ? 0 : 1;
+            sm.newdead[t] = 0;
+        }
+        __syncthreads();
+        // phase 1: kBcastThreads / kColChunk threads per column, a slice of the rows each
+        {
+            constexpr int kTpc = kBcastThreads / kColChunk, kRpt = (kRowChunk + kTpc - 1) / kTpc;
+            const int j = t % kColChunk, part = t / kColChunk;
+            const unsigned lane = t & 31;
+            const bool col_on = !sm.dead[j];
+            const NmsAux Q = sm.caux[col_on ? j : 0];
+            unsigned npairs = 0;
+            for (int u = 0; u < kRpt; ++u) {
+                const int r = part * kRpt + u;
+                bool want = col_on && r < nrows;
+                if (want) {
+                    ++npairs;
+                    const NmsAux& P = sm.raux[r];
+                    if (pair_inter_is_zero(P, Q, sm.rbox[r], sm.cbox[j]) && (P.area + Q.area) != 0.f) want = false;
+                }
+                queue_push(sm.queue, &sm.qn, want, static_cast<unsigned short>((r << 7) | j), lane);
+            }
+            for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
+            if (lane == 0 && npairs) atomicAdd(&sm.stat_pairs, npairs);
+        }
+        __syncthreads();
+        // phase 2: 16 lanes per queued pair
+        const int qn = sm.qn;
         const unsigned lane = t & 31;
-        const bool col_on = !sm.dead[j];
-        const NmsAux Q = sm.caux[col_on ? j : 0];
-        unsigned npairs = 0;
-        for (int u = 0; u < kRpt; ++u) {
-            const int r = part * kRpt + u;
-            bool want = col_on && r < nrows;
-            if (want) {
-                ++npairs;
-                const NmsAux& P = sm.raux[r];
-                if (pair_inter_is_zero(P, Q, sm.rbox[r], sm.cbox[j]) && (P.area + Q.area) != 0.f) want = false;
+        for (int e0 = 0; e0 < qn; e0 += kBcastThreads / 16) {
+            const int e = e0 + (t >> 4);
+            bool active = e < qn;
+            const int r = active ? sm.queue[e] >> 7 : 0, j = active ? sm.queue[e] & 127 : 0;
+            // a column some kept row already hit needs no further clip (any hit is enough); atomic read / write of the
+            // 0 -> 1 flag so that concurrent warps are race-free by construction (compute-sanitizer racecheck clean)
+            if (active && atomicOr(&sm.newdead[j], 0u)) active = false;
+            const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active,
+                                                lane, sm.poly + t, kBcastThreads);
+            if (hit && (lane & 15) == 0) atomicExch(&sm.newdead[j], 1u);
+        }
+        if (t == 0) {
+            atomicAdd(stats + kStBcastPairs, static_cast<u64>(sm.stat_pairs));
+            atomicAdd(stats + kStBcastQueued, static_cast<u64>(qn));
+        }
+        __syncthreads();
+        if (t < kColChunk) {
+            const bool newly = alive && sm.newdead[t];
+            const unsigned bal = __ballot_sync(0xffffffffu, newly);
+            if (bal && (t & 31) == 0) {
+                const int cw = c0 + t;  // 32 columns of one warp share a 64-bit word
+                atomicOr(rmv + (cw >> 6), static_cast<u64>(bal) << (cw & 63));
             }
-            queue_push(sm.queue, &sm.qn, want, static_cast<unsigned short>((r << 7) | j), lane);
         }
-        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
-        if (lane == 0 && npairs) atomicAdd(&sm.stat_pairs, npairs);
-    }
-    __syncthreads();
-    // phase 2: 16 lanes per queued pair
-    const int qn = sm.qn;
-    const unsigned lane = t & 31;
-    for (int e0 = 0; e0 < qn; e0 += kBcastThreads / 16) {
-        const int e = e0 + (t >> 4);
-        bool active = e < qn;
-        const int r = active ? sm.queue[e] >> 7 : 0, j = active ? sm.queue[e] & 127 : 0;
-        // a column some kept row already hit needs no further clip (any hit is enough); atomic read / write of the
-        // 0 -> 1 flag so that concurrent warps are race-free by construction (compute-sanitizer racecheck clean)
-        if (active && atomicOr(&sm.newdead[j], 0u)) active = false;
-        const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active,
-                                            lane, sm.poly + t, kBcastThreads);
-        if (hit && (lane & 15) == 0) atomicExch(&sm.newdead[j], 1u);
-    }
-    if (t == 0) {
-        atomicAdd(stats + kStBcastPairs, static_cast<u64>(sm.stat_pairs));
-        atomicAdd(stats + kStBcastQueued, static_cast<u64>(qn));
-    }
-    __syncthreads();
-    if (t < kColChunk) {
-        const bool newly = alive && sm.newdead[t];
-        const unsigned bal = __ballot_sync(0xffffffffu, newly);
-        if (bal && (t & 31) == 0) {
-            const int cw = c0 + t;  // 32 columns of one warp share a 64-bit word
-            atomicOr(rmv + (cw >> 6), static_cast<u64>(bal) << (cw & 63));
-        }
+        // next item (everyone is done with the shared-memory tile once this barrier is passed)
+        __syncthreads();
+        if (t == 0) s_next = static_cast<int>(gridDim.x) + atomicAdd(work_ctr, 1);
+        __syncthreads();
+        item = s_next;
     }
 }
 
@@ -449,7 +487,22 @@ int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float th
     u64* pk = reinterpret_cast<u64*>(b + y.o_pk);
     int* ctr = reinterpret_cast<int*>(b + y.o_ctr);
     u64* stats = reinterpret_cast<u64*>(b + y.o_stats);
-    // removed | pk | ctr | stats are contiguous: one clear
+    int* work = reinterpret_cast<int*>(b + y.o_work);
+    const int groups = (N + kBcastImages - 1) / kBcastImages;
+    static int bcast_ctas = 0;  // resident CTAs of the broadcast kernel on this device
+    if (bcast_ctas == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t q = cudaGetDevice(&dev);
+        if (q == cudaSuccess) q = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (q == cudaSuccess)
+            q = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_bcast_kernel, kBcastThreads, 0);
+        if (q != cudaSuccess || sms <= 0 || per_sm <= 0) {
+            set_error("nms: occupancy query failed: %s", cudaGetErrorString(q));
+            return -1;
+        }
+        bcast_ctas = sms * per_sm;
+    }
+    // removed | pk | ctr | stats | work are contiguous: one clear
     cudaError_t e = cudaMemsetAsync(removed, 0, y.o_diag - y.o_removed, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(nkeep, 0, static_cast<size_t>(N) * 4, s);
     if (e != cudaSuccess) {
@@ -466,9 +519,14 @@ int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float th
         NMS_CHECK_LAUNCH("nms_diag_kernel");
         ++nl;
         const int after = max_sel - (p + 1) * kPanel;
-        if (after > 0) {
-            nms_bcast_kernel<<<dim3((after + kColChunk - 1) / kColChunk, kPanel / kRowChunk, N), kBcastThreads, 0, s>>>(
-                nmsbox, aux, counts, max_sel, y.nblk, p, thr, pk, removed, stats);
+        for (int g = 0; after > 0 && g < groups; ++g) {
+            const int n0 = g * kBcastImages, ng = N - n0 < kBcastImages ? N - n0 : kBcastImages;
+            const long long most = static_cast<long long>((after + kColChunk - 1) / kColChunk) * (kPanel / kRowChunk) * ng;
+            const int grid = most < bcast_ctas ? static_cast<int>(most) : bcast_ctas;
+            nms_bcast_kernel<<<grid, kBcastThreads, 0, s>>>(
+                nmsbox + static_cast<size_t>(n0) * max_sel * 8, aux + static_cast<size_t>(n0) * max_sel, counts + n0, ng,
+                max_sel, y.nblk, p, thr, pk + static_cast<size_t>(n0) * kPanelWords,
+                removed + static_cast<size_t>(n0) * y.nblk, stats, work + p * groups + g);
             NMS_CHECK_LAUNCH("nms_bcast_kernel");
             ++nl;
         }

@@ -75,6 +75,29 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// One lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows the guarded region runs on exactly one
+// thread, so the uniform-datapath operands of tcgen05 / TMA / mbarrier instructions need no per-value convergence loop
+// (R2UR + ELECT + BRA.U.ANY around every instruction made the MMA-issuing thread the bottleneck of small-N tiles).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// A/B switches (compile time): -DDAFNE_ELECT_MASK=<bits> selects which single-thread roles use elect.sync
+// (1 = MMA issuer, 2 = operand TMA producer, 4 = residual TMA producer). Measured on one B200 (r2j A/B, R50 b8): 3x3
+// narrow-N convs -6 %, prediction convs -17 %, stem -18 % with 1|2; the residual producer is left on `lane == 0`
+// (electing it made the HBM-bound residual convs 1-2 % slower: its loads then run further ahead of the operand loads).
+#ifndef DAFNE_ELECT_MASK
+#define DAFNE_ELECT_MASK 3
+#endif
+#define DAFNE_ONE_THREAD(bit, lane) (((DAFNE_ELECT_MASK) & (bit)) ? dafne::elect_one_sync() : ((lane) == 0))
+
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
     asm volatile(

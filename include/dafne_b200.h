@@ -133,7 +133,7 @@ int dafne_detect_host_end(dafne_ctx* ctx, int ticket);
 
 /* Per-layer parity support. keep != 0 (set BEFORE dafne_bind_workspace) disables activation-memory reuse so that
  * every intermediate survives the forward; dafne_debug_activation then returns the NHWC fp16 tensor called `name`:
- * "stem", "pool", "res2.0" ... "res5.2", "p3" ... "p7", "cls_tower.l0" ... "corners_tower.l4". */
+ * "pool" (stem conv + max-pool, one kernel), "res2.0" ... "res5.2", "p3" ... "p7", "cls_tower.l0" ... "corners_tower.l4". */
 int dafne_debug_keep_activations(dafne_ctx* ctx, int keep);
 int dafne_debug_activation(dafne_ctx* ctx, const char* name, const void** dev_ptr, int* N, int* H, int* W, int* C);
 

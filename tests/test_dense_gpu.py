@@ -46,6 +46,8 @@ def test_layerwise_vs_quantisation_matched_oracle(setup):
     eng, spec, sd, sizes, ref16, ref32 = setup
     worst = 0.0
     for name, r in ref16["named"].items():
+        if name == "stem":
+            continue  # the stem's max-pool runs in its epilogue: the conv output exists only as "pool"
         a = eng.activation(name).cpu()
         assert a.shape == r.shape, name
         rel = ((a - r).norm() / (r.norm() + 1e-12)).item()
@@ -68,9 +70,10 @@ def test_head_outputs_vs_fp32_reference_arithmetic(setup):
 def test_zero_padding_after_normalisation(setup):
     """ImageList.from_tensors pads with 0 AFTER normalising: the stem must see 0, not -mean, outside image 1."""
     eng, spec, sd, sizes, ref16, ref32 = setup
-    a = eng.activation("stem").cpu()
-    r = ref16["named"]["stem"]
+    a = eng.activation("pool").cpu()
+    r = ref16["named"]["pool"]
     assert torch.allclose(a[1, :, -8:, -16:], r[1, :, -8:, -16:], atol=1e-2)
+    assert torch.allclose(a, r, rtol=4e-3, atol=2e-2)  # (fp16 ulps) every pooled pixel, image borders and tile seams included
 
 
 def test_fused_postprocess_equals_oracle_on_gpu_heads(setup):
