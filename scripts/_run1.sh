@@ -1,3 +1,6 @@
 mkdir -p gpurun_out
-timeout 400 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'conv_tc_kernel<\(int\)256, \(int\)2, \(int\)1>' -s 47 -c 1 -o gpurun_out/r2j_res4conv3 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2j_ncu_res4.log 2>&1
-tail -n 2 gpurun_out/r2j_ncu_res4.log | cut -c1-200
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -n 6
+for rep in 1 2; do
+timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2k_bench_$rep.json 2> gpurun_out/r2k_bench.err; tail -c 300 gpurun_out/r2k_bench.err; python -c "
+import json;d=json.load(open('gpurun_out/r2k_bench_$rep.json'));print(d['value'],d['e2e']['value'],d['roofline']['all_convs']['forward_ms_sum_of_launches'],d['gpu_launches'])"
+done
