@@ -32,7 +32,10 @@ constexpr int kRowChunk = 16;  // kept rows per bcast CTA
 constexpr int kColChunk = 64;  // columns per bcast CTA
 constexpr int kBcastThreads = 256;
 constexpr int kBcastImages = 256;  // images one broadcast launch can index (larger batches: one launch per group)
-constexpr int kDiagSplit = 4;  // a 64 x 64 diagonal-panel block is worked on by 4 CTAs of 16 rows each
+#ifndef DAFNE_DIAG_SPLIT
+#define DAFNE_DIAG_SPLIT 4
+#endif
+constexpr int kDiagSplit = DAFNE_DIAG_SPLIT;  // a 64 x 64 diagonal-panel block is worked on by 4 CTAs of 16 rows each
 
 typedef unsigned long long u64;
 // work counters of the last run_nms (diagnostics, bench.py): pairs the sweep consulted and pairs that needed the clip,
@@ -163,7 +166,10 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
     const int m = counts[n];
     const int base = panel * kPanel;
     if (base >= m) return;  // uniform for the whole image: nobody counts, nothing to resolve
-    __shared__ DiagSmem sm;
+    // the pair phase's tile and the sweep's copy of the panel's hit words (32 KB) share the same shared memory
+    constexpr size_t kSweepBytes = static_cast<size_t>(kPanel) * kPanelWords * sizeof(u64);
+    __shared__ __align__(16) unsigned char smem_raw[sizeof(DiagSmem) > kSweepBytes ? sizeof(DiagSmem) : kSweepBytes];
+    DiagSmem& sm = *reinterpret_cast<DiagSmem*>(smem_raw);
     // decode (rb, cb) from the linear upper-triangle index; `sub` = which 16 rows of the 64-row block
     const int sub = blockIdx.x % kDiagSplit;
     int rb = 0, rem = blockIdx.x / kDiagSplit;
@@ -244,32 +250,37 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
     __syncthreads();
     if (t == 0) sm.last = (atomicAdd(&ctr[n], 1) == kDiagBlocks * kDiagSplit - 1);
     __syncthreads();
-    if (!sm.last) return;
+    const bool last = sm.last;
+    __syncthreads();  // the tile is dead from here on: the sweep reuses its memory
+    if (!last) return;
     __threadfence();
 
-    // ---- last block of this image: sequential sweep inside the panel (64 rows at a time)
+    // ---- last block of this image: sequential sweep inside the panel (64 rows at a time). All hit words of the panel
+    // come to shared memory in one pass of independent loads first: the sweep is a chain of 8 dependent steps, and a
+    // dependent L2 round trip per step and per later word (28 of them) was what it spent its 25 us on.
     __shared__ u64 s_rem[kPanelWords], s_kept[kPanelWords];
+    u64* s_dg = reinterpret_cast<u64*>(smem_raw);
     const u64* dg = diag + static_cast<size_t>(n) * kPanel * kPanelWords;
+    const int rows_in_panel = min(kPanel, m - base);
+#pragma unroll 8
+    for (int i = t; i < rows_in_panel * kPanelWords; i += kDiagThreads) s_dg[i] = __ldcg(dg + i);
     if (t < kPanelWords) {
         const int w = (base >> 6) + t;
         s_rem[t] = w < nblk ? rmv[w] : ~0ull;
         s_kept[t] = 0;
     }
     __syncthreads();
-    const int rows_in_panel = min(kPanel, m - base);
     for (int b = 0; b * 64 < rows_in_panel; ++b) {
         const int rows = min(64, rows_in_panel - b * 64);
-        // the diagonal word of each row of this block, staged so one thread can walk them back to back
-        if (t < 64) sm.bits[t] = t < rows ? __ldcg(dg + (static_cast<size_t>(b) * 64 + t) * kPanelWords + b) : 0ull;
-        __syncthreads();
         if (t == 0) {
             u64 cur = s_rem[b], alive = 0;
             if (rows < 64) cur |= ~0ull << rows;
+            const u64* dw = s_dg + static_cast<size_t>(b) * 64 * kPanelWords + b;  // diagonal word of row r: dw[r * 8]
 #pragma unroll 8
             for (int r = 0; r < 64; ++r) {
                 if (!((cur >> r) & 1ull)) {
                     alive |= 1ull << r;
-                    cur |= sm.bits[r];
+                    if (r < rows) cur |= dw[r * kPanelWords];
                 }
             }
             s_kept[b] = alive;
@@ -278,7 +289,7 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
         // survivors of this block suppress later blocks of the panel
         if (t < 64 && ((s_kept[b] >> t) & 1ull)) {
             for (int w = b + 1; w < kPanelWords; ++w) {
-                const u64 v = __ldcg(dg + (static_cast<size_t>(b) * 64 + t) * kPanelWords + w);
+                const u64 v = s_dg[(static_cast<size_t>(b) * 64 + t) * kPanelWords + w];
                 if (v) atomicOr(&s_rem[w], v);
             }
         }

@@ -571,7 +571,7 @@ struct FinalArgs {
     int capacity;
 };
 
-__global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
+__global__ void __launch_bounds__(1024) finalize_kernel(FinalArgs a) {
     const int n = blockIdx.x;
     const size_t rowbase = static_cast<size_t>(n) * a.max_sel;
     const int* kp = a.keep + rowbase;
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
     const float sy = static_cast<float>(static_cast<double>(oh_i) / static_cast<double>(ih));
     const float ow = static_cast<float>(ow_i), oh = static_cast<float>(oh_i);
     float* out = a.dets + static_cast<size_t>(n) * a.capacity * kDet;
-    // order-preserving compaction, 256 rows per round
+    // order-preserving compaction, one block-wide round per blockDim.x rows (the usual <= ~1000 kept rows: one round)
     for (int r0 = 0; r0 < nk; r0 += blockDim.x) {
         const int r = r0 + threadIdx.x;
         bool ok = false;
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
             }
         }
         // block-wide exclusive scan of ok
-        __shared__ int s_warp[8];
+        __shared__ int s_warp[32];
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
         if (lane == 0) s_warp[w] = __popc(m);
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
         __syncthreads();
         if (threadIdx.x == 0) {
             int tot = 0;
-            for (int i = 0; i < 8; ++i) tot += s_warp[i];
+            for (unsigned i = 0; i < (blockDim.x >> 5); ++i) tot += s_warp[i];
             s_out += tot;
         }
         __syncthreads();
@@ -813,7 +813,7 @@ int launch_postprocess(const PostParams& p, cudaStream_t s, int64_t* launches) {
         a.dets = p.dets;
         a.counts = p.counts;
         a.capacity = p.capacity;
-        finalize_kernel<<<p.N, 256, 0, s>>>(a);
+        finalize_kernel<<<p.N, 1024, 0, s>>>(a);
         POST_CHECK_LAUNCH("finalize_kernel");
         if (launches) *launches += 1;
     }
