@@ -274,6 +274,7 @@ int dafne_detect_host_begin(dafne_ctx* ctx, const void* host_images, int dtype, 
     cudaError_t e = cudaSuccess;
     if (!ctx->copy_stream) {
         e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
             e = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_compute[i], cudaEventDisableTiming);
@@ -301,13 +302,17 @@ int dafne_detect_host_begin(dafne_ctx* ctx, const void* host_images, int dtype, 
         return -1;
     }
     if (dafne_detect(ctx, img, dtype, image_sizes, output_sizes, dets, counts, capacity, stream)) return -1;
+    // results go back on their own stream: the next batch's kernels do not queue behind the D2H copies (the staging
+    // buffers of this slot are not rewritten before dafne_detect_host_end(ticket) has seen ev_result)
     e = cudaEventRecord(ctx->ev_compute[k], s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_compute[k], 0);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(host_dets, dets, static_cast<size_t>(ctx->N) * capacity * DAFNE_DET_STRIDE * 4,
-                            cudaMemcpyDeviceToHost, s);
+                            cudaMemcpyDeviceToHost, ctx->d2h_stream);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(host_counts, counts, static_cast<size_t>(ctx->N) * 4, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_result[k], s);
+        e = cudaMemcpyAsync(host_counts, counts, static_cast<size_t>(ctx->N) * 4, cudaMemcpyDeviceToHost,
+                            ctx->d2h_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_result[k], ctx->d2h_stream);
     if (e != cudaSuccess) {
         set_error("dafne_detect_host_begin D2H: %s", cudaGetErrorString(e));
         return -1;

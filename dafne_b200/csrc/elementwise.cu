@@ -99,58 +99,11 @@ int launch_preprocess(const void* images, int dtype, const int32_t* sizes_dev, i
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ max pool
+// ------------------------------------------------------------------------------------------------ fp16x2 max (ReLU copy)
+// (the stem's 3x3 max-pool lives in the stem kernel's epilogue, stem_tc.cu)
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
     const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
     return *reinterpret_cast<const uint32_t*>(&r);
-}
-
-__global__ void maxpool_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int Ho, int Wo,
-                               __half* __restrict__ out) {
-    const int c8 = C / 8;
-    const size_t total = static_cast<size_t>(N) * Ho * Wo * c8;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int cv = i % c8;
-        const int ox = (i / c8) % Wo;
-        const int oy = (i / (static_cast<size_t>(c8) * Wo)) % Ho;
-        const int n = i / (static_cast<size_t>(c8) * Wo * Ho);
-        uint4 m;
-        bool first = true;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = 2 * oy - 1 + ky;
-            if (iy < 0 || iy >= H) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = 2 * ox - 1 + kx;
-                if (ix < 0 || ix >= W) continue;
-                const uint4 v =
-                    __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(n) * H + iy) * W + ix) * C) + cv);
-                if (first) {
-                    m = v;
-                    first = false;
-                } else {
-                    m.x = hmax2_u32(m.x, v.x);
-                    m.y = hmax2_u32(m.y, v.y);
-                    m.z = hmax2_u32(m.z, v.z);
-                    m.w = hmax2_u32(m.w, v.w);
-                }
-            }
-        }
-        reinterpret_cast<uint4*>(out)[i] = m;
-    }
-}
-
-int launch_maxpool3x3s2(const __half* in, int N, int H, int W, int C, __half* out, cudaStream_t s) {
-    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-    const size_t total = static_cast<size_t>(N) * Ho * Wo * (C / 8);
-    const int threads = 256;
-    size_t blocks = (total + threads - 1) / threads;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    maxpool_kernel<<<static_cast<int>(blocks), threads, 0, s>>>(in, N, H, W, C, Ho, Wo, out);
-    DAFNE_CHECK_LAUNCH("maxpool_kernel");
-    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm + ReLU

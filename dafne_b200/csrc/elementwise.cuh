@@ -13,7 +13,6 @@ int launch_preprocess(const void* images, int dtype, const int32_t* sizes_dev, i
                       const float* std3, __half* out_canvas, cudaStream_t s);
 
 // 3x3 stride-2 pad-1 max pool, NHWC fp16, C % 8 == 0.
-int launch_maxpool3x3s2(const __half* in, int N, int H, int W, int C, __half* out, cudaStream_t s);
 
 // In-place y = relu(groupnorm(x)) of several NHWC fp16 tensors [N, HW, 256] (32 groups of 8 channels) in one launch.
 constexpr int kMaxGnProblems = 16;

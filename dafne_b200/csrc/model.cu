@@ -196,6 +196,7 @@ void ctx_destroy(dafne_ctx* c) {
     if (c->stem_shift) cudaFree(c->stem_shift);
     if (c->scales_dev) cudaFree(c->scales_dev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     for (int k = 0; k < 2; ++k) {
         if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]);
         if (c->ev_compute[k]) cudaEventDestroy(c->ev_compute[k]);

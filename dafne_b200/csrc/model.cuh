@@ -103,7 +103,8 @@ struct dafne_ctx {
     void* images_dev2 = nullptr;
     float* dets_dev2 = nullptr;
     int32_t* counts_dev2 = nullptr;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of the next batch
+    cudaStream_t d2h_stream = nullptr;   // D2H of finished results (keeps the compute stream free of copies)
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_result[2] = {nullptr, nullptr};
     bool slot_pending[2] = {false, false};
     bool slot_used[2] = {false, false};

@@ -443,7 +443,7 @@ __device__ __forceinline__ float float_from_order_key(unsigned k) {
 constexpr int kRankRows = 256;
 
 __global__ void __launch_bounds__(kRankRows) rank_decode_kernel(DecodeArgs a) {
-    extern __shared__ unsigned long long s_keys[];
+    extern __shared__ __align__(16) unsigned long long s_keys[];
     __shared__ float s_min[kRankRows / 32], s_max[kRankRows / 32];
     const int n = blockIdx.y;
     const int m = a.sel_cnt[n];
@@ -457,9 +457,13 @@ __global__ void __launch_bounds__(kRankRows) rank_decode_kernel(DecodeArgs a) {
     const unsigned long long key = on ? s_keys[i] : 0ull;
     int r = 0;
     {
+        // two keys per 16-byte broadcast load (the dynamic shared-memory window is 16-byte aligned)
+        const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(s_keys);
         int j = 0;
+#pragma unroll 4
         for (; j + 4 <= m; j += 4) {
-            r += (s_keys[j] > key) + (s_keys[j + 1] > key) + (s_keys[j + 2] > key) + (s_keys[j + 3] > key);
+            const ulonglong2 u = k2[j >> 1], v = k2[(j >> 1) + 1];
+            r += (u.x > key) + (u.y > key) + (v.x > key) + (v.y > key);
         }
         for (; j < m; ++j) r += s_keys[j] > key;
     }

@@ -87,7 +87,7 @@ def tensor_pipe(csv_path, per_launch_json, dst, first_global_index):
             continue
         nm = o["name"]
         g = ("head towers" if "tower" in nm else "head predictions" if nm.startswith("pred") else
-             "FPN + P6/P7" if ("fpn" in nm or "top_block" in nm) else "stem" if nm == "stem" else "ResNet " + nm.split("bottom_up.")[-1].split(".")[0])
+             "FPN + P6/P7" if ("fpn" in nm or "top_block" in nm) else "stem" if nm.startswith("stem") else "ResNet " + nm.split("bottom_up.")[-1].split(".")[0])
         tp = m["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
         us = m["gpu__time_duration.sum"] / 1e3
         dram = (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) / 1e6
