@@ -57,13 +57,13 @@ struct ConvCfg {
     static constexpr int B_BYTES = BLOCK_N * 128;  // BLOCK_N couts x 64 ch fp16
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SLOT_BYTES = 16384;  // 128 pixels x 64 ch fp16, one epilogue chunk
-    static constexpr int AUX_HDR = 512;       // barriers, tmem pointer, tile offsets
+    static constexpr int AUX_HDR = 512;       // barriers (2 x MAX_RING residual slots at +256 / +352), tmem pointer, tile offsets
     // + (scale, shift) pairs per warpgroup; MODE 2 (tower convs: bias only) keeps the shifts alone
     static constexpr int aux_bytes(int mode) { return AUX_HDR + EPI_WGS * BLOCK_N * (mode == 2 ? 4 : 8); }
     static constexpr int AUX_BYTES = AUX_HDR + EPI_WGS * BLOCK_N * 8;
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
     static constexpr int THREADS = 128 + 128 * EPI_WGS;
-    static constexpr int MAX_STAGES = 8, MAX_RING = 4;
+    static constexpr int MAX_STAGES = 8, MAX_RING = 6;
     // row-shared taps: A box = 18 rows x 8 px x 64 ch (18 KB, padded to 19 KB so B stays 1024-aligned) + B of 3 taps
     static constexpr int A_RS_BOX_BYTES = 18 * 1024;
     static constexpr int A_RS_BYTES = 19 * 1024;
@@ -212,9 +212,10 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
     const uint32_t bar_tempty = s_aux + 144;     // 2 x 8 B
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(aux + 160);
     int* s_begin = reinterpret_cast<int*>(aux + 168);  // nprob + 1 tile offsets (<= 17 ints)
-    const uint32_t bar_rfull = s_aux + 256;      // [EPI_WGS][4] x 8 B: residual chunk landed in the slot
-    const uint32_t bar_rempty = s_aux + 320;     // [EPI_WGS][4] x 8 B: the slot's output store has been read out
-    const uint32_t bar_bfull = s_aux + 384;      // resident weights landed
+    constexpr int RS = Cfg::MAX_RING;            // barrier slots per warpgroup
+    const uint32_t bar_rfull = s_aux + 256;      // [2][MAX_RING] x 8 B: residual chunk landed in the slot
+    const uint32_t bar_rempty = s_aux + 352;     // [2][MAX_RING] x 8 B: the slot's output store has been read out
+    const uint32_t bar_bfull = s_aux + 448;      // resident weights landed
     float2* s_tab_all = reinterpret_cast<float2*>(aux + Cfg::AUX_HDR);
 
     if (warp == 0 && lane < nprob) {
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
         }
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 2 * RS; ++i) {
             mbar_init(bar_rfull + 8 * i, 1);
             mbar_init(bar_rempty + 8 * i, 1);
         }
@@ -444,8 +445,8 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                     const int c = cnt[wg]++;
                     const int slot = c % ring;
                     const uint32_t round = static_cast<uint32_t>(c / ring);
-                    mbar_wait(bar_rempty + 8 * (wg * 4 + slot), (round & 1) ^ 1);
-                    const uint32_t full = bar_rfull + 8 * (wg * 4 + slot);
+                    mbar_wait(bar_rempty + 8 * (wg * RS + slot), (round & 1) ^ 1);
+                    const uint32_t full = bar_rfull + 8 * (wg * RS + slot);
                     mbar_arrive_expect_tx(full, Cfg::SLOT_BYTES);
                     tma_load_4d(s_epi + (wg * ring + slot) * Cfg::SLOT_BYTES, &pr->tmRes, full,
                                 tc.nt * BLOCK_N + j * 64, tc.x0, tc.y0, tc.n0);
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                     DAFNE_TMEM_LD_X32(taddr + chbase + 32, (v + 32));
                     if (res_tma) {
                         // the residual chunk of this tile, TMA-loaded into the slot the output is staged in
-                        mbar_wait(bar_rfull + 8 * (wg * 4 + slot), static_cast<uint32_t>(chunk_cnt / ring) & 1);
+                        mbar_wait(bar_rfull + 8 * (wg * RS + slot), static_cast<uint32_t>(chunk_cnt / ring) & 1);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const uint32_t src = buf + row * 128 + ((q ^ (row & 7)) << 4);
@@ -652,7 +653,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                         if (res_tma && chunk_cnt > 0) {
                             // the previous chunk's store has read its slot: the residual producer may refill it
                             tma_store_wait_read<1>();
-                            mbar_arrive(bar_rempty + 8 * (wg * 4 + (chunk_cnt - 1) % ring));
+                            mbar_arrive(bar_rempty + 8 * (wg * RS + (chunk_cnt - 1) % ring));
                         }
                     }
                 }
@@ -786,6 +787,17 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
             return -1;
         }
         bn = d.Cout % 256 == 0 ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
+        // The bottleneck-closing 1x1 convolutions of res2-res4 (K <= 256, residual at the output's resolution) are
+        // HBM-bound and their critical path is the residual stream through the epilogue ring: 128-wide tiles leave
+        // shared memory for a deeper ring and more operand stages (r2n A/B on one B200, per forward: res2 conv3
+        // 382 -> 302 us and res3 303 -> 239 us with ring 4 / 3 stages; res4 282 -> 237 us with ring 3 / 4 stages;
+        // ring 5 / 2 stages and ring 2 are both worse, the latter by 50 %).
+        const bool res_1x1 = d.residual != nullptr && d.res_shift == 0 && d.ksize == 1 && d.Cin <= 256;
+        if (res_1x1 && d.Cout % 128 == 0) bn = 128;
+        if (const char* ov = getenv("DAFNE_CONV_RES_BN")) {  // tuning aid: tile width of those convolutions
+            const int v = atoi(ov);
+            if (res_1x1 && (v == 256 || v == 128 || v == 64) && d.Cout % v == 0) bn = v;
+        }
     }
     ConvParams& p = plan->prob.p;
     p.N = d.N;
@@ -924,7 +936,13 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
         const uint64_t str[3] = {Co * 2, Wo * Co * 2, Ho * Wo * Co * 2};
         if (encode_map(&plan->prob.tmRes, d.residual, 4, dims, str, boxA, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "Res"))
             return -1;
-        plan->res_tma = 1;
+        // res_tma carries the ring depth asked for (>= 2): the residual prefetch distance, paid for in operand stages
+        plan->res_tma = 4;
+        if (d.ksize == 1 && bn == 128 && d.Cin > 128) plan->res_tma = 3;  // K = 256: four operand stages matter more
+        if (const char* ov = getenv("DAFNE_CONV_RING")) {  // tuning aid: 2 .. MAX_RING
+            const int v = atoi(ov);
+            if (v >= 2 && v <= 6) plan->res_tma = v;
+        }
     }
     // K <= 256 (every 1x1 of res2-res4, the 3x3 of res2): HBM-bound, the epilogue is the critical path
     plan->epi_wgs = (!small && p.num_taps * d.Cin <= 256) ? 2 : 1;
@@ -940,7 +958,7 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
 template <int BN, int WGS>
 static void conv_smem_config(int res_tma, int row_shared, int breg, int mode, int* stages, int* ring) {
     using Cfg = ConvCfg<BN, WGS>;
-    int r = BN < 64 ? 2 : (res_tma ? 4 : (WGS == 2 ? 3 : 2));
+    int r = BN < 64 ? 2 : (res_tma ? (res_tma >= 2 && res_tma <= Cfg::MAX_RING ? res_tma : 4) : (WGS == 2 ? 3 : 2));
     int st = Cfg::MAX_STAGES;
     while (st > 2 && Cfg::smem_bytes(st, r, row_shared, breg, mode) > kMaxSmem) --st;
     while (r > 2 && Cfg::smem_bytes(st, r, row_shared, breg, mode) > kMaxSmem) --r;

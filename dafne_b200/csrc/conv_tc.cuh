@@ -65,7 +65,8 @@ struct ConvPlan {
     int block_n;
     int epi_wgs;  // epilogue warpgroups the shape wants (1 | 2, see ConvCfg)
     int mode;     // epilogue variant: 0 plain, 1 residual add, 2 GroupNorm statistics
-    int res_tma;  // residual at the output's resolution: loaded by TMA into the epilogue ring
+    int res_tma;  // != 0: residual at the output's resolution, loaded by TMA into the epilogue ring; the value is the
+                  // ring depth asked for (2..6)
     int row_shared;  // 3x3 stride 1, narrow N tile: 0 one A load per tap; 1 one per horizontal tap (18-row box);
                      // 2 one halo box for all nine taps; 3 the same with the weights resident in shared memory
     int breg_bytes;  // mode 3: bytes of the resident weight region (9 x Cin/64 x BLOCK_N x 128)

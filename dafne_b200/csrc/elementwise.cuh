@@ -12,8 +12,6 @@ namespace dafne {
 int launch_preprocess(const void* images, int dtype, const int32_t* sizes_dev, int N, int H, int W, const float* mean3,
                       const float* std3, __half* out_canvas, cudaStream_t s);
 
-// 3x3 stride-2 pad-1 max pool, NHWC fp16, C % 8 == 0.
-
 // In-place y = relu(groupnorm(x)) of several NHWC fp16 tensors [N, HW, 256] (32 groups of 8 channels) in one launch.
 constexpr int kMaxGnProblems = 16;
 struct GnProblem {
