@@ -67,29 +67,66 @@ def load_spec(workload):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). NVML in-process (one
+    sample every 5 ms: the timed region of a default run is a quarter of a second) with nvidia-smi as the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.rows = []  # (sm_mhz, max_mhz, set(reasons))
+        self.source = None
         self._stop = threading.Event()
         self._t = None
 
-    def _run(self):
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _run_nvml(self):
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.source = "nvml"
+        while not self._stop.is_set():
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            mask = int(get_reasons(h))
+            self.rows.append((sm, mx, {k for k, b in self.BITS.items() if mask & b}))
+            self._stop.wait(0.005)
+        nv.nvmlShutdown()
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
         while not self._stop.is_set():
             try:
                 out = subprocess.run(
-                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                    capture_output=True, text=True, timeout=5).stdout.strip()
+                    ["nvidia-smi", f"--id={self._physical_index()}", f"--query-gpu={self.Q}",
+                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                    r = [c.strip() for c in out.split(",")]
+                    names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                    self.rows.append((float(r[0]), float(r[1]),
+                                      {n for n, v in zip(names, r[3:7]) if v.lower().startswith("active")}))
             except Exception:
                 pass
             self._stop.wait(0.2)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -99,19 +136,11 @@ class ClockSampler:
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except (ValueError, IndexError):
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = sorted(r[0] for r in self.rows)
+        mx = max((r[1] for r in self.rows), default=0.0)
+        reasons = set().union(*[r[2] for r in self.rows]) if self.rows else set()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def measured_peaks():
@@ -194,6 +223,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG set on the box) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, spec, batch, H, W, what = load_spec(args.workload)
