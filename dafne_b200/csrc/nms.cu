@@ -6,7 +6,8 @@
 // 512:
 //   nms_diag_kernel   panel x panel upper triangle for the rows/columns still alive, then (last block done) the
 //                     sequential sweep inside the panel -> the panel's kept rows
-//   nms_bcast_kernel  kept rows of the panel x every later box still alive; sets `removed` bits
+//   nms_bcast_kernel  kept rows of the panel x every later box still alive; sets `removed` bits (one wave of resident
+//                     CTAs pulling (column chunk, row chunk, image) items from a counter)
 // Work drops from n^2/2 pairs to about (kept x alive) pairs. Inside both kernels a pair first goes through
 // pair_inter_is_zero() (polyiou.cuh: proves inter == 0 for separated boxes without running the clip); the pairs that
 // need the full fp32 clip are compacted into a shared-memory queue and processed with all lanes busy: a queued pair is
@@ -35,7 +36,9 @@ constexpr int kBcastImages = 256;  // images one broadcast launch can index (lar
 #ifndef DAFNE_DIAG_SPLIT
 #define DAFNE_DIAG_SPLIT 4
 #endif
-constexpr int kDiagSplit = DAFNE_DIAG_SPLIT;  // a 64 x 64 diagonal-panel block is worked on by 4 CTAs of 16 rows each
+// a 64 x 64 diagonal-panel block is worked on by 4 CTAs of 16 rows each (measured r2k, diag kernels per step:
+// split 4 = 402 us, 8 = 416 us, 16 = 480 us)
+constexpr int kDiagSplit = DAFNE_DIAG_SPLIT;
 
 typedef unsigned long long u64;
 // work counters of the last run_nms (diagnostics, bench.py): pairs the sweep consulted and pairs that needed the clip,
