@@ -207,7 +207,17 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle to the real stdout for it and point fd 1 at stderr for
+    everything else in the process (NCCL's banner when NCCL_DEBUG is set on the box, library warnings)."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def run_ours(args):
+    out_stream = claim_stdout()
     import torch
     import torch.distributed as dist
 
@@ -223,8 +233,6 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG set on the box) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, spec, batch, H, W, what = load_spec(args.workload)
@@ -411,7 +419,7 @@ def run_ours(args):
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

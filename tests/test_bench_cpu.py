@@ -54,3 +54,14 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_claim_stdout_keeps_stdout_for_the_json_line_only():
+    code = ("import sys, os; sys.path.insert(0, %r); import importlib.util as u;"
+            "sp = u.spec_from_file_location('b', os.path.join(%r, 'bench.py')); b = u.module_from_spec(sp); sp.loader.exec_module(b);"
+            "out = b.claim_stdout(); print('noise from a library'); os.write(1, b'raw fd-1 noise\\n');"
+            "print('{\"ok\": 1}', file=out, flush=True)") % (ROOT, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == '{"ok": 1}'
+    assert "noise from a library" in r.stderr and "raw fd-1 noise" in r.stderr
