@@ -121,8 +121,9 @@ int dafne_detect_host(dafne_ctx* ctx, const void* host_images, int dtype, const 
                       void* stream);
 
 /* Pipelined form of dafne_detect_host for serving loops (same arguments, same results). _begin enqueues the H2D copy
- * of this batch on the context's own copy stream into one of two staging buffers, then detection and the D2H copies
- * on `stream`, and returns without synchronising; *ticket identifies the batch. _end blocks until that batch's
+ * of this batch on the context's own copy stream into one of two staging buffers, then detection on `stream` and the
+ * D2H copies of its results on a second copy stream (so the next batch's kernels never queue behind a copy), and
+ * returns without synchronising; *ticket identifies the batch. _end blocks until that batch's
  * detections and counts are in the host buffers given to _begin. At most two batches are in flight: calling
  * _begin(i + 1) before _end(i) overlaps the H2D copy of batch i + 1 with the compute of batch i. The host buffers of
  * a batch must stay valid and untouched until its _end returns. */
