@@ -19,23 +19,38 @@ def shard_range(n_items: int, rank: int, world: int) -> range:
     return range(begin, min(begin + per, n_items))
 
 
+def pack_wire(dets: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """[B, cap, D] float32 detections + [B] int32 counts -> one [B, cap * D + 1] float32 buffer; the count rides in the
+    last element of its image's row as raw bits (a view, not a conversion), so the exchange is ONE collective."""
+    b = dets.shape[0]
+    wire = torch.empty(b, dets[0].numel() + 1, dtype=torch.float32, device=dets.device)
+    wire[:, :-1] = dets.reshape(b, -1)
+    wire[:, -1] = counts.to(torch.int32).view(torch.float32)
+    return wire
+
+
+def unpack_wire(wire: torch.Tensor, det_shape) -> Tuple[torch.Tensor, torch.Tensor]:
+    n = wire.shape[0]
+    dets = wire[:, :-1].reshape((n,) + tuple(det_shape))
+    counts = wire[:, -1].contiguous().view(torch.int32)
+    return dets, counts
+
+
 def gather_detections(dets: torch.Tensor, counts: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """All-gather [B_local, cap, 20] detections and [B_local] counts -> ([world*B_local, cap, 20], [world*B_local]),
-    rank-major. One collective per tensor, issued on the current stream (NCCL) right after the NMS kernel."""
+    rank-major: exactly one all-gather, issued on the current stream (NCCL) right after the last kernel."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return dets, counts
     world = dist.get_world_size(group)
+    wire = pack_wire(dets, counts)
     if dist.get_backend(group) == "nccl":
-        out_d = torch.empty((world * dets.shape[0],) + tuple(dets.shape[1:]), dtype=dets.dtype, device=dets.device)
-        out_c = torch.empty(world * counts.shape[0], dtype=counts.dtype, device=counts.device)
-        dist.all_gather_into_tensor(out_d, dets.contiguous(), group=group)
-        dist.all_gather_into_tensor(out_c, counts.contiguous(), group=group)
-        return out_d, out_c
-    ld = [torch.empty_like(dets) for _ in range(world)]
-    lc = [torch.empty_like(counts) for _ in range(world)]
-    dist.all_gather(ld, dets.contiguous(), group=group)
-    dist.all_gather(lc, counts.contiguous(), group=group)
-    return torch.cat(ld, 0), torch.cat(lc, 0)
+        out = torch.empty(world * wire.shape[0], wire.shape[1], dtype=wire.dtype, device=wire.device)
+        dist.all_gather_into_tensor(out, wire, group=group)
+    else:
+        parts = [torch.empty_like(wire) for _ in range(world)]
+        dist.all_gather(parts, wire, group=group)
+        out = torch.cat(parts, 0)
+    return unpack_wire(out, dets.shape[1:])
 
 
 def pad_shard(items: Sequence, per_rank: int, filler):

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from dafne_b200.distributed import detect_sharded, gather_detections, shard_range
+from dafne_b200.distributed import detect_sharded, gather_detections, pack_wire, shard_range, unpack_wire
 
 
 class FakeEngine:
@@ -75,3 +75,14 @@ def test_shard_range():
     assert [list(shard_range(5, r, 2)) for r in range(2)] == [[0, 1, 2], [3, 4]]
     assert [list(shard_range(2, r, 4)) for r in range(4)] == [[0], [1], [], []]
     assert sum(len(shard_range(128, r, 8)) for r in range(8)) == 128
+
+
+def test_wire_format_round_trips_counts_bit_exactly():
+    g = torch.Generator().manual_seed(0)
+    dets = torch.randn(3, 5, 20, generator=g)
+    counts = torch.tensor([0, 5, 2_000_000_000], dtype=torch.int32)  # as raw bits: includes NaN-looking patterns
+    wire = pack_wire(dets, counts)
+    assert wire.shape == (3, 101) and wire.dtype == torch.float32
+    d2, c2 = unpack_wire(wire.clone(), dets.shape[1:])
+    assert torch.equal(d2, dets) and torch.equal(c2, counts)
+
