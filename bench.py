@@ -1,14 +1,19 @@
 #!/usr/bin/env python
 """Benchmark of the DAFNe inference hot path on B200 (contract: see the task description / DESIGN.md section 6).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload r50_b8|r101_b32|...]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload r101_b32|r50_b8|...]
+
+Default workload: `r101_b32` = BASELINE.json configs[2] (ResNet-101 dota-1.0_r101_ms, 32 x 1024^2 on one B200), the
+configuration the north_star's targets are quoted on; under torchrun (WORLD_SIZE > 1) `r101_b16` = configs[3]
+(16 images per GPU, global batch 128 on 8 GPUs). The other names are alternates for profiles/.
 
 A "step" = one pass of the hot path (normalise -> ResNet+FPN -> head -> threshold/top-k/decode/rotated NMS) over one
 batch of synthetic 1024x1024x3 uint8 images. `value` = images/s with the inputs already resident in HBM; `e2e` = the
 same through the reference-facing C-ABI call with HOST buffers, `dafne_detect_host` in its pipelined form
 (`dafne_detect_host_begin` / `_end`, two batches in flight): H2D of every step's images and D2H of its detections are
 inside the timed region, the copy of step i+1 overlapping the compute of step i. Under torchrun every rank runs its own shard of the batch (weak scaling) and a
-step ends with ONE all-gather of the fixed-shape detections.
+step ends with ONE all-gather of the fixed-shape detection record (dafne_b200.distributed.gather_wire), straight from
+device memory in both legs.
 
 `--impl reference` times the reference's CPU implementation of the same path on the host cores. detectron2 / poly_nms
 cannot be installed here (no network), so that arm is the restated oracle (kind "port"): torch CPU fp32 ops +
@@ -32,6 +37,12 @@ WORKLOADS = {
     "r50_b8": ("configs/dota10_r50_1024.yaml", 8, 1024, 1024, "configs[1]: ResNet-50 + FPN DAFNe, batch 8x1024x1024"),
     "r101_b32": ("configs/dota10_r101_ms.yaml", 32, 1024, 1024, "configs[2]: ResNet-101 DAFNe dota-1.0_r101_ms, batch 32"),
     "r101_b16": ("configs/dota10_r101_ms.yaml", 16, 1024, 1024, "configs[3]: ResNet-101 DAFNe, 16 images per GPU"),
+    # SURVEY 8(d) worst case for the rotated NMS: the class bias is raised until the per-level top-k cap (2000) binds at
+    # p3, p4 and p5, so about 8-9 thousand boxes per image enter the NMS
+    "r101_b32_nmsmax": ("configs/dota10_r101_ms.yaml", 32, 1024, 1024,
+                        "configs[2] with the NMS worst case of SURVEY 8(d): top-k cap binding at p3/p4/p5"),
+    "r50_b8_nmsmax": ("configs/dota10_r50_1024.yaml", 8, 1024, 1024,
+                      "configs[1] with the NMS worst case of SURVEY 8(d): top-k cap binding at p3/p4/p5"),
     "hrsc_r50_b8": ("configs/hrsc_r50_ms.yaml", 8, 1024, 1024, "configs[4] (single size): HRSC r50_ms, batch 8"),
     # configs[4] as the reference runs it: images of 512^2 / 800^2 / 1024^2 in ONE batch, zero-padded to the largest
     # (ImageList.from_tensors) -- the padded area is computed like the reference computes it, images/s counts images
@@ -49,9 +60,14 @@ MIXED_SIZES = [(512, 512), (800, 800), (1024, 1024)]
 HRSC_SYNTH = dict(cls_bias=-2.9, base_quad=(-4.0, -0.5, 4.0, -0.5, 4.0, 0.5, -4.0, 0.5))
 
 
+NMSMAX_CLS_BIAS = {"r101_b32_nmsmax": -4.6, "r50_b8_nmsmax": -2.6}  # calibrated: candidates per level in the bench line
+
+
 def synth_weights(workload, spec):
     from dafne_b200.weights import synthetic_state_dict
 
+    if workload in NMSMAX_CLS_BIAS:
+        return synthetic_state_dict(spec, 0, cls_bias=NMSMAX_CLS_BIAS[workload])
     return synthetic_state_dict(spec, 0, **(HRSC_SYNTH if workload.startswith("hrsc") else {}))
 GFLOP_PER_IMAGE = {"r50": 505.97, "r101": 661.13}  # BASELINE.md section 2 (C = 15, 1024^2)
 
@@ -144,12 +160,16 @@ class ClockSampler:
 
 
 def measured_peaks():
+    """(sustained bf16 TFLOP/s, burst bf16 TFLOP/s, HBM GB/s, where from). The tower kernels are timed per launch inside
+    a step that runs for tens of milliseconds under the power cap: `frac` is against the sustained peak, `frac_burst`
+    against the burst one -- both are reported."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return p.get("bf16_tflops_sustained", 1383.4), p.get("hbm_gbs", 6555.5), "measured (MEASURED_PEAKS.json, sustained)"
-    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return (p.get("bf16_tflops_sustained", 1383.4), p.get("bf16_tflops", 1651.8), p.get("hbm_gbs", 6555.5),
+                "measured (MEASURED_PEAKS.json)")
+    return 1400.0, 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
@@ -178,8 +198,6 @@ def run_reference(args):
         return 0
     import torch
 
-    from dafne_b200.weights import synthetic_state_dict
-
     cfg, spec, batch, H, W, what = load_spec(args.workload)
     cores = os.cpu_count() or 1
     sd = synth_weights(args.workload, spec)
@@ -196,7 +214,12 @@ def run_reference(args):
         "impl": "reference", "metric": "images_per_sec_1024x1024", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "what": what, "per_step": "1 image (bounded sample of the batch)"},
+        # the same workload as the GPU arm's line; a step of this arm is a bounded SAMPLE of it (one image of the batch),
+        # images/s is per image either way
+        "config": {"workload": args.workload, "what": what, "per_gpu_batch": batch, "global_batch": batch,
+                   "image": [3, H, W], "resnet_depth": spec.resnet_depth, "num_classes": spec.num_classes,
+                   "weights": "seeded random init (dafne_b200.weights.synthetic_state_dict)",
+                   "parallelism": f"{cores} host threads", "per_step": "1 image (bounded sample of the batch)"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} x 1 image 1024x1024, restated reference (torch CPU fp32 + C polygon NMS)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -221,8 +244,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from dafne_b200.engine import DET, DafneEngine
-    from dafne_b200.weights import synthetic_state_dict
+    from dafne_b200.distributed import gather_wire
+    from dafne_b200.engine import DET, DafneEngine, DetectionWire
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -262,20 +285,25 @@ def run_ours(args):
         # two result buffers: the reference-facing host call is used in its pipelined form (two batches in flight)
         bk["host_dets"] = [torch.empty(b, cap, DET, dtype=torch.float32).pin_memory() for _ in range(2)]
         bk["host_counts"] = [torch.empty(b, dtype=torch.int32).pin_memory() for _ in range(2)]
+        # the step's result record, allocated once: detections + counts in ONE buffer (no per-step allocation, and
+        # what a rank contributes to the all-gather)
+        bk["wire"] = DetectionWire(b, cap, dev)
         if world > 1:
-            bk["gathered"] = torch.empty(world * b, cap, DET, dtype=torch.float32, device=dev)
-            bk["gathered_counts"] = torch.empty(world * b, dtype=torch.int32, device=dev)
+            n_wire = bk["wire"].buf.numel()
+            bk["gathered"] = [torch.empty(world, n_wire, dtype=torch.int32, device=dev) for _ in range(2)]
+            bk["gathered_host"] = [torch.empty(world, n_wire, dtype=torch.int32).pin_memory() for _ in range(2)]
         buckets.append(bk)
     eng = buckets[-1]["eng"]  # the largest shape: per-launch profile and roofline
     sizes, host_sets, dev_sets = buckets[-1]["sizes"], buckets[-1]["host_sets"], buckets[-1]["dev_sets"]
 
+    side = torch.cuda.Stream(device=dev) if world > 1 else None  # D2H of the gathered record (e2e leg)
+
     def step_device(i):
         out = None
         for bk in buckets:
-            dets, counts = bk["eng"].detect(bk["dev_sets"][i % n_sets], bk["sizes"], None, True, cap)
-            if world > 1:  # the path's one exchange: fixed-shape detections of every rank
-                dist.all_gather_into_tensor(bk["gathered"], dets)
-                dist.all_gather_into_tensor(bk["gathered_counts"], counts)
+            dets, counts = bk["eng"].detect(bk["dev_sets"][i % n_sets], bk["sizes"], None, True, cap, out=bk["wire"])
+            if world > 1:  # the path's one exchange: ONE all-gather of every rank's fixed-shape record
+                gather_wire(bk["wire"].buf, bk["batch"], cap, DET, out=bk["gathered"][0])
             out = (dets, counts)
         return out
 
@@ -289,6 +317,14 @@ def run_ours(args):
                 k = i % 2
                 t = bk["eng"].detect_host_begin(bk["host_sets"][i % n_sets], bk["sizes"], None, bk["host_dets"][k],
                                                 bk["host_counts"][k], cap)
+                if world > 1:
+                    # the exchange reads the batch's record where the kernels left it (device memory, compute stream,
+                    # right behind the last kernel); every rank then reads the gathered record back on a side stream
+                    torch.cuda.current_stream().wait_stream(side)  # gathered[k] of two steps ago has been read out
+                    gather_wire(bk["eng"].slot_wire(t), bk["batch"], cap, DET, out=bk["gathered"][k])
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        bk["gathered_host"][k].copy_(bk["gathered"][k], non_blocking=True)
                 if prev is not None:
                     finish_host(*prev)
                 prev = (bk, t, k)
@@ -296,14 +332,11 @@ def run_ours(args):
 
     def finish_host(bk, ticket, k):
         bk["eng"].detect_host_end(ticket)  # detections of that batch are now in host_dets[k] / host_counts[k]
-        if world > 1:
-            dist.all_gather_into_tensor(bk["gathered"], bk["host_dets"][k].to(dev, non_blocking=True))
-            dist.all_gather_into_tensor(bk["gathered_counts"], bk["host_counts"][k].to(dev, non_blocking=True))
 
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        torch.cuda.synchronize()  # all streams of the device, the side stream included
 
     def timed(fn, steps, whole_loop=False):
         barrier()
@@ -347,7 +380,7 @@ def run_ours(args):
     prof = eng.profile_forward(dev_sets[0], sizes)
     dom = [o for o in prof if o["kind"] == 1 and o["block_n"] == 256 and o["ksize"] == 3 and o["cin"] == 256
            and o["cout"] == 256 and o["stride"] == 1 and "tower" in o["name"]]
-    peak_tf, peak_hbm, peak_src = measured_peaks()
+    peak_tf, peak_burst, peak_hbm, peak_src = measured_peaks()
     dom_ms = sum(o["ms"] for o in dom)
     dom_fl = sum(o["flops"] for o in dom)
     total_ms = sum(o["ms"] for o in prof)
@@ -377,7 +410,8 @@ def run_ours(args):
                 "image": [3, H, W], "batches_per_step": [[b, 3, h, w] for b, h, w in shapes], "resnet_depth": spec.resnet_depth, "num_classes": spec.num_classes,
                 "weights": "seeded random init (dafne_b200.weights.synthetic_state_dict"
                            + (", HRSC stress recipe)" if args.workload.startswith("hrsc") else ")"),
-                "parallelism": f"batch-sharded x{world}, one all-gather of detections" if world > 1 else "single GPU",
+                "parallelism": f"batch-sharded x{world}, ONE all-gather of the detection record per step (both legs, "
+                               f"from device memory)" if world > 1 else "single GPU",
                 "l2": f"{n_sets} distinct input sets ({n_sets * step_bytes / 2**20:.0f} MiB) rotate; "
                       f"activation workspace {eng.workspace_bytes / 2**20:.0f} MiB >> 126 MiB L2",
                 "detections_per_image": det_counts[:8],
@@ -390,12 +424,18 @@ def run_ours(args):
             },
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": step_bytes,
-                    "d2h_bytes_per_step": batch * cap * DET * 4 + batch * 4, "ms_per_step": ms_host / args.steps},
+                    "d2h_bytes_per_step": (batch * cap * DET * 4 + batch * 4) * (1 + (world if world > 1 else 0)),
+                    "ms_per_step": ms_host / args.steps,
+                    "what": "dafne_detect_host_begin/_end with pinned host buffers, per rank: H2D of the step's images, "
+                            "D2H of its detections" + ("; the gathered record of all ranks is read back too"
+                                                       if world > 1 else "")},
             "gpu_launches": launches,
             "roofline": {
                 "kernel": "conv_tc_kernel<256> (head tower 3x3 256->256 convs, all levels)", "bound": "tensor",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                "peak_source": peak_src, "launches": len(dom), "ms_in_step": dom_ms,
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "peak_burst": peak_burst, "frac_burst": achieved / peak_burst, "traffic": traffic,
+                "peak_source": peak_src + ": `peak` = sustained bf16 (the kernel is timed inside a long power-capped "
+                               "step), `peak_burst` = burst bf16", "launches": len(dom), "ms_in_step": dom_ms,
                 "share_of_forward": dom_ms / total_ms if total_ms else None,
                 "all_convs": {"achieved": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0,
                               "ms": conv_ms, "forward_ms_sum_of_launches": total_ms},
@@ -432,12 +472,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="r50_b8", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: r101_b32 (configs[2]); r101_b16 (configs[3]) when WORLD_SIZE > 1")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--cpu-images", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="")
     args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "r101_b16" if int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.gpus > 1 else "r101_b32"
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -88,6 +88,7 @@ _SIGNATURES = {
     "dafne_detect_host_begin": (_i, [_vp, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _i, _vp,
                                      C.POINTER(_i)]),
     "dafne_detect_host_end": (_i, [_vp, _i]),
+    "dafne_host_slot_wire": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(C.c_size_t), C.POINTER(_i)]),
     "dafne_voc_match_f64_host": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int32), _i, C.POINTER(C.c_double),
                                       C.POINTER(C.c_int32), _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "dafne_resize_bilinear_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),

@@ -17,12 +17,12 @@ using namespace dafne;
 
 namespace {
 int num_sms_cached() {
-    static int sms = 0;
+    static DeviceOnce cached;
+    int dev = 0;
+    int sms = cached.get(&dev);
     if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cached.set(dev, sms);
     }
     return sms;
 }
@@ -288,10 +288,13 @@ int dafne_detect_host_begin(dafne_ctx* ctx, const void* host_images, int dtype, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     void* img = k == 0 ? ctx->images_dev : ctx->images_dev2;
     float* dets = k == 0 ? ctx->dets_dev : ctx->dets_dev2;
-    int32_t* counts = k == 0 ? ctx->counts_dev : ctx->counts_dev2;
     const size_t esz = dtype == 0 ? 1 : 4;
     const size_t bytes = static_cast<size_t>(ctx->N) * 3 * ctx->H * ctx->W * esz;
     if (capacity > ctx->dets_capacity) capacity = ctx->dets_capacity;
+    // the counts of a slot sit right behind its [N][capacity][20] detections: one contiguous "wire" record that a
+    // multi-GPU caller can all-gather in ONE collective straight from device memory (dafne_host_slot_wire)
+    int32_t* counts = reinterpret_cast<int32_t*>(dets + static_cast<size_t>(ctx->N) * capacity * DAFNE_DET_STRIDE);
+    ctx->slot_capacity[k] = capacity;
     // H2D on the copy stream, once the batch that last read this staging buffer has been computed
     if (ctx->slot_used[k]) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute[k], 0);
     if (e == cudaSuccess) e = cudaMemcpyAsync(img, host_images, bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
@@ -321,6 +324,19 @@ int dafne_detect_host_begin(dafne_ctx* ctx, const void* host_images, int dtype, 
     ctx->slot_used[k] = true;
     ctx->slot_next++;
     *ticket = k;
+    return 0;
+}
+
+int dafne_host_slot_wire(dafne_ctx* ctx, int ticket, const void** dev_wire, size_t* bytes, int* capacity) {
+    NEED_CTX(ctx, "dafne_host_slot_wire");
+    if (ticket < 0 || ticket > 1 || !ctx->slot_used[ticket] || !dev_wire || !bytes) {
+        set_error("dafne_host_slot_wire: ticket %d was never issued (or null output pointer)", ticket);
+        return -1;
+    }
+    const int cap = ctx->slot_capacity[ticket];
+    *dev_wire = ticket == 0 ? ctx->dets_dev : ctx->dets_dev2;
+    *bytes = static_cast<size_t>(ctx->N) * cap * DAFNE_DET_STRIDE * 4 + static_cast<size_t>(ctx->N) * 4;
+    if (capacity) *capacity = cap;
     return 0;
 }
 

@@ -970,8 +970,9 @@ template <int BN, int WGS, int MODE>
 static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, int grid, int res_tma, int row_shared,
                      int breg, cudaStream_t stream) {
     using Cfg = ConvCfg<BN, WGS>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    int dev;
+    if (!configured.get(&dev)) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, WGS, MODE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) {
@@ -979,7 +980,7 @@ static int launch_bn(const ConvProblem* dev_probs, int nprob, int total_tiles, i
                       cudaGetErrorString(e));
             return -1;
         }
-        configured = true;
+        configured.set(dev, 1);
     }
     int stages, ring;
     conv_smem_config<BN, WGS>(res_tma, row_shared, breg, MODE, &stages, &ring);

@@ -7,6 +7,21 @@
 
 namespace dafne {
 
+// Function attributes (opt-in dynamic shared memory) and occupancy are PER DEVICE: a process that creates contexts on
+// several GPUs must configure each kernel on each of them. `slot` is a function-local `static DeviceOnce`.
+struct DeviceOnce {
+    static constexpr int kMaxDevices = 64;
+    int value[kMaxDevices] = {};  // 0 = not configured on that device yet; otherwise the cached value (>= 1)
+    // current device's cached value, or 0 (then the caller configures and calls set())
+    int get(int* dev_out) const {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+        *dev_out = dev;
+        return value[dev];
+    }
+    void set(int dev, int v) { value[dev] = v; }
+};
+
 // What one convolution launch computes. Activations are NHWC fp16; weights are packed
 // [Cout][tap][Cin] fp16 (tap = ky*k+kx); the epilogue is out = relu?(acc*scale + shift (+ residual)).
 struct ConvDesc {

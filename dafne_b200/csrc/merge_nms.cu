@@ -17,6 +17,7 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "conv_tc.cuh"  // set_error
@@ -105,6 +106,41 @@ __global__ void __launch_bounds__(32) merge_sweep_kernel(const MergeProblem* __r
         }                                                                                  \
     } while (0)
 
+// Device scratch of the host-facing calls below: ONE grow-only allocation per device, kept for the life of the process
+// and carved up per call -- in steady state these calls allocate nothing (the external poly_nms they stand in for does a
+// cudaMalloc / cudaFree pair per buffer and call). Calls on the same device are serialised by the pool's mutex (they
+// are synchronous anyway: host pointers in, host pointers out).
+namespace {
+struct HostCallPool {
+    std::mutex mu;
+    void* base[64] = {};
+    size_t cap[64] = {};
+    // returns nullptr (with the error set) on failure; `bytes` may be 0
+    uint8_t* reserve(int device, size_t bytes) {
+        if (device < 0 || device >= 64) {
+            dafne::set_error("host call: device id %d out of range", device);
+            return nullptr;
+        }
+        if (bytes > cap[device]) {
+            if (base[device]) cudaFree(base[device]);
+            base[device] = nullptr;
+            cap[device] = 0;
+            const size_t want = bytes + bytes / 4 + (1u << 20);
+            cudaError_t e = cudaMalloc(&base[device], want);
+            if (e != cudaSuccess) {
+                dafne::set_error("host call: cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+                return nullptr;
+            }
+            cap[device] = want;
+        }
+        return static_cast<uint8_t*>(base[device]);
+    }
+};
+HostCallPool g_pool;
+inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+}  // namespace
+
+
 int merge_nms_f64_batch_host(const double* dets, const int* offsets, int nproblems, double thresh, int device,
                              int* keep_out, int* nkeep_out) {
     if (nproblems <= 0) return 0;
@@ -184,13 +220,23 @@ int merge_nms_f64_batch_host(const double* dets, const int* offsets, int nproble
     u64* d_mask = nullptr;
     int *d_keep = nullptr, *d_nkeep = nullptr;
     std::vector<int> keep_sorted(total);
+    std::lock_guard<std::mutex> lock(g_pool.mu);
     MERGE_CUDA(cudaSetDevice(device));
-    MERGE_CUDA(cudaMalloc(&d_rec, rec.size() * sizeof(double)));
-    MERGE_CUDA(cudaMalloc(&d_tiles, tiles.size() * sizeof(MergeTile)));
-    MERGE_CUDA(cudaMalloc(&d_probs, probs.size() * sizeof(MergeProblem)));
-    MERGE_CUDA(cudaMalloc(&d_mask, std::max<long long>(mask_words, 1) * 8));
-    MERGE_CUDA(cudaMalloc(&d_keep, static_cast<size_t>(total) * sizeof(int)));
-    MERGE_CUDA(cudaMalloc(&d_nkeep, static_cast<size_t>(nproblems) * sizeof(int)));
+    {
+        const size_t b_rec = up256(rec.size() * sizeof(double)), b_tiles = up256(tiles.size() * sizeof(MergeTile)),
+                     b_probs = up256(probs.size() * sizeof(MergeProblem)),
+                     b_mask = up256(static_cast<size_t>(std::max<long long>(mask_words, 1)) * 8),
+                     b_keep = up256(static_cast<size_t>(total) * sizeof(int)),
+                     b_nkeep = up256(static_cast<size_t>(nproblems) * sizeof(int));
+        uint8_t* pool = g_pool.reserve(device, b_rec + b_tiles + b_probs + b_mask + b_keep + b_nkeep);
+        if (!pool) return -1;
+        d_rec = reinterpret_cast<double*>(pool);
+        d_tiles = reinterpret_cast<MergeTile*>(pool + b_rec);
+        d_probs = reinterpret_cast<MergeProblem*>(pool + b_rec + b_tiles);
+        d_mask = reinterpret_cast<u64*>(pool + b_rec + b_tiles + b_probs);
+        d_keep = reinterpret_cast<int*>(pool + b_rec + b_tiles + b_probs + b_mask);
+        d_nkeep = reinterpret_cast<int*>(pool + b_rec + b_tiles + b_probs + b_mask + b_keep);
+    }
     MERGE_CUDA(cudaMemcpy(d_rec, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
     MERGE_CUDA(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(MergeTile), cudaMemcpyHostToDevice));
     MERGE_CUDA(cudaMemcpy(d_probs, probs.data(), probs.size() * sizeof(MergeProblem), cudaMemcpyHostToDevice));
@@ -214,12 +260,6 @@ int merge_nms_f64_batch_host(const double* dets, const int* offsets, int nproble
         for (int k = 0; k < nkeep_out[p]; ++k) keep_out[b + k] = order[b + keep_sorted[b + k]];
     }
 done:
-    cudaFree(d_rec);
-    cudaFree(d_tiles);
-    cudaFree(d_probs);
-    cudaFree(d_mask);
-    cudaFree(d_keep);
-    cudaFree(d_nkeep);
     return rc;
 }
 
@@ -295,13 +335,21 @@ int voc_match_f64_host(const double* dets, const int* det_image, int nd, const d
     int rc = 0;
     double *d_dets = nullptr, *d_gts = nullptr, *d_ov = nullptr;
     int *d_img = nullptr, *d_off = nullptr, *d_j = nullptr;
+    std::lock_guard<std::mutex> lock(g_pool.mu);
     MERGE_CUDA(cudaSetDevice(device));
-    MERGE_CUDA(cudaMalloc(&d_dets, static_cast<size_t>(nd) * 64));
-    MERGE_CUDA(cudaMalloc(&d_gts, static_cast<size_t>(ng > 0 ? ng : 1) * 64));
-    MERGE_CUDA(cudaMalloc(&d_ov, static_cast<size_t>(nd) * 8));
-    MERGE_CUDA(cudaMalloc(&d_img, static_cast<size_t>(nd) * 4));
-    MERGE_CUDA(cudaMalloc(&d_off, static_cast<size_t>(nimages + 1) * 4));
-    MERGE_CUDA(cudaMalloc(&d_j, static_cast<size_t>(nd) * 4));
+    {
+        const size_t b_dets = up256(static_cast<size_t>(nd) * 64), b_gts = up256(static_cast<size_t>(ng > 0 ? ng : 1) * 64),
+                     b_ov = up256(static_cast<size_t>(nd) * 8), b_img = up256(static_cast<size_t>(nd) * 4),
+                     b_off = up256(static_cast<size_t>(nimages + 1) * 4), b_j = up256(static_cast<size_t>(nd) * 4);
+        uint8_t* pool = g_pool.reserve(device, b_dets + b_gts + b_ov + b_img + b_off + b_j);
+        if (!pool) return -1;
+        d_dets = reinterpret_cast<double*>(pool);
+        d_gts = reinterpret_cast<double*>(pool + b_dets);
+        d_ov = reinterpret_cast<double*>(pool + b_dets + b_gts);
+        d_img = reinterpret_cast<int*>(pool + b_dets + b_gts + b_ov);
+        d_off = reinterpret_cast<int*>(pool + b_dets + b_gts + b_ov + b_img);
+        d_j = reinterpret_cast<int*>(pool + b_dets + b_gts + b_ov + b_img + b_off);
+    }
     MERGE_CUDA(cudaMemcpy(d_dets, dets, static_cast<size_t>(nd) * 64, cudaMemcpyHostToDevice));
     if (ng > 0) MERGE_CUDA(cudaMemcpy(d_gts, gts, static_cast<size_t>(ng) * 64, cudaMemcpyHostToDevice));
     MERGE_CUDA(cudaMemcpy(d_img, det_image, static_cast<size_t>(nd) * 4, cudaMemcpyHostToDevice));
@@ -311,12 +359,6 @@ int voc_match_f64_host(const double* dets, const int* det_image, int nd, const d
     MERGE_CUDA(cudaMemcpy(ovmax_out, d_ov, static_cast<size_t>(nd) * 8, cudaMemcpyDeviceToHost));
     MERGE_CUDA(cudaMemcpy(jmax_out, d_j, static_cast<size_t>(nd) * 4, cudaMemcpyDeviceToHost));
 done:
-    cudaFree(d_dets);
-    cudaFree(d_gts);
-    cudaFree(d_ov);
-    cudaFree(d_img);
-    cudaFree(d_off);
-    cudaFree(d_j);
     return rc;
 }
 

@@ -493,6 +493,16 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
         return -1;
     }
     CUDA_OK(cudaSetDevice(c->device));
+    if (base && (c->slot_pending[0] || c->slot_pending[1])) {
+        set_error("bind_workspace: a pipelined batch is still in flight (call dafne_detect_host_end first)");
+        return -1;
+    }
+    if (base && c->copy_stream) {
+        // copies of an earlier plan may still be running on the context's private streams: they must not outlive the
+        // workspace they read / write
+        CUDA_OK(cudaStreamSynchronize(c->copy_stream));
+        CUDA_OK(cudaStreamSynchronize(c->d2h_stream));
+    }
     Builder B;
     B.c = c;
     B.base = base;
@@ -540,10 +550,12 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     const size_t img_bytes = static_cast<size_t>(N) * 3 * H * W * sizeof(float);
     void* images_dev = B.persistent<uint8_t>(img_bytes);
     const int det_cap = 2048;
-    float* dets_dev = B.persistent<float>(static_cast<size_t>(N) * det_cap * DAFNE_DET_STRIDE * sizeof(float));
+    // + N int32: the pipelined host call keeps a slot's counts right behind its detections (dafne_host_slot_wire)
+    const size_t dets_bytes = static_cast<size_t>(N) * det_cap * DAFNE_DET_STRIDE * sizeof(float) + static_cast<size_t>(N) * 4;
+    float* dets_dev = B.persistent<float>(dets_bytes);
     int32_t* counts_dev = B.persistent<int32_t>(static_cast<size_t>(N) * sizeof(int32_t));
     void* images_dev2 = B.persistent<uint8_t>(img_bytes);
-    float* dets_dev2 = B.persistent<float>(static_cast<size_t>(N) * det_cap * DAFNE_DET_STRIDE * sizeof(float));
+    float* dets_dev2 = B.persistent<float>(dets_bytes);
     int32_t* counts_dev2 = B.persistent<int32_t>(static_cast<size_t>(N) * sizeof(int32_t));
 
     // ---- stem (tensor cores; the preprocess kernel writes the zero-bordered NHWC4 canvas it reads)

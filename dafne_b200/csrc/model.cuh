@@ -108,6 +108,7 @@ struct dafne_ctx {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_result[2] = {nullptr, nullptr};
     bool slot_pending[2] = {false, false};
     bool slot_used[2] = {false, false};
+    int slot_capacity[2] = {0, 0};  // rows per image of the slot's wire record (detections, then counts)
     unsigned slot_next = 0;
     dafne::HeadOut head_out[DAFNE_MAX_LEVELS][3];
     void* post_scratch = nullptr;

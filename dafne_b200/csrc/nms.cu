@@ -503,11 +503,12 @@ int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float th
     u64* stats = reinterpret_cast<u64*>(b + y.o_stats);
     int* work = reinterpret_cast<int*>(b + y.o_work);
     const int groups = (N + kBcastImages - 1) / kBcastImages;
-    static int bcast_ctas = 0;  // resident CTAs of the broadcast kernel on this device
+    static DeviceOnce bcast_ctas_of;  // resident CTAs of the broadcast kernel, per device
+    int dev = 0;
+    int bcast_ctas = bcast_ctas_of.get(&dev);
     if (bcast_ctas == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaError_t q = cudaGetDevice(&dev);
-        if (q == cudaSuccess) q = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int sms = 0, per_sm = 0;
+        cudaError_t q = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (q == cudaSuccess)
             q = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_bcast_kernel, kBcastThreads, 0);
         if (q != cudaSuccess || sms <= 0 || per_sm <= 0) {
@@ -515,6 +516,7 @@ int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float th
             return -1;
         }
         bcast_ctas = sms * per_sm;
+        bcast_ctas_of.set(dev, bcast_ctas);
     }
     // removed | pk | ctr | stats | work are contiguous: one clear
     cudaError_t e = cudaMemsetAsync(removed, 0, y.o_diag - y.o_removed, s);

@@ -613,15 +613,14 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalArgs a) {
             hb[1] = h[1];
             hb[2] = h[2];
             hb[3] = h[3];
-            ok = true;
-            if (a.do_postprocess) {
-                // Boxes.scale, Boxes.clip(output size), Boxes.nonempty()   (detectron2 detector_postprocess)
-                hb[0] = fminf(fmaxf(hb[0] * sx, 0.f), ow);
-                hb[2] = fminf(fmaxf(hb[2] * sx, 0.f), ow);
-                hb[1] = fminf(fmaxf(hb[1] * sy, 0.f), oh);
-                hb[3] = fminf(fmaxf(hb[3] * sy, 0.f), oh);
-                ok = (hb[2] - hb[0]) > 0.f && (hb[3] - hb[1]) > 0.f;
-            }
+            // Boxes.scale, Boxes.clip(output size), Boxes.nonempty(): detectron2's ProposalNetwork.forward runs
+            // detector_postprocess on every result, whatever OneStageDetector.forward's do_postprocess says -- that
+            // flag only gates the corner / location rescale below (one_stage_detector.py:45-55, 78-98)
+            hb[0] = fminf(fmaxf(hb[0] * sx, 0.f), ow);
+            hb[2] = fminf(fmaxf(hb[2] * sx, 0.f), ow);
+            hb[1] = fminf(fmaxf(hb[1] * sy, 0.f), oh);
+            hb[3] = fminf(fmaxf(hb[3] * sy, 0.f), oh);
+            ok = (hb[2] - hb[0]) > 0.f && (hb[3] - hb[1]) > 0.f;
         }
         // block-wide exclusive scan of ok
         __shared__ int s_warp[32];
@@ -668,6 +667,12 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalArgs a) {
         __syncthreads();
     }
     if (threadIdx.x == 0) a.counts[n] = s_out;
+    // rows past the last detection are zero: the output is a fixed-shape wire record (one all-gather per batch,
+    // dafne_b200/distributed.py) and the caller never has to clear it
+    const int used = min(s_out, a.capacity);
+    float4* z = reinterpret_cast<float4*>(out + static_cast<size_t>(used) * kDet);  // kDet * 4 B = 80 B rows: 16-B aligned
+    const int nz = (a.capacity - used) * (kDet / 4);
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ================================================================================================ host orchestration
@@ -774,15 +779,16 @@ int launch_postprocess(const PostParams& p, cudaStream_t s, int64_t* launches) {
         a.canon = canon;
         a.minmax = reinterpret_cast<unsigned*>(cand_cnt);
         const size_t smem = static_cast<size_t>(y.max_sel) * 8;
-        static size_t configured = 0;
-        if (smem > configured) {
+        static DeviceOnce configured;  // largest size configured so far, per device
+        int dev_rd;
+        if (static_cast<int>(smem) > configured.get(&dev_rd)) {
             e = cudaFuncSetAttribute(rank_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem));
             if (e != cudaSuccess) {
                 set_error("rank_decode_kernel smem attribute (%zu): %s", smem, cudaGetErrorString(e));
                 return -1;
             }
-            configured = smem;
+            configured.set(dev_rd, static_cast<int>(smem));
         }
         const dim3 grid((y.max_sel + kRankRows - 1) / kRankRows, p.N);
         rank_decode_kernel<<<grid, kRankRows, smem, s>>>(a);
@@ -1039,15 +1045,16 @@ int launch_poly_nms(const float* polys, const float* scores, const int32_t* clas
         int np2 = 1;
         while (np2 < n) np2 <<= 1;
         const size_t smem = static_cast<size_t>(np2) * 8;
-        static size_t configured = 0;
-        if (smem > configured) {
+        static DeviceOnce configured;
+        int dev_np;
+        if (static_cast<int>(smem) > configured.get(&dev_np)) {
             cudaError_t e = cudaFuncSetAttribute(nms_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  static_cast<int>(smem));
             if (e != cudaSuccess) {
                 set_error("nms_prepare_kernel smem attribute: %s", cudaGetErrorString(e));
                 return -1;
             }
-            configured = smem;
+            configured.set(dev_np, static_cast<int>(smem));
         }
         nms_prepare_kernel<<<1, 1024, smem, s>>>(polys, scores, classes, n, vehicle_merge, nmsbox, order, count);
         POST_CHECK_LAUNCH("nms_prepare_kernel");
@@ -1056,15 +1063,16 @@ int launch_poly_nms(const float* polys, const float* scores, const int32_t* clas
         b += a256(ms * 8);
         unsigned long long* keys_b = reinterpret_cast<unsigned long long*>(b);
         const size_t smem = static_cast<size_t>(kMaxSorted) * 8;
-        static bool configured_chunk = false;
-        if (!configured_chunk) {
+        static DeviceOnce configured_chunk;
+        int dev_chunk;
+        if (!configured_chunk.get(&dev_chunk)) {
             cudaError_t e = cudaFuncSetAttribute(nms_sort_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  static_cast<int>(smem));
             if (e != cudaSuccess) {
                 set_error("nms_sort_chunk_kernel smem attribute: %s", cudaGetErrorString(e));
                 return -1;
             }
-            configured_chunk = true;
+            configured_chunk.set(dev_chunk, 1);
         }
         const int chunks = (n + kMaxSorted - 1) / kMaxSorted;
         nms_sort_chunk_kernel<<<chunks, 1024, smem, s>>>(scores, n, keys_a);

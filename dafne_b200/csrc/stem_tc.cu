@@ -357,14 +357,15 @@ int stem_plan_build(const __half* canvas, int N, int H, int W, const __half* w_p
 }
 
 int stem_plan_launch(const StemPlan& pl, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    int dev;
+    if (!configured.get(&dev)) {
         cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(stem_tc_kernel): %s", cudaGetErrorString(e));
             return -1;
         }
-        configured = true;
+        configured.set(dev, 1);
     }
     stem_tc_kernel<<<pl.grid, kThreads, kSmemBytes, s>>>(pl.tmA, pl.tmB, pl.p);
     cudaError_t e = cudaGetLastError();

@@ -20,25 +20,26 @@ def shard_range(n_items: int, rank: int, world: int) -> range:
 
 
 def pack_wire(dets: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
-    """[B, cap, D] float32 detections + [B] int32 counts -> one [B, cap * D + 1] float32 buffer; the count rides in the
-    last element of its image's row as raw bits (a view, not a conversion), so the exchange is ONE collective."""
+    """[B, cap, D] float32 detections + [B] int32 counts -> one [B, cap * D + 1] int32 buffer (the detections as raw
+    bits: the wire is never typed as arithmetic data), so the exchange is ONE collective."""
     b = dets.shape[0]
-    wire = torch.empty(b, dets[0].numel() + 1, dtype=torch.float32, device=dets.device)
-    wire[:, :-1] = dets.reshape(b, -1)
-    wire[:, -1] = counts.to(torch.int32).view(torch.float32)
+    wire = torch.empty(b, dets[0].numel() + 1, dtype=torch.int32, device=dets.device)
+    wire[:, :-1] = dets.contiguous().view(torch.int32).reshape(b, -1)
+    wire[:, -1] = counts.to(torch.int32)
     return wire
 
 
 def unpack_wire(wire: torch.Tensor, det_shape) -> Tuple[torch.Tensor, torch.Tensor]:
     n = wire.shape[0]
-    dets = wire[:, :-1].reshape((n,) + tuple(det_shape))
-    counts = wire[:, -1].contiguous().view(torch.int32)
+    dets = wire[:, :-1].contiguous().view(torch.float32).reshape((n,) + tuple(det_shape))
+    counts = wire[:, -1].contiguous()
     return dets, counts
 
 
 def gather_detections(dets: torch.Tensor, counts: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """All-gather [B_local, cap, 20] detections and [B_local] counts -> ([world*B_local, cap, 20], [world*B_local]),
-    rank-major: exactly one all-gather, issued on the current stream (NCCL) right after the last kernel."""
+    rank-major: exactly one all-gather, issued on the current stream (NCCL) right after the last kernel.
+    Generic form (packs a wire buffer); a caller that holds its results in a DetectionWire uses gather_wire()."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return dets, counts
     world = dist.get_world_size(group)
@@ -51,6 +52,29 @@ def gather_detections(dets: torch.Tensor, counts: torch.Tensor, group=None) -> T
         dist.all_gather(parts, wire, group=group)
         out = torch.cat(parts, 0)
     return unpack_wire(out, dets.shape[1:])
+
+
+def gather_wire(wire: torch.Tensor, n_local: int, cap: int, det_stride: int, out: torch.Tensor = None, group=None):
+    """The path's one exchange with no packing and no allocation: `wire` is a rank's result record (int32
+    [n_local * cap * det_stride + n_local]: detections, then counts -- engine.DetectionWire.buf or
+    DafneEngine.slot_wire(ticket)), `out` an int32 [world, len(wire)] buffer. ONE all_gather_into_tensor on the current
+    stream; returns views (dets [world, n_local, cap, det_stride] float32, counts [world, n_local] int32) of `out`."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    nd = n_local * cap * det_stride
+    assert wire.dtype == torch.int32 and wire.numel() == nd + n_local
+    if out is None:
+        out = torch.empty(world, wire.numel(), dtype=torch.int32, device=wire.device)
+    if world == 1:
+        out[0].copy_(wire)
+    elif dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, wire, group=group)
+    else:
+        parts = [torch.empty_like(wire) for _ in range(world)]
+        dist.all_gather(parts, wire, group=group)
+        out.copy_(torch.stack(parts, 0))
+    dets = out[:, :nd].view(torch.float32).view(world, n_local, cap, det_stride)
+    counts = out[:, nd:]
+    return dets, counts
 
 
 def pad_shard(items: Sequence, per_rank: int, filler):
@@ -81,8 +105,9 @@ def detect_sharded(engine, images: torch.Tensor, image_sizes: Sequence[Tuple[int
             osz = osz + [(output_sizes[0] if len(r) == 0 else osz[-1])] * pad
     dets, counts = engine.detect(local.contiguous(), sizes, osz, True, capacity)
     dets, counts = gather_detections(dets, counts, group)
-    return dets[:n] if world * per == n else _drop_padding(dets, counts, n, per, world)[0], \
-        counts[:n] if world * per == n else _drop_padding(dets, counts, n, per, world)[1]
+    if world * per == n:
+        return dets[:n], counts[:n]
+    return _drop_padding(dets, counts, n, per, world)
 
 
 def _drop_padding(dets, counts, n, per, world):

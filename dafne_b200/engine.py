@@ -16,6 +16,26 @@ from .spec import ModelSpec
 DET = _capi.DET_STRIDE
 
 
+class DetectionWire:
+    """The fixed-shape result record of one batch in ONE device buffer: [N][cap][DET] float32 detections immediately
+    followed by [N] int32 counts (typed int32: the payload is never arithmetic data). `dets` / `counts` are views.
+    It is what a rank contributes to the all-gather of a multi-GPU step (dafne_b200/distributed.py::gather_wire), and
+    a caller that keeps one across steps has no per-step allocation: the kernels write every element (rows past the
+    last detection are zero-filled by the finalize kernel)."""
+
+    def __init__(self, N: int, cap: int, device):
+        self.N, self.cap = int(N), int(cap)
+        self.buf = torch.empty(self.N * self.cap * DET + self.N, dtype=torch.int32, device=device)
+
+    @property
+    def dets(self) -> torch.Tensor:
+        return self.buf[: self.N * self.cap * DET].view(torch.float32).view(self.N, self.cap, DET)
+
+    @property
+    def counts(self) -> torch.Tensor:
+        return self.buf[self.N * self.cap * DET:]
+
+
 def _i32_array(values: Sequence[int]):
     arr = (C.c_int32 * len(values))(*[int(v) for v in values])
     return arr
@@ -36,6 +56,7 @@ class DafneEngine:
         self._ws: Optional[torch.Tensor] = None
         self._shape: Optional[Tuple[int, int, int]] = None
         self._weights_ready = False
+        self._in_flight: Dict[int, tuple] = {}  # ticket -> host tensors of a pipelined batch (kept alive until _end)
 
     def close(self) -> None:
         if getattr(self, "_ctx", None):
@@ -85,9 +106,16 @@ class DafneEngine:
             return
         if not self._weights_ready:
             raise _capi.DafneError("load_state_dict() must be called before running the model")
+        if self._in_flight:
+            raise _capi.DafneError("bind(): pipelined batches are still in flight (call detect_host_end first)")
         need = C.c_size_t()
         _capi.check(self.lib.dafne_workspace_bytes(self._ctx, N, H, W, C.byref(need)), "dafne_workspace_bytes")
         if self._ws is None or self._ws.numel() < need.value + 1024:
+            if self._ws is not None:
+                # the context's private copy streams are invisible to torch's caching allocator: nothing may still
+                # be running on the old workspace when its block goes back to the pool
+                with torch.cuda.device(self.device):
+                    torch.cuda.synchronize()
             self._ws = None
             self._ws = torch.empty(need.value + 1024, dtype=torch.uint8, device=self.device)
         base = (self._ws.data_ptr() + 1023) // 1024 * 1024
@@ -132,11 +160,17 @@ class DafneEngine:
         t = torch.as_tensor(_DeviceHalfs(p.value, n_el), device=self.device)
         return t.view(n.value, h.value, w.value, c.value).permute(0, 3, 1, 2).float().contiguous()
 
-    def postprocess(self, image_sizes, output_sizes=None, do_postprocess=True, capacity: Optional[int] = None):
+    def postprocess(self, image_sizes, output_sizes=None, do_postprocess=True, capacity: Optional[int] = None,
+                    out: Optional[DetectionWire] = None):
+        """-> (dets [N, cap, 20] fp32, counts [N] int32) on the device. `out`: a DetectionWire to write into (no
+        allocation in the call); otherwise fresh tensors are returned."""
         N = self._shape[0]
         cap = capacity or (self.spec.post_nms_topk + 64)
-        dets = torch.zeros(N, cap, DET, dtype=torch.float32, device=self.device)
-        counts = torch.zeros(N, dtype=torch.int32, device=self.device)
+        if out is None:
+            out = DetectionWire(N, cap, self.device)  # torch.empty: the kernels write every element
+        elif (out.N, out.cap) != (N, cap) or out.buf.device != self.device:
+            raise ValueError(f"DetectionWire is [{out.N}, {out.cap}] on {out.buf.device}, need [{N}, {cap}] on {self.device}")
+        dets, counts = out.dets, out.counts
         sizes = _i32_array([v for hw in image_sizes for v in hw])
         osz = _i32_array([v for hw in (output_sizes or image_sizes) for v in hw])
         _capi.check(self.lib.dafne_postprocess(self._ctx, sizes, osz, int(do_postprocess), dets.data_ptr(),
@@ -144,10 +178,26 @@ class DafneEngine:
         return dets, counts
 
     def detect(self, images: torch.Tensor, image_sizes, output_sizes=None, do_postprocess=True,
-               capacity: Optional[int] = None):
+               capacity: Optional[int] = None, out: Optional[DetectionWire] = None):
         """Device tensors in, device tensors out: dets [N, cap, 20] fp32, counts [N] int32. No host sync."""
         self.forward_dense(images, image_sizes)
-        return self.postprocess(image_sizes, output_sizes, do_postprocess, capacity)
+        return self.postprocess(image_sizes, output_sizes, do_postprocess, capacity, out)
+
+    def _check_host_buffers(self, host_images, host_dets, host_counts, N, cap):
+        """The C side copies N * cap * 20 floats packed at row stride `cap`, asynchronously: shapes must match
+        exactly, the tensors must be contiguous, and pinned (a pageable buffer would make the copies synchronous and
+        the pipelined form meaningless)."""
+        if tuple(host_dets.shape) != (N, cap, DET) or host_dets.dtype != torch.float32 or not host_dets.is_contiguous():
+            raise ValueError(f"host_dets must be a contiguous float32 [{N}, {cap}, {DET}] tensor, got "
+                             f"{tuple(host_dets.shape)} {host_dets.dtype}")
+        if tuple(host_counts.shape) != (N,) or host_counts.dtype != torch.int32 or not host_counts.is_contiguous():
+            raise ValueError(f"host_counts must be a contiguous int32 [{N}] tensor, got {tuple(host_counts.shape)}")
+        for name, t in (("host_images", host_images), ("host_dets", host_dets), ("host_counts", host_counts)):
+            if t.is_cuda or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous HOST tensor")
+        for name, t in (("host_dets", host_dets), ("host_counts", host_counts)):
+            if not t.is_pinned():
+                raise ValueError(f"{name} must be pinned host memory (tensor.pin_memory())")
 
     def detect_host(self, host_images: torch.Tensor, image_sizes, output_sizes=None, host_dets=None,
                     host_counts=None, capacity: Optional[int] = None):
@@ -159,6 +209,7 @@ class DafneEngine:
             host_dets = torch.empty(N, cap, DET, dtype=torch.float32).pin_memory()
         if host_counts is None:
             host_counts = torch.empty(N, dtype=torch.int32).pin_memory()
+        self._check_host_buffers(host_images, host_dets, host_counts, N, cap)
         dtype = {torch.uint8: 0, torch.float32: 1}[host_images.dtype]
         sizes = _i32_array([v for hw in image_sizes for v in hw])
         osz = _i32_array([v for hw in (output_sizes or image_sizes) for v in hw])
@@ -170,11 +221,12 @@ class DafneEngine:
     def detect_host_begin(self, host_images: torch.Tensor, image_sizes, output_sizes, host_dets: torch.Tensor,
                           host_counts: torch.Tensor, capacity: Optional[int] = None) -> int:
         """Pipelined detect_host: enqueue H2D (copy stream) + detect + D2H, return a ticket without synchronising.
-        Up to two batches in flight; `host_dets` / `host_counts` (pinned) are filled when detect_host_end returns."""
+        Up to two batches in flight; `host_dets` / `host_counts` (pinned) are filled when detect_host_end returns.
+        The engine keeps the host tensors referenced until then."""
         N, _, H, W = host_images.shape
         self.bind(N, H, W)
         cap = min(capacity or (self.spec.post_nms_topk + 64), 2048)
-        assert host_dets.shape[1] >= cap and host_dets.is_contiguous()
+        self._check_host_buffers(host_images, host_dets, host_counts, N, cap)
         dtype = {torch.uint8: 0, torch.float32: 1}[host_images.dtype]
         sizes = _i32_array([v for hw in image_sizes for v in hw])
         osz = _i32_array([v for hw in (output_sizes or image_sizes) for v in hw])
@@ -182,10 +234,21 @@ class DafneEngine:
         _capi.check(self.lib.dafne_detect_host_begin(self._ctx, host_images.data_ptr(), dtype, sizes, osz,
                                                      host_dets.data_ptr(), host_counts.data_ptr(), cap,
                                                      _capi.stream_ptr(), C.byref(ticket)), "dafne_detect_host_begin")
+        self._in_flight[ticket.value] = (host_images, host_dets, host_counts)
         return ticket.value
 
     def detect_host_end(self, ticket: int) -> None:
         _capi.check(self.lib.dafne_detect_host_end(self._ctx, int(ticket)), "dafne_detect_host_end")
+        self._in_flight.pop(int(ticket), None)
+
+    def slot_wire(self, ticket: int) -> torch.Tensor:
+        """Zero-copy int32 view of the DEVICE result record of a pipelined batch (detections, then counts -- the layout
+        of DetectionWire.buf), valid in stream order after detect_host_begin(ticket): what a multi-GPU step
+        all-gathers, with no host bounce."""
+        p, nbytes, cap = C.c_void_p(), C.c_size_t(), C.c_int()
+        _capi.check(self.lib.dafne_host_slot_wire(self._ctx, int(ticket), C.byref(p), C.byref(nbytes), C.byref(cap)),
+                    "dafne_host_slot_wire")
+        return torch.as_tensor(_DeviceInts(p.value, nbytes.value // 4), device=self.device)
 
     def postprocess_external(self, logits: List[torch.Tensor], reg: List[torch.Tensor], ctr: List[torch.Tensor],
                              image_sizes, output_sizes=None, do_postprocess=True, capacity: Optional[int] = None):
@@ -209,8 +272,8 @@ class DafneEngine:
         scratch = torch.empty(need.value + 1024, dtype=torch.uint8, device=self.device)
         sbase = (scratch.data_ptr() + 1023) // 1024 * 1024
         cap = capacity or (self.spec.post_nms_topk + 64)
-        dets = torch.zeros(N, cap, DET, dtype=torch.float32, device=self.device)
-        counts = torch.zeros(N, dtype=torch.int32, device=self.device)
+        wire = DetectionWire(N, cap, self.device)
+        dets, counts = wire.dets, wire.counts
         sizes = _i32_array([v for s in image_sizes for v in s])
         osz = _i32_array([v for s in (output_sizes or image_sizes) for v in s])
         L = len(logits)
@@ -267,6 +330,11 @@ class _DeviceFloats:
 
     def __init__(self, ptr: int, n: int):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class _DeviceInts:
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
 
 class _DeviceHalfs:

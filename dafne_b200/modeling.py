@@ -328,8 +328,10 @@ class OneStageDetector(nn.Module):
             if n > cap:
                 raise _capi.DafneError(f"{n} detections exceed the output capacity {cap} (score ties at the cut)")
             d = dets[i, :n]
-            image_size = out_sizes[i] if do_postprocess else sizes[i]
-            inst = Instances(image_size)
+            # detectron2's detector_postprocess runs inside ProposalNetwork.forward whatever do_postprocess says: the
+            # boxes are scaled / clipped / filtered and image_size is the requested output size either way;
+            # do_postprocess only gates the corner / location rescale (one_stage_detector.py:45-55, 78-98)
+            inst = Instances(out_sizes[i])
             inst.pred_boxes = Boxes(d[:, 8:12].clone())
             inst.pred_corners = d[:, 0:8].clone()
             inst.scores = d[:, 12].clone()

@@ -94,6 +94,9 @@ int dafne_head_output(dafne_ctx* ctx, int level, int which, const float** dev_pt
 
 /* Post-processing of head outputs held in the workspace.
  * image_sizes / output_sizes: N x (h, w) int32 on the host (output = the "height"/"width" the caller asked for).
+ * The horizontal boxes are ALWAYS scaled to the output size, clipped and rows with an empty clipped box dropped
+ * (detectron2 ProposalNetwork.forward -> detector_postprocess); do_postprocess gates only the rescale of the corners
+ * and locations (OneStageDetector.forward(batched_inputs, do_postprocess), one_stage_detector.py:45-55, 78-98).
  * dev_dets: [N][capacity][DAFNE_DET_STRIDE] fp32, rows in descending score; dev_counts: [N] int32 = number of
  * detections the reference would return (may exceed `capacity` only through exact score ties at the top-k cut; rows
  * beyond capacity are dropped and the count still reports them). */
@@ -131,6 +134,12 @@ int dafne_detect_host_begin(dafne_ctx* ctx, const void* host_images, int dtype, 
                             const int32_t* output_sizes, float* host_dets, int32_t* host_counts, int capacity,
                             void* stream, int* ticket);
 int dafne_detect_host_end(dafne_ctx* ctx, int ticket);
+
+/* Device-side result record of a pipelined batch, for multi-GPU callers: [N][capacity][DAFNE_DET_STRIDE] fp32
+ * detections immediately followed by [N] int32 counts, `*bytes` long, valid from dafne_detect_host_begin(ticket) (in
+ * stream order) until the second dafne_detect_host_begin after it. One all-gather of this record on the compute stream
+ * replaces the reference's pickled comm.gather (dafne/evaluation/dafne_evaluator.py:61-64) with no host bounce. */
+int dafne_host_slot_wire(dafne_ctx* ctx, int ticket, const void** dev_wire, size_t* bytes, int* capacity);
 
 /* Per-layer parity support. keep != 0 (set BEFORE dafne_bind_workspace) disables activation-memory reuse so that
  * every intermediate survives the forward; dafne_debug_activation then returns the NHWC fp16 tensor called `name`:

@@ -57,15 +57,21 @@ def test_float_images_and_uint8_images_agree(model):
 
 
 def test_do_postprocess_false_then_manual_rescale(model):
+    """detectron2's ProposalNetwork.forward runs detector_postprocess on every result: with do_postprocess=False the
+    boxes are still scaled / clipped / filtered and image_size is the output size; only the corner / location rescale
+    (one_stage_detector.py:78-98) is left to the caller -- the TTA call shape (tta.py:190-194)."""
     inp = _inputs(7)[:1]
     raw = model.inference(inp, do_postprocess=False)
     inst = raw[0]["instances"]
-    assert inst.image_size == (256, 320)
+    assert inst.image_size == (512, 640)
     full = model(inp)[0]["instances"]
-    model._postprocess(raw, inp)
-    # the rescaled corners of the unfiltered result contain every post-processed row
-    assert len(inst) >= len(full)
-    assert torch.allclose(inst.pred_corners[: 5], full.pred_corners[: 5]) or len(inst) != len(full)
+    assert len(inst) == len(full)
+    assert torch.equal(inst.pred_boxes.tensor, full.pred_boxes.tensor)  # already in output coordinates
+    assert torch.equal(inst.scores, full.scores) and torch.equal(inst.pred_classes, full.pred_classes)
+    assert not torch.equal(inst.pred_corners, full.pred_corners)  # still in input coordinates
+    model._postprocess(raw, inp)  # in place, like the reference's
+    assert torch.equal(inst.pred_corners, full.pred_corners)
+    assert torch.equal(inst.locations, full.locations)
 
 
 def test_select_over_all_levels_like_tta(model):

@@ -44,6 +44,11 @@ def _worker(rank, world, port, n_images, out_q):
         out_q.put(("sharded", rank, dets[:, 0, 0].tolist(), counts.tolist()))
         d2, c2 = gather_detections(torch.full((2, 4, 20), float(rank)), torch.full((2,), rank, dtype=torch.int32))
         out_q.put(("gather", rank, d2[:, 0, 0].tolist(), c2.tolist()))
+        from dafne_b200.distributed import gather_wire
+
+        wire = torch.cat([torch.full((2 * 4 * 20,), float(rank)).view(torch.int32), torch.full((2,), rank + 7, dtype=torch.int32)])
+        d3, c3 = gather_wire(wire, 2, 4, 20)
+        out_q.put(("wire", rank, d3[:, :, 0, 0].reshape(-1).tolist(), c3.reshape(-1).tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -56,7 +61,7 @@ def test_sharded_detect_two_ranks_gloo(n_images):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_images, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=120) for _ in range(4)]
+    results = [q.get(timeout=120) for _ in range(6)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -69,6 +74,10 @@ def test_sharded_detect_two_ranks_gloo(n_images):
     assert len(second) == 2
     for _, _, tags, counts in second:
         assert tags == [0.0, 0.0, 1.0, 1.0] and counts == [0, 0, 1, 1]
+    third = [r for r in results if r[0] == "wire"]
+    assert len(third) == 2
+    for _, _, tags, counts in third:  # one collective on the engine's record layout, rank-major
+        assert tags == [0.0, 0.0, 1.0, 1.0] and counts == [7, 7, 8, 8]
 
 
 def test_shard_range():
@@ -77,12 +86,26 @@ def test_shard_range():
     assert sum(len(shard_range(128, r, 8)) for r in range(8)) == 128
 
 
-def test_wire_format_round_trips_counts_bit_exactly():
+def test_wire_format_round_trips_bit_exactly():
+    """The wire is typed int32 (raw bits): NaN payloads, denormals and -0.0 in the detections survive unchanged."""
     g = torch.Generator().manual_seed(0)
     dets = torch.randn(3, 5, 20, generator=g)
-    counts = torch.tensor([0, 5, 2_000_000_000], dtype=torch.int32)  # as raw bits: includes NaN-looking patterns
+    dets[0, 0, :4] = torch.tensor([float("nan"), -0.0, 1e-42, float("inf")])
+    counts = torch.tensor([0, 5, 2_000_000_000], dtype=torch.int32)
     wire = pack_wire(dets, counts)
-    assert wire.shape == (3, 101) and wire.dtype == torch.float32
+    assert wire.shape == (3, 101) and wire.dtype == torch.int32
     d2, c2 = unpack_wire(wire.clone(), dets.shape[1:])
-    assert torch.equal(d2, dets) and torch.equal(c2, counts)
+    assert torch.equal(d2.view(torch.int32), dets.view(torch.int32)) and torch.equal(c2, counts)
 
+
+def test_gather_wire_single_process_views():
+    """gather_wire on the engine's record layout (detections then counts in one int32 buffer), world size 1."""
+    from dafne_b200.distributed import gather_wire
+
+    n, cap, det = 2, 3, 20
+    dets = torch.arange(n * cap * det, dtype=torch.float32).view(n, cap, det)
+    counts = torch.tensor([3, 1], dtype=torch.int32)
+    wire = torch.cat([dets.view(torch.int32).reshape(-1), counts])
+    d, c = gather_wire(wire, n, cap, det)
+    assert d.shape == (1, n, cap, det) and c.shape == (1, n)
+    assert torch.equal(d[0], dets) and torch.equal(c[0], counts)

@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from oracle import postprocess as opost
+from tests import golden
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 REF = "/root/reference"
@@ -108,6 +109,54 @@ def test_postprocess_oracle_regression_and_invariants(tag):
         b = r["pred_boxes"]
         assert np.all(b[:, 0] >= 0) and np.all(b[:, 2] <= ow) and np.all(b[:, 1] >= 0) and np.all(b[:, 3] <= oh)
         assert np.all(b[:, 2] > b[:, 0]) and np.all(b[:, 3] > b[:, 1])  # nonempty()
+
+
+@pytest.mark.parametrize("name", golden.ref_postprocess_cases())
+def test_postprocess_oracle_reproduces_the_reference_chain(name):
+    """Fixtures made by EXECUTING the reference's dafne_outputs.py:733-925, nms/nms.py:10-92, sort_corners.py and
+    one_stage_detector.py:45-98 (tests/golden/make_golden_postprocess_ref.py): threshold / top-k membership, decode,
+    corner sort, class offsets, NMS order, the post-NMS cut with kthvalue, detectron2's scale / clip / nonempty and the
+    do_postprocess gate -- same detections, same order, identical coordinates."""
+    c = golden.load_ref_postprocess(name)
+    res = opost.postprocess(c["logits"], c["reg"], c["ctr"], golden.STRIDES, c["sizes"], c["osz"],
+                            do_postprocess=c["do_postprocess"], **c["kw"])
+    assert len(res) == len(c["want"])
+    assert max(len(w["scores"]) for w in c["want"]) > 60  # the fixture itself is non-trivial
+    for i, (r, w) in enumerate(zip(res, c["want"])):
+        golden.assert_matches_reference_chain(r, w, (name, i))
+        assert r["image_size"] == c["osz"][i]
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("seed,C_,sort_c,twc", [(101, 15, True, True), (102, 2, False, False), (103, 15, True, False)])
+def test_postprocess_oracle_reproduces_the_reference_chain_live(seed, C_, sort_c, twc):
+    """The same comparison on fresh seeds, with the reference's code executed now (not only the stored fixtures)."""
+    from tests.golden import make_golden_postprocess_ref as ref
+
+    cfg = dict(C=C_, sort=sort_c, twc=twc, pre=300, post=120, seed=seed, bias=-2.2 if twc else (-3.2 if C_ > 2 else -1.6))
+    for dop in (True, False):
+        blob, want = ref.run_reference(cfg, dop)
+        res = opost.postprocess([blob[f"logits{l}"] for l in range(5)], [blob[f"reg{l}"] for l in range(5)],
+                                [blob[f"ctr{l}"] for l in range(5)], golden.STRIDES,
+                                [tuple(r) for r in blob["sizes"].tolist()], [tuple(r) for r in blob["osz"].tolist()],
+                                pre_nms_topk=300, post_nms_topk=120, sort_corners=sort_c, thresh_with_ctr=twc,
+                                do_postprocess=dop)
+        for i, (r, w) in enumerate(zip(res, want)):
+            golden.assert_matches_reference_chain(r, w, (seed, dop, i))
+
+
+def test_reference_chain_fixtures_exercise_every_cut():
+    """The fixtures cover: per-level top-k binding (more candidates than pre_nms_topk), the post-NMS cut binding,
+    rows dropped by the clipped-box filter, THRESH_WITH_CTR on and off, one class and sixteen, do_postprocess off."""
+    names = golden.ref_postprocess_cases()
+    assert {"c15_sort", "c15_ctr", "c16_nosort", "c1_sort", "c15_default_topk", "c15_sort_nopost"} <= set(names)
+    c = golden.load_ref_postprocess("c15_sort")
+    cls = opost.sigmoid_cr(c["logits"][0])
+    assert int((cls[0] > 0.05).sum()) > c["kw"]["pre_nms_topk"]  # top-k binds at the first level
+    assert len(c["want"][0]["scores"]) == c["kw"]["post_nms_topk"]  # the post-NMS cut binds
+    nopost = golden.load_ref_postprocess("c15_sort_nopost")
+    assert np.array_equal(nopost["want"][0]["pred_boxes"], c["want"][0]["pred_boxes"])  # boxes scaled either way
+    assert not np.array_equal(nopost["want"][0]["pred_corners"], c["want"][0]["pred_corners"])
 
 
 def test_postprocess_empty_image():

@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from oracle import postprocess as opost
+from tests import golden
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 pytestmark = pytest.mark.gpu
@@ -265,6 +266,30 @@ def test_postprocess_external_matches_golden(tag):
     eng.close()
 
 
+@pytest.mark.parametrize("name", golden.ref_postprocess_cases())
+def test_postprocess_device_reproduces_the_reference_chain(name):
+    """The device post-processing against fixtures made by EXECUTING the reference's own dafne_outputs.py:733-925,
+    nms/nms.py:10-92, sort_corners.py and one_stage_detector.py:45-98 (tests/golden/make_golden_postprocess_ref.py):
+    identical detections in identical order, identical classes / levels / coordinates / boxes; scores within the
+    sigmoid convention's ulps (tests/golden/__init__.py::assert_matches_reference_chain)."""
+    c = golden.load_ref_postprocess(name)
+    kw = c["kw"]
+    eng, spec = _engine(c["num_classes"], kw["sort_corners"], kw["thresh_with_ctr"], kw["pre_nms_topk"],
+                        kw["post_nms_topk"])
+    dets, counts = eng.postprocess_external([torch.from_numpy(t) for t in c["logits"]],
+                                            [torch.from_numpy(t) for t in c["reg"]],
+                                            [torch.from_numpy(t) for t in c["ctr"]], c["sizes"], c["osz"],
+                                            c["do_postprocess"])
+    dets, counts = dets.cpu().numpy(), counts.cpu().numpy()
+    for i, w in enumerate(c["want"]):
+        n = int(counts[i])
+        g = dets[i, :n]
+        got = dict(pred_corners=g[:, 0:8], pred_boxes=g[:, 8:12], scores=g[:, 12], centerness=g[:, 13],
+                   pred_classes=g[:, 14].astype(np.int64), fpn_levels=g[:, 15].astype(np.int64), locations=g[:, 16:18])
+        golden.assert_matches_reference_chain(got, w, (name, i))
+    eng.close()
+
+
 @pytest.mark.parametrize("C_,sort_c,twc,seed,scale", [(15, True, False, 21, 1.0), (15, True, True, 22, 1.0),
                                                       (1, True, False, 23, 2.0), (16, False, False, 24, 1.0),
                                                       (2, False, True, 25, 0.5)])
@@ -288,7 +313,7 @@ def test_postprocess_random_heads_match_oracle(C_, sort_c, twc, seed, scale):
                                             [torch.from_numpy(t) for t in ctr], sizes, osz, True)
     assert max(len(r["scores"]) for r in res) > 20  # sanity of the test inputs themselves
     _compare(res, dets, counts)
-    # do_postprocess=False (the TTA call shape, tta.py:190-194): no rescale / clip / filter
+    # do_postprocess=False (the TTA call shape, tta.py:190-194): boxes scaled / clipped / filtered, corners untouched
     res2 = opost.postprocess(logits, reg, ctr, strides, sizes, osz, pre_nms_topk=300, post_nms_topk=200,
                              sort_corners=sort_c, thresh_with_ctr=twc, do_postprocess=False)
     dets2, counts2 = eng.postprocess_external([torch.from_numpy(t) for t in logits], [torch.from_numpy(t) for t in reg],
@@ -312,4 +337,54 @@ def test_postprocess_empty_and_all_pass():
                                             [torch.from_numpy(t) for t in ctr], sizes, None, True)
     assert counts.tolist()[0] == 0 and len(res[0]["scores"]) == 0
     _compare(res, dets, counts)
+    eng.close()
+
+
+def test_post_nms_cut_keeps_every_score_tied_with_the_kth():
+    """dafne_outputs.py:916-923: `kthvalue` + `scores >= thr` keeps ALL detections whose score equals the k-th best, so
+    an image can return more than POST_NMS_TOPK_TEST rows. Exact ties at the cut, on the device: 10 distinct scores,
+    then 8 boxes with identical logits and centerness (identical scores), then lower ones; post_nms_topk = 12 lands
+    inside the tie group -> 18 rows. Boxes are 4 px wide on a stride-8 grid, so the NMS suppresses nothing."""
+    C_, H, W = 1, 12, 12
+    eng, spec = _engine(C_, False, False, 2000, 12)
+    hw = [(H, W), (6, 6), (3, 3), (2, 2), (1, 1)]
+    logits = [np.full((1, C_, h, w), -20.0, np.float32) for h, w in hw]
+    ctr = [np.zeros((1, 1, h, w), np.float32) for h, w in hw]
+    base = np.array([-0.25, -0.25, 0.25, -0.25, 0.25, 0.25, -0.25, 0.25], np.float32).reshape(1, 8, 1, 1)  # stride units
+    reg = [np.tile(base, (1, 1, h, w)).astype(np.float32) for h, w in hw]
+    flat = logits[0].reshape(-1)
+    flat[0:10] = np.linspace(3.0, 2.1, 10, dtype=np.float32)  # 10 distinct, best first
+    flat[20:28] = 1.5                                          # 8 exact ties
+    flat[40:60] = np.linspace(1.0, 0.2, 20, dtype=np.float32)  # 20 lower ones
+    sizes = [(H * 8, W * 8)]
+    res = opost.postprocess(logits, reg, ctr, [8, 16, 32, 64, 128], sizes, None, pre_nms_topk=2000, post_nms_topk=12,
+                            sort_corners=False, thresh_with_ctr=False)
+    assert len(res[0]["scores"]) == 18 and len(np.unique(res[0]["scores"][10:])) == 1
+    t = [[torch.from_numpy(a) for a in x] for x in (logits, reg, ctr)]
+    dets, counts = eng.postprocess_external(t[0], t[1], t[2], sizes, None, True)
+    _compare(res, dets, counts)
+    assert int(counts[0]) == 18
+    # the reference's semantics when the ties do not fit the caller's buffer: the count still says 18, rows are cut
+    dets2, counts2 = eng.postprocess_external(t[0], t[1], t[2], sizes, None, True, capacity=14)
+    assert int(counts2[0]) == 18 and dets2.shape[1] == 14
+    assert np.array_equal(dets2[0].cpu().numpy()[:, 12], res[0]["scores"][:14])
+    eng.close()
+
+
+def test_rows_past_the_count_are_zero_and_buffers_are_reusable():
+    """The finalize kernel writes every element of the record: a caller-owned DetectionWire reused across batches never
+    shows rows of an earlier batch (no per-step clear on the host side)."""
+    from dafne_b200.engine import DetectionWire
+
+    c = golden.load_ref_postprocess("c15_sort")
+    kw = c["kw"]
+    eng, spec = _engine(c["num_classes"], kw["sort_corners"], kw["thresh_with_ctr"], kw["pre_nms_topk"],
+                        kw["post_nms_topk"])
+    t = [[torch.from_numpy(a) for a in c[k]] for k in ("logits", "reg", "ctr")]
+    dets, counts = eng.postprocess_external(t[0], t[1], t[2], c["sizes"], c["osz"], True)
+    for i, n in enumerate(counts.tolist()):
+        assert n > 0 and float(dets[i, n:].abs().max()) == 0.0
+    w = DetectionWire(2, 8, _dev())
+    assert w.dets.shape == (2, 8, 20) and w.counts.shape == (2,) and w.counts.dtype == torch.int32
+    assert w.dets.data_ptr() == w.buf.data_ptr() and w.counts.data_ptr() == w.buf.data_ptr() + 2 * 8 * 20 * 4
     eng.close()

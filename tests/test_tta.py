@@ -26,6 +26,30 @@ def test_resize_shortest_edge_sizes_like_detectron2():
     assert (t.new_h, t.new_w) == (1200, 1200)
 
 
+def test_transforms_agree_with_the_oracle_restatement():
+    """Product transforms (dafne_b200/tta.py) against the oracle's independent restatement (oracle/tta.py): output
+    sizes of ResizeShortestEdge over a sweep of image sizes, and apply_coords / inverse of every copy's chain, bit for
+    bit in float32."""
+    from oracle import tta as otta
+
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        h, w = int(rng.integers(32, 2400)), int(rng.integers(32, 2400))
+        size, max_size = int(rng.choice([400, 512, 600, 800, 1024, 1200, 1333])), int(rng.choice([800, 1333, 2000]))
+        t = tta.resize_shortest_edge_transform(h, w, size, max_size)
+        assert (t.new_h, t.new_w) == otta.shortest_edge_size(h, w, size, max_size), (h, w, size, max_size)
+    cfg = _cfg(min_sizes=(96, 128, 200), max_size=180)
+    g = torch.Generator().manual_seed(0)
+    image = torch.randint(0, 256, (3, 100, 140), dtype=torch.uint8, generator=g)
+    copies = tta.DotaDatasetMapperTTA(cfg)({"image": image, "height": 100, "width": 140})
+    chains = [otta.chain_of_copy(100, 140, ms, 180, flip) for ms in (96, 128, 200) for flip in ("", "h", "v")]
+    pts = rng.uniform(-5, 260, (64, 2)).astype(np.float32)
+    for c, chain in zip(copies, chains):
+        tfm = c["transforms"]
+        assert np.array_equal(tfm.apply_coords(pts.copy()), otta.apply_coords(chain, pts))
+        assert np.array_equal(tfm.inverse().apply_coords(pts.copy()), otta.apply_coords(otta.inverse_chain(chain), pts))
+
+
 def test_transform_inverse_round_trip_and_device_free_math():
     rng = np.random.default_rng(0)
     pts = rng.uniform(0, 300, (50, 2)).astype(np.float32)
@@ -84,7 +108,12 @@ def test_tta_wrapper_equals_oracle_merge_of_the_copies():
     classes = [o["instances"].pred_classes.cpu().numpy() for o in per_copy]
     assert sum(len(s) for s in scores) > 50, "the synthetic model should detect something in every copy"
     spec = model.spec
-    want_c, want_s, want_k, _ = otta.merge_detections(corners, scores, classes, tfms, spec.nms_thresh,
+    # the oracle applies ITS OWN restatement of the transforms: the chains are rebuilt from the mapper's configuration
+    # (sizes and flips), not taken from the product's transform objects
+    H, W = image.shape[1:]
+    chains = [otta.chain_of_copy(H, W, ms, 320, flip) for ms in (160, 192, 256) for flip in ("", "h", "v")]
+    assert len(chains) == len(tfms)
+    want_c, want_s, want_k, _ = otta.merge_detections(corners, scores, classes, chains, spec.nms_thresh,
                                                       spec.post_nms_topk, spec.vehicle_merge)
     assert len(out) == len(want_s)
     assert np.array_equal(out.scores.cpu().numpy(), want_s)
