@@ -111,6 +111,7 @@ _SIGNATURES = {
     "dafne_sort_quadrilateral": (_i, [_vp, _vp, _i, _vp]),
     "dafne_poly_iou": (_i, [_vp, _vp, _vp, _i, _vp]),
     "dafne_poly_pair_filter": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "dafne_poly_term_filter": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "dafne_poly_nms": (_i, [_vp, _vp, _vp, _i, _f, _i, _vp, _vp, _vp, C.c_size_t, _vp]),
     "dafne_poly_nms_scratch_bytes": (_i, [_i, C.POINTER(C.c_size_t)]),
     "dafne_poly_nms_host": (_i, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), _i, _i, _f, _i]),

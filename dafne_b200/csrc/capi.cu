@@ -494,6 +494,9 @@ int dafne_poly_iou(const float* p, const float* q, float* iou, int n, void* stre
 int dafne_poly_pair_filter(const float* p, const float* q, uint8_t* fired, int n, void* stream) {
     return launch_pair_filter(p, q, fired, n, static_cast<cudaStream_t>(stream));
 }
+int dafne_poly_term_filter(const float* p, const float* q, uint16_t* fired, uint16_t* nonzero, int n, void* stream) {
+    return launch_term_filter(p, q, fired, nonzero, n, static_cast<cudaStream_t>(stream));
+}
 int dafne_poly_nms_scratch_bytes(int n, size_t* bytes) {
     *bytes = poly_nms_scratch_bytes(n);
     return 0;

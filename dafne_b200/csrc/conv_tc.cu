@@ -139,16 +139,18 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int lt) {
     return c;
 }
 
-// out[c], out[c+1] = fp16(relu?(acc * scale + shift (+ residual))) for the 64 channels of one chunk. The ReLU rides on
+// out[c], out[c+1] = fp16(relu?(acc * scale + shift (+ residual))) for 32 channels (HALF a chunk: with a whole chunk
+// in flight -- 64 accumulators + 32 residual + 32 packed registers -- the epilogue needed 196 registers; in halves it
+// needs 145, which fits the 168 a 384-thread CTA starts with). The ReLU rides on
 // the conversion (cvt.rn.relu.f16x2.f32), the (scale, shift) pairs come as one 128-bit shared-memory broadcast per two
 // channels. Compile-time RELU / HAS_RES: the epilogue of the HBM-bound convolutions is issue-bound, so nothing that is
 // switched off may cost an instruction.
 template <bool RELU, bool HAS_RES>
-__device__ __forceinline__ void epilogue_chunk_math(const uint32_t (&v)[64], const float2* tab, const uint4 (&res)[8],
-                                                    uint32_t (&packed)[32]) {
+__device__ __forceinline__ void epilogue_half_math(const uint32_t (&v)[32], const float2* tab, const uint4 (&res)[4],
+                                                   uint32_t (&packed)[16]) {
     const uint32_t* rw = reinterpret_cast<const uint32_t*>(res);
 #pragma unroll
-    for (int c = 0; c < 64; c += 2) {
+    for (int c = 0; c < 32; c += 2) {
         const float4 tb = *reinterpret_cast<const float4*>(&tab[c]);  // (scale, shift) x 2
         float a0 = fmaf(__uint_as_float(v[c]), tb.x, tb.y);
         float a1 = fmaf(__uint_as_float(v[c + 1]), tb.z, tb.w);
@@ -249,10 +251,14 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    // EPI_WGS == 2: 384 threads start with 168 registers each; the producer/MMA warpgroup hands its surplus to the two
-    // epilogue warpgroups (128 x 56 + 256 x 224 = 384 x 168).
+    // EPI_WGS == 2: 384 threads start with 168 registers each; the producer / MMA warpgroup hands part of its share to
+    // the two epilogue warpgroups: 128 x 88 + 256 x 208 = 384 x 168 EXACTLY -- setmaxnreg.inc blocks until the CTA's own
+    // pool holds the registers, so asking for more than the other side released hangs the kernel (88 / 208 and the
+    // earlier 56 / 224 balance; 96 / 208 does not). ptxas allocates each side under its setmaxnreg
+    // value: with the earlier 56 / 224 split the PRODUCER warps spilled (84 B stores, 412 B loads per thread, inside
+    // the per-tile loop that feeds the HBM-bound 1x1 convolutions).
     if (warp < 4) {
-        if constexpr (EPI_WGS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if constexpr (EPI_WGS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     }
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (operands)
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue
-        if constexpr (EPI_WGS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        if constexpr (EPI_WGS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         const int wg = (warp - 4) >> 2;  // epilogue warpgroup
         const int wi = warp & 3;         // this warp may touch TMEM lanes [32*wi, 32*wi+32)
         const int et = (threadIdx.x - 128) & 127;
@@ -541,48 +547,75 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                     const int chbase = j * 64;
                     const int slot = chunk_cnt % ring;
                     const uint32_t buf = s_epi_wg + slot * Cfg::SLOT_BYTES;
-                    uint4 res[8];
-                    if (res_ldg) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            res[q] = valid ? __ldg(reinterpret_cast<const uint4*>(res_row + chbase) + q)
-                                           : make_uint4(0, 0, 0, 0);
-                    }
-                    uint32_t v[64];
-                    DAFNE_TMEM_LD_X32(taddr + chbase, v);
-                    DAFNE_TMEM_LD_X32(taddr + chbase + 32, (v + 32));
                     if (res_tma) {
                         // the residual chunk of this tile, TMA-loaded into the slot the output is staged in
                         mbar_wait(bar_rfull + 8 * (wg * RS + slot), static_cast<uint32_t>(chunk_cnt / ring) & 1);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const uint32_t src = buf + row * 128 + ((q ^ (row & 7)) << 4);
-                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(res[q].x), "=r"(res[q].y), "=r"(res[q].z), "=r"(res[q].w)
-                                         : "r"(src)
-                                         : "memory");
-                        }
-                    }
-                    tmem_ld_wait();
-                    if (j == CHUNKS - 1) {
-                        // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                     }
                     uint32_t packed[32];
                     if (MODE == 2) {
+                        uint32_t v[64];
+                        DAFNE_TMEM_LD_X32(taddr + chbase, v);
+                        DAFNE_TMEM_LD_X32(taddr + chbase + 32, (v + 32));
+                        tmem_ld_wait();
+                        if (j == CHUNKS - 1) {
+                            // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                        }
                         epilogue_chunk_bias(v, s_bias + chbase, packed);
-                    } else if (MODE == 1) {
-                        if (p.relu)
-                            epilogue_chunk_math<true, true>(v, s_tab + chbase, res, packed);
-                        else
-                            epilogue_chunk_math<false, true>(v, s_tab + chbase, res, packed);
                     } else {
-                        if (p.relu)
-                            epilogue_chunk_math<true, false>(v, s_tab + chbase, res, packed);
-                        else
-                            epilogue_chunk_math<false, false>(v, s_tab + chbase, res, packed);
+                        // two halves of 32 channels, each: accumulators out of TMEM, residual in, math, staged out --
+                        // short live ranges (see epilogue_half_math)
+#pragma unroll 1
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t vh[32];
+                            DAFNE_TMEM_LD_X32(taddr + chbase + 32 * h, vh);
+                            uint4 res[4];
+                            if (res_ldg) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    res[q] = valid ? __ldg(reinterpret_cast<const uint4*>(res_row + chbase) + h * 4 + q)
+                                                   : make_uint4(0, 0, 0, 0);
+                            }
+                            if (res_tma) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const uint32_t src = buf + row * 128 + (((h * 4 + q) ^ (row & 7)) << 4);
+                                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=r"(res[q].x), "=r"(res[q].y), "=r"(res[q].z), "=r"(res[q].w)
+                                                 : "r"(src)
+                                                 : "memory");
+                                }
+                            }
+                            tmem_ld_wait();
+                            if (j == CHUNKS - 1 && h == 1) {
+                                // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                            }
+                            uint32_t ph[16];
+                            const float2* tb = s_tab + chbase + 32 * h;
+                            if (MODE == 1) {
+                                if (p.relu)
+                                    epilogue_half_math<true, true>(vh, tb, res, ph);
+                                else
+                                    epilogue_half_math<false, true>(vh, tb, res, ph);
+                            } else {
+                                if (p.relu)
+                                    epilogue_half_math<true, false>(vh, tb, res, ph);
+                                else
+                                    epilogue_half_math<false, false>(vh, tb, res, ph);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t dst = buf + row * 128 + (((h * 4 + q) ^ (row & 7)) << 4);
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ph[4 * q]),
+                                             "r"(ph[4 * q + 1]), "r"(ph[4 * q + 2]), "r"(ph[4 * q + 3])
+                                             : "memory");
+                            }
+                        }
                     }
                     float gs[16];
                     if (MODE == 2) {
@@ -629,12 +662,14 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                     // slot is known to be free: in residual mode because its reload was gated on the previous store
                     // (bar_rempty), otherwise because the elected thread waited for that store before the barrier
                     // of the PREVIOUS chunk (wait_group.read ring-2 below).
+                    if (MODE == 2) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t dst = buf + row * 128 + ((q ^ (row & 7)) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * q]),
-                                     "r"(packed[4 * q + 1]), "r"(packed[4 * q + 2]), "r"(packed[4 * q + 3])
-                                     : "memory");
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t dst = buf + row * 128 + ((q ^ (row & 7)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * q]),
+                                         "r"(packed[4 * q + 1]), "r"(packed[4 * q + 2]), "r"(packed[4 * q + 3])
+                                         : "memory");
+                        }
                     }
                     fence_proxy_async_smem();
                     if (et == 0 && !res_tma) {

@@ -7,15 +7,19 @@
 //   nms_diag_kernel   panel x panel upper triangle for the rows/columns still alive, then (last block done) the
 //                     sequential sweep inside the panel -> the panel's kept rows
 //   nms_bcast_kernel  kept rows of the panel x every later box still alive; sets `removed` bits (one wave of resident
-//                     CTAs pulling (column chunk, row chunk, image) items from a counter)
+//                     CTAs pulling (column chunk, row chunk, image) items from a counter). Run TWICE per panel: pass 0
+//                     evaluates only the pairs whose centres are close (the likely suppressors), pass 1 the remaining
+//                     pairs of the columns that are STILL alive -- a suppressed box needs one hit, and once its near
+//                     twin has been found none of its other pairs is clipped. Which pairs go first changes the work,
+//                     never a decision: a column dies iff SOME kept row has IoU > thr with it.
 // Work drops from n^2/2 pairs to about (kept x alive) pairs. Inside both kernels a pair first goes through
 // pair_inter_is_zero() (polyiou.cuh: proves inter == 0 for separated boxes without running the clip); the pairs that
-// need the full fp32 clip are compacted into a shared-memory queue and processed with all lanes busy: a queued pair is
-// 16 signed triangle overlaps (edge triangle i of P x edge triangle j of Q, polyiou.cpp:91-103), one per lane, added
-// in the reference's order. (Measured: of those 16 terms 14 on average run all three half-plane clips for a pair the
-// pre-filter lets through, so a second, per-triangle queue only costs -- tried in r1e, 8 % slower end to end.)
+// need the full fp32 clip are compacted into a shared-memory queue and clipped term by term (clip_queue below): a
+// queued pair is 16 signed triangle overlaps (edge triangle i of P x edge triangle j of Q, polyiou.cpp:91-103), of which
+// only the ones not provably zero are evaluated, one per lane, and added in the reference's order.
 // No decision differs from evaluating iou_poly_f32(i, j) > thr for every consulted pair.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "conv_tc.cuh"  // set_error
 #include "polyiou.cuh"
@@ -23,7 +27,10 @@
 
 namespace dafne {
 
-constexpr int kPanel = 512;
+#ifndef DAFNE_NMS_PANEL
+#define DAFNE_NMS_PANEL 512
+#endif
+constexpr int kPanel = DAFNE_NMS_PANEL;  // <= 512: the sweep keeps the panel's hit words in 48 KB of static shared memory
 constexpr int kPanelWords = kPanel / 64;  // 8
 constexpr int kDiagBlocks = kPanelWords * (kPanelWords + 1) / 2;  // 36 (rb <= cb)
 // Work items are deliberately small (16 x 64 pairs): the clips a CTA ends up with vary by an order of magnitude with
@@ -67,7 +74,7 @@ static NmsLayout nms_layout(int N, int max_sel) {
     y.o_stats = o;
     o = a256n(o + kNmsStats * 8);
     y.o_work = o;  // one work-item counter per (panel, image group) of the broadcast
-    o = a256n(o + static_cast<size_t>((max_sel + kPanel - 1) / kPanel) * ((N + kBcastImages - 1) / kBcastImages) * 4);
+    o = a256n(o + static_cast<size_t>((max_sel + kPanel - 1) / kPanel) * 2 * ((N + kBcastImages - 1) / kBcastImages) * 4);
     y.o_diag = o;
     o = a256n(o + static_cast<size_t>(N) * kPanel * kPanelWords * 8);
     y.total = o;
@@ -102,33 +109,117 @@ __device__ __forceinline__ void stage_oriented(const float* __restrict__ src, fl
     }
 }
 
-// One queued pair is evaluated by 16 consecutive lanes, lane k = 4*i + j computing the signed overlap of edge
-// triangle i of P with edge triangle j of Q; the group leader then adds the 16 terms in the reference's order
-// (i outer, j inner) and finishes the IoU with the algorithm's own a1, a2. Returns IoU > thr on the leader lane.
-// (One pair per THREAD with all lanes on the same (i, j) was measured too: lanes agree even less on the clipper's
-// branches across pairs than across a pair's sixteen terms, and the CTA waits for its slowest thread -- 7 % slower.)
-__device__ __forceinline__ bool pair_suppresses_16(const float* P, const float* Q, float a1, float a2, float thr,
-                                                   bool active, unsigned lane, float2* slots, int stride) {
-    float val = 0.f;
-    if (active) {
-        const int i = (lane >> 2) & 3, j = lane & 3;
-        P2 a, b, c, d;
-        a.x = P[2 * i];
-        a.y = P[2 * i + 1];
-        b.x = P[2 * ((i + 1) & 3)];
-        b.y = P[2 * ((i + 1) & 3) + 1];
-        c.x = Q[2 * j];
-        c.y = Q[2 * j + 1];
-        d.x = Q[2 * ((j + 1) & 3)];
-        d.y = Q[2 * ((j + 1) & 3) + 1];
-        val = tri_overlap(a, b, c, d, slots, stride);
-    }
-    float inter = 0.f;
+// Appends `want` lanes' entries to a shared-memory queue with one atomic per warp. All 32 lanes must call it.
+__device__ __forceinline__ void queue_push(unsigned short* queue, int* qn, bool want, unsigned short entry,
+                                           unsigned lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (static_cast<int>(lane) == leader) base = atomicAdd(qn, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) queue[base + __popc(m & ((1u << lane) - 1u))] = entry;
+}
+
+// Phase 2 of both kernels: the queued pairs are clipped TERM by term. A pair is 16 signed triangle overlaps (edge
+// triangle i of P x edge triangle j of Q, polyiou.cpp:91-103); on the pairs that reach this point 8 of the 16 are zero
+// on average and polyiou.cuh::term_is_zero proves it for them without clipping. Per batch of kTermBatch pairs:
+//   A  one thread per (pair, i): the four terms' zero tests; the live terms go to a shared-memory term queue
+//   B  one thread per queued term: tri_overlap -> val[pair][term]       (every lane of every warp holds a live term)
+//   C  one thread per pair: the 16 values added in the reference's order (skipped ones are +0: x + 0 == x), the
+//      algorithm's own a1 / a2, IoU > thr
+// (r1e tried a term queue with the first shortcut alone -- 14 of 16 terms live -- and lost 8 %; with half of the
+// terms gone the balance flips.)
+constexpr int kTermBatch = 128;
+struct TermSmem {
+    float val[kTermBatch][17];  // 17: thread `pair` walks its row, rows 17 words apart are conflict-free
+    unsigned short tq[kTermBatch * 16];
+    int tqn;
+};
+
+template <bool BCAST, int THREADS>
+__device__ __forceinline__ void clip_queue(const unsigned short* queue, int qn, const float (*rbox)[8],
+                                           const float (*cbox)[8], const NmsAux* raux, const NmsAux* caux,
+                                           const float (*rt)[4], const float (*ct)[4], TermSmem& ts, float2* poly,
+                                           float thr, u64* bits, unsigned int* newdead) {
+    const int t = threadIdx.x;
+    const unsigned lane = t & 31;
+    constexpr int kRowShift = BCAST ? 7 : 6;
+    constexpr int kColMask = BCAST ? 127 : 63;
+    for (int b0 = 0; b0 < qn; b0 += kTermBatch) {
+        const int nb = min(kTermBatch, qn - b0);
+        for (int i = t; i < nb * 17; i += THREADS) (&ts.val[0][0])[i] = 0.f;
+        if (t == 0) ts.tqn = 0;
+        __syncthreads();
+        // A: zero tests. Uniform trip count: every lane of a warp reaches queue_push.
+        for (int k0 = 0; k0 < nb * 4; k0 += THREADS) {
+            const int k = k0 + t;
+            bool valid = k < nb * 4;
+            const int pl = valid ? (k >> 2) : 0, i = k & 3;
+            const int e = queue[b0 + pl];
+            const int r = e >> kRowShift, j = e & kColMask;
+            // a column some kept row already hit needs no further clip (any hit is enough); atomic read of the 0 -> 1
+            // flag so that concurrent warps are race-free by construction
+            if (BCAST && valid && atomicOr(&newdead[j], 0u)) valid = false;
+            const TermPairCtx ctx = term_pair_ctx(raux[r], caux[j]);
+            P2 a, b;
+            a.x = rbox[r][2 * i];
+            a.y = rbox[r][2 * i + 1];
+            b.x = rbox[r][2 * ((i + 1) & 3)];
+            b.y = rbox[r][2 * ((i + 1) & 3) + 1];
+            const float ta = rt[r][i], tb = rt[r][(i + 1) & 3];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) inter += __shfl_sync(0xffffffffu, val, (lane & 16) + k);
-    const float uni = a1 + a2 - inter;
-    const float iou = (uni == 0.f) ? (inter + 1.f) / (uni + 1.f) : inter / uni;
-    return active && iou > thr;
+            for (int jj = 0; jj < 4; ++jj) {
+                P2 c, d;
+                c.x = cbox[j][2 * jj];
+                c.y = cbox[j][2 * jj + 1];
+                d.x = cbox[j][2 * ((jj + 1) & 3)];
+                d.y = cbox[j][2 * ((jj + 1) & 3) + 1];
+                const bool live = valid && !term_is_zero(ctx, a, b, c, d, ta, tb, ct[j][jj], ct[j][(jj + 1) & 3]);
+                queue_push(ts.tq, &ts.tqn, live, static_cast<unsigned short>((pl << 4) | (i * 4 + jj)), lane);
+            }
+        }
+        __syncthreads();
+        // B: one live term per thread
+        const int tn = ts.tqn;
+        for (int e0 = 0; e0 < tn; e0 += THREADS) {
+            const int en = e0 + t;
+            if (en < tn) {
+                const int te = ts.tq[en];
+                const int pl = te >> 4, term = te & 15, i = term >> 2, jj = term & 3;
+                const int e = queue[b0 + pl];
+                const int r = e >> kRowShift, j = e & kColMask;
+                P2 a, b, c, d;
+                a.x = rbox[r][2 * i];
+                a.y = rbox[r][2 * i + 1];
+                b.x = rbox[r][2 * ((i + 1) & 3)];
+                b.y = rbox[r][2 * ((i + 1) & 3) + 1];
+                c.x = cbox[j][2 * jj];
+                c.y = cbox[j][2 * jj + 1];
+                d.x = cbox[j][2 * ((jj + 1) & 3)];
+                d.y = cbox[j][2 * ((jj + 1) & 3) + 1];
+                ts.val[pl][term] = tri_overlap(a, b, c, d, poly, THREADS);
+            }
+        }
+        __syncthreads();
+        // C: the pair's IoU from its 16 terms, in the reference's order (i outer, j inner)
+        for (int pl = t; pl < nb; pl += THREADS) {
+            float inter = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) inter += ts.val[pl][k];
+            const int e = queue[b0 + pl];
+            const int r = e >> kRowShift, j = e & kColMask;
+            const float uni = raux[r].area + caux[j].area - inter;
+            const float iou = (uni == 0.f) ? (inter + 1.f) / (uni + 1.f) : inter / uni;
+            if (iou > thr) {
+                if (BCAST)
+                    atomicExch(&newdead[j], 1u);
+                else
+                    atomicOr(&bits[r], 1ull << j);
+            }
+        }
+        __syncthreads();  // val / tq are rewritten by the next batch
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ diagonal panel
@@ -143,20 +234,10 @@ struct DiagSmem {
     int qn;
     int last;
     unsigned stat_pairs;
+    float rt[64][4], ct[64][4];     // t(v) of the staged boxes' vertices (term_is_zero)
     float2 poly[9 * kDiagThreads];  // tri_overlap's per-thread polygon columns
+    TermSmem terms;
 };
-
-// Appends `want` lanes' entries to a shared-memory queue with one atomic per warp. All 32 lanes must call it.
-__device__ __forceinline__ void queue_push(unsigned short* queue, int* qn, bool want, unsigned short entry,
-                                           unsigned lane) {
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (m == 0) return;
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (static_cast<int>(lane) == leader) base = atomicAdd(qn, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (want) queue[base + __popc(m & ((1u << lane) - 1u))] = entry;
-}
 
 // grid (36 * kDiagSplit, N), 256 threads. Block b / kDiagSplit -> (rb, cb), rb <= cb, both 64-box blocks of panel `panel`.
 __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __restrict__ boxes, const NmsAux* __restrict__ aux,
@@ -193,10 +274,14 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
             if (row < m) {
                 stage_oriented(boxes + (ibase + row) * 8, sm.rbox[t]);
                 sm.raux[t] = aux[ibase + row];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sm.rt[t][k] = vertex_t(sm.rbox[t][2 * k], sm.rbox[t][2 * k + 1]);
             }
             if (col < m) {
                 stage_oriented(boxes + (ibase + col) * 8, sm.cbox[t]);
                 sm.caux[t] = aux[ibase + col];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sm.ct[t][k] = vertex_t(sm.cbox[t][2 * k], sm.cbox[t][2 * k + 1]);
             }
             sm.bits[t] = 0;
         }
@@ -229,18 +314,10 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
             if (lane == 0 && npairs) atomicAdd(&sm.stat_pairs, npairs);
         }
         __syncthreads();
-        // phase 2: 16 lanes per queued pair
+        // phase 2: the queued pairs, term by term
         const int qn = sm.qn;
-        const unsigned lane = t & 31;
-        for (int e0 = 0; e0 < qn; e0 += kDiagThreads / 16) {
-            const int e = e0 + (t >> 4);
-            const bool active = e < qn;
-            const int r = active ? sm.queue[e] >> 6 : 0, j = active ? sm.queue[e] & 63 : 0;
-            const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active,
-                                                lane, sm.poly + t, kDiagThreads);
-            if (hit && (lane & 15) == 0) atomicOr(&sm.bits[r], 1ull << j);
-        }
-        __syncthreads();
+        clip_queue<false, kDiagThreads>(sm.queue, qn, sm.rbox, sm.cbox, sm.raux, sm.caux, sm.rt, sm.ct, sm.terms,
+                                        sm.poly + t, thr, sm.bits, nullptr);
         if (t == 0) {
             atomicAdd(stats + kStDiagPairs, static_cast<u64>(sm.stat_pairs));
             atomicAdd(stats + kStDiagQueued, static_cast<u64>(qn));
@@ -322,6 +399,9 @@ struct BcastSmem {
     NmsAux raux[kRowChunk];
     float cbox[kColChunk][8];
     NmsAux caux[kColChunk];
+    float2 rctr[kRowChunk], cctr[kColChunk];  // 4 x centre (vertex sum) of the staged boxes: the "close pair" test
+    float rt[kRowChunk][4], ct[kColChunk][4];  // t(v) of the staged boxes' vertices (term_is_zero)
+    TermSmem terms;
     unsigned short queue[kRowChunk * kColChunk];
     unsigned char dead[kColChunk];
     unsigned int newdead[kColChunk];  // 0 -> 1 flags, touched with atomics while phase 2 runs
@@ -340,7 +420,8 @@ struct BcastSmem {
 __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* __restrict__ boxes,
                                                               const NmsAux* __restrict__ aux,
                                                               const int* __restrict__ counts, int N, int max_sel,
-                                                              int nblk, int panel, float thr,
+                                                              int nblk, int panel, float thr, int pass,
+                                                              float close_k,
                                                               const u64* __restrict__ pk, u64* __restrict__ removed,
                                                               u64* __restrict__ stats, int* __restrict__ work_ctr) {
     __shared__ BcastSmem sm;
@@ -404,6 +485,10 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
         if (t < nrows) {
             stage_oriented(boxes + (ibase + sm.rows[t]) * 8, sm.rbox[t]);
             sm.raux[t] = aux[ibase + sm.rows[t]];
+            const float* b = sm.rbox[t];
+            sm.rctr[t] = make_float2(b[0] + b[2] + b[4] + b[6], b[1] + b[3] + b[5] + b[7]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sm.rt[t][k] = vertex_t(b[2 * k], b[2 * k + 1]);
         }
         u64* rmv = removed + static_cast<size_t>(n) * nblk;
         bool alive = false;
@@ -414,6 +499,10 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
                 if (alive) {
                     stage_oriented(boxes + (ibase + col) * 8, sm.cbox[t]);
                     sm.caux[t] = aux[ibase + col];
+                    const float* b = sm.cbox[t];
+                    sm.cctr[t] = make_float2(b[0] + b[2] + b[4] + b[6], b[1] + b[3] + b[5] + b[7]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sm.ct[t][k] = vertex_t(b[2 * k], b[2 * k + 1]);
                 }
             }
             sm.dead[t] = alive ? 0 : 1;
@@ -427,14 +516,25 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
             const unsigned lane = t & 31;
             const bool col_on = !sm.dead[j];
             const NmsAux Q = sm.caux[col_on ? j : 0];
+            const float2 qc = sm.cctr[col_on ? j : 0];
             unsigned npairs = 0;
             for (int u = 0; u < kRpt; ++u) {
                 const int r = part * kRpt + u;
                 bool want = col_on && r < nrows;
                 if (want) {
-                    ++npairs;
                     const NmsAux& P = sm.raux[r];
-                    if (pair_inter_is_zero(P, Q, sm.rbox[r], sm.cbox[j]) && (P.area + Q.area) != 0.f) want = false;
+                    // "close": squared centre distance below close_k x the smaller area (centres are kept x 4, hence
+                    // the 16). A work-ordering heuristic only -- every pair is evaluated in exactly one of the passes
+                    // unless its column has died in between.
+                    const float dx = sm.rctr[r].x - qc.x, dy = sm.rctr[r].y - qc.y;
+                    const bool close = dx * dx + dy * dy < 16.0f * close_k * fminf(P.area, Q.area);
+                    if (close != (pass == 0)) {
+                        want = false;
+                    } else {
+                        ++npairs;
+                        if (pass != 0 && pair_inter_is_zero(P, Q, sm.rbox[r], sm.cbox[j]) && (P.area + Q.area) != 0.f)
+                            want = false;
+                    }
                 }
                 queue_push(sm.queue, &sm.qn, want, static_cast<unsigned short>((r << 7) | j), lane);
             }
@@ -442,20 +542,10 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
             if (lane == 0 && npairs) atomicAdd(&sm.stat_pairs, npairs);
         }
         __syncthreads();
-        // phase 2: 16 lanes per queued pair
+        // phase 2: the queued pairs, term by term
         const int qn = sm.qn;
-        const unsigned lane = t & 31;
-        for (int e0 = 0; e0 < qn; e0 += kBcastThreads / 16) {
-            const int e = e0 + (t >> 4);
-            bool active = e < qn;
-            const int r = active ? sm.queue[e] >> 7 : 0, j = active ? sm.queue[e] & 127 : 0;
-            // a column some kept row already hit needs no further clip (any hit is enough); atomic read / write of the
-            // 0 -> 1 flag so that concurrent warps are race-free by construction (compute-sanitizer racecheck clean)
-            if (active && atomicOr(&sm.newdead[j], 0u)) active = false;
-            const bool hit = pair_suppresses_16(sm.rbox[r], sm.cbox[j], sm.raux[r].area, sm.caux[j].area, thr, active,
-                                                lane, sm.poly + t, kBcastThreads);
-            if (hit && (lane & 15) == 0) atomicExch(&sm.newdead[j], 1u);
-        }
+        clip_queue<true, kBcastThreads>(sm.queue, qn, sm.rbox, sm.cbox, sm.raux, sm.caux, sm.rt, sm.ct, sm.terms,
+                                        sm.poly + t, thr, nullptr, sm.newdead);
         if (t == 0) {
             atomicAdd(stats + kStBcastPairs, static_cast<u64>(sm.stat_pairs));
             atomicAdd(stats + kStBcastQueued, static_cast<u64>(qn));
@@ -503,6 +593,12 @@ int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float th
     u64* stats = reinterpret_cast<u64*>(b + y.o_stats);
     int* work = reinterpret_cast<int*>(b + y.o_work);
     const int groups = (N + kBcastImages - 1) / kBcastImages;
+    // pass 0 of the broadcast takes the pairs with squared centre distance < close_k x min(area): tuning aid
+    static float close_k = -1.f;
+    if (close_k < 0.f) {
+        const char* ev = getenv("DAFNE_NMS_CLOSE");
+        close_k = ev ? static_cast<float>(atof(ev)) : 5.0f;
+    }
     static DeviceOnce bcast_ctas_of;  // resident CTAs of the broadcast kernel, per device
     int dev = 0;
     int bcast_ctas = bcast_ctas_of.get(&dev);
@@ -535,16 +631,20 @@ int run_nms(const float* nmsbox, const int* counts, int N, int max_sel, float th
         NMS_CHECK_LAUNCH("nms_diag_kernel");
         ++nl;
         const int after = max_sel - (p + 1) * kPanel;
-        for (int g = 0; after > 0 && g < groups; ++g) {
-            const int n0 = g * kBcastImages, ng = N - n0 < kBcastImages ? N - n0 : kBcastImages;
-            const long long most = static_cast<long long>((after + kColChunk - 1) / kColChunk) * (kPanel / kRowChunk) * ng;
-            const int grid = most < bcast_ctas ? static_cast<int>(most) : bcast_ctas;
-            nms_bcast_kernel<<<grid, kBcastThreads, 0, s>>>(
-                nmsbox + static_cast<size_t>(n0) * max_sel * 8, aux + static_cast<size_t>(n0) * max_sel, counts + n0, ng,
-                max_sel, y.nblk, p, thr, pk + static_cast<size_t>(n0) * kPanelWords,
-                removed + static_cast<size_t>(n0) * y.nblk, stats, work + p * groups + g);
-            NMS_CHECK_LAUNCH("nms_bcast_kernel");
-            ++nl;
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 0 && !(close_k > 0.f)) continue;  // DAFNE_NMS_CLOSE=0: single pass (every pair is "far")
+            for (int g = 0; after > 0 && g < groups; ++g) {
+                const int n0 = g * kBcastImages, ng = N - n0 < kBcastImages ? N - n0 : kBcastImages;
+                const long long most =
+                    static_cast<long long>((after + kColChunk - 1) / kColChunk) * (kPanel / kRowChunk) * ng;
+                const int grid = most < bcast_ctas ? static_cast<int>(most) : bcast_ctas;
+                nms_bcast_kernel<<<grid, kBcastThreads, 0, s>>>(
+                    nmsbox + static_cast<size_t>(n0) * max_sel * 8, aux + static_cast<size_t>(n0) * max_sel, counts + n0,
+                    ng, max_sel, y.nblk, p, thr, pass, close_k, pk + static_cast<size_t>(n0) * kPanelWords,
+                    removed + static_cast<size_t>(n0) * y.nblk, stats, work + (p * 2 + pass) * groups + g);
+                NMS_CHECK_LAUNCH("nms_bcast_kernel");
+                ++nl;
+            }
         }
     }
     if (launches) *launches += nl;

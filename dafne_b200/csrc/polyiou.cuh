@@ -458,4 +458,58 @@ __device__ __forceinline__ bool pair_inter_is_zero(const NmsAux& P, const NmsAux
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------ per-term filter
+// The same proofs, one term at a time. A pair that reaches the clip has, on average, 8 of its 16 signed triangle
+// overlaps equal to zero (measured on class-shifted boxes: 4 where the edge triangle of P lies clockwise of Q's --
+// tri_overlap's own first shortcut -- and 4 where it lies counter-clockwise of it); `term_is_zero` decides that
+// BEFORE a lane is spent on the term, so the NMS kernels only queue the terms that have to be clipped.
+//
+//   a, b, c, d: the term's vertices as iou_poly_f32 passes them to tri_overlap (edge i of P, edge j of Q, both
+//   polygons already oriented by load_oriented); ta .. td: t(v) = (v.y - v.x) / (v.x + v.y) of those vertices, computed
+//   with exactly this expression. Returns true only if tri_overlap(a, b, c, d) is exactly (+-)0:
+//     * s1 == 0 or s2 == 0: tri_overlap returns 0 before any cut (polyiou.cpp:77-79);
+//     * both P vertices strictly right of O->c: tri_overlap's shortcut (exact by construction);
+//     * case A'' of pair_inter_is_zero for THIS term: the proof never looks at another term -- the term's own gap
+//       min(t(a), t(b)) - max(t(c), t(d)) (each t widened by 1e-6 like NmsAux does) replaces the boxes' gap, the bounds
+//       smax / sminx / kq of the boxes cover the term's vertices and its edge, and "no vertex of P within eps of an
+//       oriented edge line of Q" is needed for the term's own two vertices and its own edge only.
+struct TermPairCtx {
+    float kmin, rhs;  // of the pair; kmin == 0 disables the counter-clockwise case
+};
+__device__ __forceinline__ TermPairCtx term_pair_ctx(const NmsAux& P, const NmsAux& Q) {
+    TermPairCtx x;
+    x.kmin = 0.f;
+    x.rhs = 1.f;
+    if (P.ext < INFINITY && Q.kq > 0.f) {  // both boxes eligible (coordinates in [1, 1e7]), sminx is a valid bound
+        x.kmin = Q.kq / (Q.kq + 1.002f * (P.smax + Q.smax));
+        const float rho = Q.smax / P.sminx;
+        x.rhs = 2.4e-7f * (4.0f * P.smax / P.sminx + rho + 2.0f) + 5.0e-9f;
+    }
+    return x;
+}
+__device__ __forceinline__ bool term_is_zero(const TermPairCtx& x, P2 a, P2 b, P2 c, P2 d, float ta, float tb, float tc,
+                                             float td) {
+    const int s1 = sigf(a.x * b.y - b.x * a.y);  // == cross3(O, a, b): v - 0 is exact
+    const int s2 = sigf(c.x * d.y - d.x * c.y);
+    if (s1 == 0 || s2 == 0) return true;
+    if (s1 == -1) {
+        const P2 t = a;
+        a = b;
+        b = t;
+    }
+    if (s2 == -1) {
+        const P2 t = c;
+        c = d;
+        d = t;
+    }
+    const int ga = sigf(c.x * a.y - a.x * c.y), gb = sigf(c.x * b.y - b.x * c.y);
+    if (ga < 0 && gb < 0) return true;
+    if (!(x.kmin > 0.f)) return false;
+    const float gap0 = ((fminf(ta, tb) - 1.0e-6f) - (fmaxf(tc, td) + 1.0e-6f)) - 4.0e-6f;
+    if (!(gap0 > 0.f)) return false;
+    if (!(x.kmin * (0.5f * gap0 - 2.4e-7f) * 0.999f > x.rhs)) return false;
+    return sigf(cross3(c, d, a)) != 0 && sigf(cross3(c, d, b)) != 0;
+}
+__device__ __forceinline__ float vertex_t(float vx, float vy) { return (vy - vx) / (vx + vy); }
+
 }  // namespace dafne

@@ -67,6 +67,43 @@ __global__ void pair_filter_kernel(const float* __restrict__ p, const float* __r
     }
     fired[i] = (pair_inter_is_zero(P, Q, po, qo) && (P.area + Q.area) != 0.f) ? 1 : 0;
 }
+// Test hook for the per-term filter (polyiou.cuh::term_is_zero): per pair, bit k = 4 * i + j of `fired` says the filter
+// declared term (edge i of P, edge j of Q) zero, the same bit of `nonzero` that tri_overlap's value is not (+-)0.
+__global__ void term_filter_kernel(const float* __restrict__ p, const float* __restrict__ q,
+                                   unsigned short* __restrict__ fired, unsigned short* __restrict__ nonzero, int n) {
+    __shared__ float2 slots[9 * 64];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    float a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        a[k] = p[8 * idx + k];
+        b[k] = q[8 * idx + k];
+    }
+    const NmsAux P = nms_aux_of(a), Q = nms_aux_of(b);
+    const TermPairCtx ctx = term_pair_ctx(P, Q);
+    P2 pp[6], qq[6];
+    load_oriented(a, pp);
+    load_oriented(b, qq);
+    unsigned f = 0, nz = 0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            const P2 A = pp[i], B = pp[i + 1], Cc = qq[j], D = qq[j + 1];
+            if (term_is_zero(ctx, A, B, Cc, D, vertex_t(A.x, A.y), vertex_t(B.x, B.y), vertex_t(Cc.x, Cc.y),
+                             vertex_t(D.x, D.y)))
+                f |= 1u << (4 * i + j);
+            if (tri_overlap(A, B, Cc, D, slots + threadIdx.x, 64) != 0.f) nz |= 1u << (4 * i + j);
+        }
+    fired[idx] = static_cast<unsigned short>(f);
+    nonzero[idx] = static_cast<unsigned short>(nz);
+}
+int launch_term_filter(const float* p, const float* q, unsigned short* fired, unsigned short* nonzero, int n,
+                       cudaStream_t s) {
+    if (n <= 0) return 0;
+    term_filter_kernel<<<(n + 63) / 64, 64, 0, s>>>(p, q, fired, nonzero, n);
+    POST_CHECK_LAUNCH("term_filter_kernel");
+    return 0;
+}
 int launch_pair_filter(const float* p, const float* q, unsigned char* fired, int n, cudaStream_t s) {
     if (n <= 0) return 0;
     pair_filter_kernel<<<(n + 127) / 128, 128, 0, s>>>(p, q, fired, n);

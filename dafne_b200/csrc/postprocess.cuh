@@ -51,6 +51,8 @@ int launch_sort_quadrilateral(const float* quads, float* out, int n, cudaStream_
 int launch_poly_iou(const float* p, const float* q, float* iou, int n, cudaStream_t stream);
 // fired[i] = 1 where the NMS pre-filter claims IoU(p[i], q[i]) == 0 without running the clip (test hook).
 int launch_pair_filter(const float* p, const float* q, unsigned char* fired, int n, cudaStream_t stream);
+int launch_term_filter(const float* p, const float* q, unsigned short* fired, unsigned short* nonzero, int n,
+                       cudaStream_t stream);
 
 // Lazily evaluated greedy polygon NMS of N images (nms.cu). nmsbox [N][max_sel][8] sorted by descending score with the
 // class offsets applied, counts [N]; writes keep [N][max_sel] (kept positions, ascending) and nkeep [N].

@@ -201,6 +201,11 @@ int dafne_poly_iou(const float* dev_p, const float* dev_q, float* dev_iou, int n
  * higher-scored box, q[i] = the lower-scored one) because it can prove the faithful fp32 arithmetic yields IoU == 0.
  * Contract (tests/test_postprocess_gpu.py): fired[i] implies dafne_poly_iou gives exactly 0 for that pair. */
 int dafne_poly_pair_filter(const float* dev_p, const float* dev_q, uint8_t* dev_fired, int n, void* stream);
+/* Test hook for the per-TERM form of that filter: per pair, bit 4 * i + j of dev_fired = the filter declares the signed
+ * overlap of edge triangle i of p with edge triangle j of q (polyiou.cpp:91-103) exactly zero; the same bit of
+ * dev_nonzero = the faithful arithmetic's value of that term is not zero. Contract: (fired & nonzero) == 0. */
+int dafne_poly_term_filter(const float* dev_p, const float* dev_q, uint16_t* dev_fired, uint16_t* dev_nonzero, int n,
+                           void* stream);
 
 /* Class-aware polygon NMS of one image (ml_nms -> batched_nms_poly -> poly_gpu_nms semantics): polys [n,8], scores
  * [n], classes [n] int32, all on device. dev_keep receives the kept input indices in descending score order

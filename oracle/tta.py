@@ -40,11 +40,15 @@ def shortest_edge_size(h: int, w: int, size: int, max_size: int) -> Tuple[int, i
     return int(newh + 0.5), int(neww + 0.5)
 
 
-def chain_of_copy(h: int, w: int, min_size: int, max_size: int, flip: str = "") -> List[tuple]:
-    """The transform chain the mapper builds for one augmented copy (tta.py:96-135): resize, then an optional flip of
-    the RESIZED image."""
+def chain_of_copy(h: int, w: int, min_size: int, max_size: int, flip: str = "", orig_hw=None) -> List[tuple]:
+    """The transform chain the mapper builds for one augmented copy of an h x w input image (tta.py:69-135, detectron2
+    DatasetMapperTTA): `pre_tfm` from the ORIGINAL image (dataset_dict["height"], ["width"]) to the input tensor when
+    the two differ, the resize, then an optional flip of the RESIZED image."""
+    chain = []
+    if orig_hw is not None and tuple(orig_hw) != (h, w):
+        chain.append(("resize", orig_hw[0], orig_hw[1], h, w))
     nh, nw = shortest_edge_size(h, w, min_size, max_size)
-    chain = [("resize", h, w, nh, nw)]
+    chain.append(("resize", h, w, nh, nw))
     if flip == "h":
         chain.append(("hflip", nw))
     elif flip == "v":

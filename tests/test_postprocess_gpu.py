@@ -73,17 +73,14 @@ def _rot_rects_t(gen, n, wmin, wmax, aspect, cx, cy, dev):
     return torch.stack([x, y], 2).reshape(n, 8).float().contiguous()
 
 
-@pytest.mark.parametrize("regime", ["same_class", "cross_class", "near_margin", "angular_touch", "integer_grid",
-                                    "tiny_boxes", "huge_boxes", "near_origin", "degenerate"])
-def test_nms_prefilter_never_skips_a_nonzero_iou(regime):
-    """Contract of polyiou.cuh::pair_inter_is_zero: wherever the NMS skips the polygon clip, the faithful fp32
-    arithmetic (dafne_poly_iou == the oracle's float instantiation, bit for bit) yields EXACTLY 0 -- including the
-    class-offset regimes where fp32 IoU of disjoint boxes is noise (SURVEY appendix C). 4M pairs per regime."""
-    from dafne_b200.modeling import poly_iou
+REGIMES = ["same_class", "cross_class", "near_margin", "angular_touch", "integer_grid", "tiny_boxes", "huge_boxes",
+           "near_origin", "degenerate"]
 
+
+def _regime_pairs(regime, n=1 << 22):
+    """(p, q): n pairs of quadrilaterals [n, 8] on the device for one regime of the NMS filter tests."""
     dev = _dev()
     gen = torch.Generator(device=dev).manual_seed(sum(map(ord, regime)))
-    n = 1 << 22
     U = lambda lo, hi: torch.rand(n, generator=gen, device=dev) * (hi - lo) + lo  # noqa: E731
     span = 1100.0
     if regime == "same_class":
@@ -140,6 +137,17 @@ def test_nms_prefilter_never_skips_a_nonzero_iou(regime):
         q[1::3] = q[1::3, :2].repeat(1, 4)              # a single point
         k = torch.arange(2, n, 3, device=dev)           # a radial sliver: two vertices on one ray from the origin
         q[k, 2:4] = q[k, 0:2] * 1.25
+    return p, q
+
+
+@pytest.mark.parametrize("regime", REGIMES)
+def test_nms_prefilter_never_skips_a_nonzero_iou(regime):
+    """Contract of polyiou.cuh::pair_inter_is_zero: wherever the NMS skips the polygon clip, the faithful fp32
+    arithmetic (dafne_poly_iou == the oracle's float instantiation, bit for bit) yields EXACTLY 0 -- including the
+    class-offset regimes where fp32 IoU of disjoint boxes is noise (SURVEY appendix C). 4M pairs per regime."""
+    from dafne_b200.modeling import poly_iou
+
+    p, q = _regime_pairs(regime)
     fired = _pair_filter(p, q)
     iou = poly_iou(p, q)
     bad = fired & (iou != 0)
@@ -148,6 +156,34 @@ def test_nms_prefilter_never_skips_a_nonzero_iou(regime):
         assert fired.float().mean() > 0.3, f"{regime}: the filter should fire on most separated pairs"
     if regime == "near_origin":
         assert int((fired & (p.min(1).values < 1.0)).sum()) == 0  # boxes with a coordinate < 1 are never eligible
+
+
+def _term_filter(p, q):
+    import ctypes as C
+
+    from dafne_b200 import _capi
+
+    fired = torch.zeros(p.shape[0], dtype=torch.int16, device=p.device)
+    nonzero = torch.zeros(p.shape[0], dtype=torch.int16, device=p.device)
+    _capi.check(_capi.lib().dafne_poly_term_filter(p.data_ptr(), q.data_ptr(), fired.data_ptr(), nonzero.data_ptr(),
+                                                   p.shape[0], C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                "dafne_poly_term_filter")
+    return fired.to(torch.int32) & 0xFFFF, nonzero.to(torch.int32) & 0xFFFF
+
+
+@pytest.mark.parametrize("regime", REGIMES)
+def test_nms_term_filter_never_skips_a_nonzero_term(regime):
+    """Contract of polyiou.cuh::term_is_zero, the per-term form of the filter: a signed triangle overlap the NMS does
+    not evaluate is EXACTLY zero in the faithful fp32 arithmetic (the skipped terms enter the sum as +0). 2M pairs =
+    32M terms per regime, the same regimes as the pair filter (class offsets, near margins, degenerate quads)."""
+    p, q = _regime_pairs(regime, 1 << 21)
+    fired, nonzero = _term_filter(p, q)
+    bad = (fired & nonzero) != 0
+    assert int(bad.sum()) == 0, f"{regime}: {int(bad.sum())} pairs have a skipped term that is not zero"
+    live = 16 - torch.tensor([bin(v).count("1") for v in range(1 << 16)], device=p.device)[fired.long()]
+    if regime in ("same_class", "near_margin", "angular_touch"):
+        # the point of the filter: of the pairs whose wedges overlap, about half of the 16 terms are provably zero
+        assert live.float().mean() < 12.5, f"{regime}: {live.float().mean():.2f} of 16 terms left to clip"
 
 
 def _random_boxes(rng, n, span=400, ncls=15, small=False):

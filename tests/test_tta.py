@@ -41,8 +41,9 @@ def test_transforms_agree_with_the_oracle_restatement():
     cfg = _cfg(min_sizes=(96, 128, 200), max_size=180)
     g = torch.Generator().manual_seed(0)
     image = torch.randint(0, 256, (3, 100, 140), dtype=torch.uint8, generator=g)
-    copies = tta.DotaDatasetMapperTTA(cfg)({"image": image, "height": 100, "width": 140})
-    chains = [otta.chain_of_copy(100, 140, ms, 180, flip) for ms in (96, 128, 200) for flip in ("", "h", "v")]
+    copies = tta.DotaDatasetMapperTTA(cfg)({"image": image, "height": 300, "width": 420})
+    chains = [otta.chain_of_copy(100, 140, ms, 180, flip, orig_hw=(300, 420)) for ms in (96, 128, 200)
+              for flip in ("", "h", "v")]
     pts = rng.uniform(-5, 260, (64, 2)).astype(np.float32)
     for c, chain in zip(copies, chains):
         tfm = c["transforms"]
@@ -111,7 +112,8 @@ def test_tta_wrapper_equals_oracle_merge_of_the_copies():
     # the oracle applies ITS OWN restatement of the transforms: the chains are rebuilt from the mapper's configuration
     # (sizes and flips), not taken from the product's transform objects
     H, W = image.shape[1:]
-    chains = [otta.chain_of_copy(H, W, ms, 320, flip) for ms in (160, 192, 256) for flip in ("", "h", "v")]
+    chains = [otta.chain_of_copy(H, W, ms, 320, flip, orig_hw=(400, 512)) for ms in (160, 192, 256)
+              for flip in ("", "h", "v")]
     assert len(chains) == len(tfms)
     want_c, want_s, want_k, _ = otta.merge_detections(corners, scores, classes, chains, spec.nms_thresh,
                                                       spec.post_nms_topk, spec.vehicle_merge)
