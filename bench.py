@@ -391,7 +391,11 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            per = json.load(f).get("per_workload", {})
+        # the capture of the workload with this (depth, per-GPU batch, image size); null if none was taken
+        key = {(101, 32): "r101_b32", (50, 8): "r50_b8"}.get((spec.resnet_depth, batch))
+        if key in per and (H, W) == (1024, 1024):
+            traffic = per[key].get("dram_bytes_per_launch")
 
     line = None
     if rank == 0:

@@ -130,7 +130,8 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int lt) {
     TileCoord c;
     c.nt = lt % p.n_tiles;
-    const int mt = lt / p.n_tiles;
+    int mt = lt / p.n_tiles;
+    if (p.reverse_m) mt = p.m_tiles - 1 - mt;
     const int tx = mt % p.tiles_x;
     const int r = mt / p.tiles_x;
     c.x0 = tx * p.tw;
@@ -878,6 +879,7 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     p.n_tiles = (d.Cout + bn - 1) / bn;
     p.total_tiles = p.m_tiles * p.n_tiles;
     p.tile_begin = 0;
+    p.reverse_m = d.reverse_m;
     p.scale = d.scale;
     p.shift = d.shift;
     p.relu = d.relu;

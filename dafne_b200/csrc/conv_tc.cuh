@@ -36,6 +36,7 @@ struct ConvDesc {
     const float* scale = nullptr;  // per-Cout multiplier (folded FrozenBN), nullptr = 1
     const float* shift = nullptr;  // per-Cout addend (folded FrozenBN shift or conv bias), nullptr = 0
     int relu = 0;
+    int reverse_m = 0;  // walk the pixel tiles from the last to the first (see ConvParams::reverse_m)
     const __half* residual = nullptr;  // NHWC fp16 [N, res_H, res_W, Cout]; added at (y>>res_shift, x>>res_shift)
     int res_H = 0, res_W = 0, res_shift = 0;
     // [N][Cout/8][2] 64-bit fixed point, accumulated: (sum * 2^20, sum of squares * 2^12) of the fp16-rounded output
@@ -52,6 +53,10 @@ struct ConvParams {
     int tw, th, nb;
     int tiles_x, tiles_y, tiles_n, m_tiles, n_tiles, total_tiles;
     int tile_begin;  // index of this problem's first tile inside a grouped launch
+    // Pixel tiles in DESCENDING order: for a convolution whose input was written by the launch right before it and is
+    // larger than the 126 MB L2 -- conv1 of a bottleneck reading the previous block's 268 MB output -- the tail of that
+    // tensor is what L2 still holds, so reading it back to front turns the first third of the reads into L2 hits.
+    int reverse_m;
     int tap_view[9], tap_dy[9], tap_dx[9];
     const float* scale;
     const float* shift;

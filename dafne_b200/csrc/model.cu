@@ -9,6 +9,7 @@
 #include "model.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "elementwise.cuh"
@@ -304,6 +305,7 @@ struct Builder {
     double group_flops = 0, group_bytes = 0;
     std::string group_name;
     OpInfo group_info;
+    bool reverse_next = false;  // the next conv() walks its pixel tiles back to front (ConvParams::reverse_m)
 
     void begin_group(const std::string& name) {
         grouping = true;
@@ -425,6 +427,8 @@ struct Builder {
             d.res_shift = res_shift;
         }
         d.gn_sums = gn_sums;
+        d.reverse_m = reverse_next ? 1 : 0;
+        reverse_next = false;
         const bool single = !grouping;
         if (single) begin_group(L.parts[0].prefix);
         flops += 2.0 * in.N * d.Hout * d.Wout * (double)L.Cout * L.k * L.k * L.Cin;
@@ -595,6 +599,10 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
                 sc = B.conv(B.layer(pre + ".shortcut"), x, false);
                 own_sc = true;
             }
+            // conv1 reads the block input the previous block's conv3 has just written (268 MB at 32 x 1024^2 in res4,
+            // twice the L2): back to front, the part L2 still holds comes first. DAFNE_CONV_REVERSE=0: A/B switch.
+            static const bool reverse_on = !(getenv("DAFNE_CONV_REVERSE") && atoi(getenv("DAFNE_CONV_REVERSE")) == 0);
+            B.reverse_next = reverse_on && b > 0;
             Act a = B.conv(B.layer(pre + ".conv1"), x, true);
             Act m = B.conv(B.layer(pre + ".conv2"), a, true);
             B.free_act(a);
