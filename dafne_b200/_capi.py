@@ -84,6 +84,8 @@ _SIGNATURES = {
     ),
     "dafne_postprocess_scratch_bytes": (_i, [_vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]),
     "dafne_detect": (_i, [_vp, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _i, _vp]),
+    "dafne_graph_capture": (_i, [_vp, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i, _vp, _vp, _i, _vp]),
+    "dafne_graph_launch": (_i, [_vp, _vp]),
     "dafne_detect_host": (_i, [_vp, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _i, _vp]),
     "dafne_detect_host_begin": (_i, [_vp, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _i, _vp,
                                      C.POINTER(_i)]),

@@ -226,6 +226,72 @@ int dafne_detect(dafne_ctx* ctx, const void* images, int dtype, const int32_t* i
     return ctx_postprocess(ctx, image_sizes, output_sizes, 1, dets, counts, capacity, s);
 }
 
+int dafne_graph_capture(dafne_ctx* ctx, const void* images, int dtype, const int32_t* image_sizes,
+                        const int32_t* output_sizes, int do_postprocess, float* dets, int32_t* counts, int capacity,
+                        void* stream) {
+    NEED_CTX(ctx, "dafne_graph_capture");
+    if (!ctx->ws) {
+        set_error("dafne_graph_capture: no workspace bound");
+        return -1;
+    }
+    if (ctx->profiling) {
+        set_error("dafne_graph_capture: per-launch profiling is on (events cannot be captured)");
+        return -1;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // one eager step first: lazily configured kernel attributes / occupancy queries happen outside the capture
+    if (ctx_forward(ctx, images, dtype, image_sizes, s)) return -1;
+    if (ctx_postprocess(ctx, image_sizes, output_sizes, do_postprocess, dets, counts, capacity, s)) return -1;
+    const int64_t l0 = ctx->stat_launches;
+    const double f0 = ctx->stat_flops;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        set_error("dafne_graph_capture: cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    int rc = ctx_forward(ctx, images, dtype, image_sizes, s);
+    if (rc == 0) rc = ctx_postprocess(ctx, image_sizes, output_sizes, do_postprocess, dets, counts, capacity, s);
+    e = cudaStreamEndCapture(s, &graph);
+    if (rc != 0 || e != cudaSuccess || graph == nullptr) {
+        if (rc == 0) set_error("dafne_graph_capture: cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        if (graph) cudaGraphDestroy(graph);
+        return -1;
+    }
+    if (ctx->graph_exec) {
+        cudaGraphExecDestroy(ctx->graph_exec);
+        ctx->graph_exec = nullptr;
+    }
+    e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        ctx->graph_exec = nullptr;
+        set_error("dafne_graph_capture: cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    ctx->graph_launches = ctx->stat_launches - l0;  // what the captured step issued
+    ctx->graph_flops = ctx->stat_flops - f0;
+    ctx->stat_launches = l0;  // the capture itself ran nothing
+    ctx->stat_flops = f0;
+    return 0;
+}
+
+int dafne_graph_launch(dafne_ctx* ctx, void* stream) {
+    NEED_CTX(ctx, "dafne_graph_launch");
+    if (!ctx->graph_exec) {
+        set_error("dafne_graph_launch: no captured step (call dafne_graph_capture after dafne_bind_workspace)");
+        return -1;
+    }
+    cudaError_t e = cudaGraphLaunch(ctx->graph_exec, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) {
+        set_error("dafne_graph_launch: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    ctx->stat_launches += ctx->graph_launches;
+    ctx->stat_flops += ctx->graph_flops;
+    return 0;
+}
+
 int dafne_detect_host(dafne_ctx* ctx, const void* host_images, int dtype, const int32_t* image_sizes,
                       const int32_t* output_sizes, float* host_dets, int32_t* host_counts, int capacity,
                       void* stream) {

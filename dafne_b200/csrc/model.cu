@@ -196,6 +196,7 @@ void ctx_destroy(dafne_ctx* c) {
     if (c->stem_scale) cudaFree(c->stem_scale);
     if (c->stem_shift) cudaFree(c->stem_shift);
     if (c->scales_dev) cudaFree(c->scales_dev);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     for (int k = 0; k < 2; ++k) {
@@ -511,6 +512,10 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     B.c = c;
     B.base = base;
     if (base) {
+        if (c->graph_exec) {  // a captured step refers to the old plan's buffers
+            cudaGraphExecDestroy(c->graph_exec);
+            c->graph_exec = nullptr;
+        }
         c->ops.clear();
         c->named.clear();
         c->op_info.clear();

@@ -116,6 +116,10 @@ struct dafne_ctx {
     // debugging / per-layer parity: keep every activation alive and addressable by name
     bool keep_activations = false;
     std::unordered_map<std::string, dafne::Act> named;
+    // dafne_graph_capture / _launch: one whole step (dense forward + post-processing) as an instantiated CUDA graph
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t graph_launches = 0;  // kernel launches one replay stands for
+    double graph_flops = 0;
     // counters
     int64_t stat_launches = 0;
     double stat_flops = 0;

@@ -183,6 +183,34 @@ class DafneEngine:
         self.forward_dense(images, image_sizes)
         return self.postprocess(image_sizes, output_sizes, do_postprocess, capacity, out)
 
+    def capture(self, images: torch.Tensor, image_sizes, output_sizes=None, do_postprocess=True,
+                capacity: Optional[int] = None, out: Optional[DetectionWire] = None):
+        """Capture the whole step as one CUDA graph bound to THESE tensors (`images` is read, `out` written on every
+        `replay()`; the caller refreshes the contents of `images` in place). Returns (dets, counts) views of `out`."""
+        N, _, H, W = images.shape
+        self.bind(N, H, W)
+        cap = capacity or (self.spec.post_nms_topk + 64)
+        out = out if out is not None else DetectionWire(N, cap, self.device)
+        dtype = {torch.uint8: 0, torch.float32: 1}[images.dtype]
+        sizes = _i32_array([v for hw in image_sizes for v in hw])
+        osz = _i32_array([v for hw in (output_sizes or image_sizes) for v in hw])
+        # stream capture is not allowed on the legacy default stream: capture on a side stream ordered after the
+        # current one (the replay may go to any stream)
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            _capi.check(self.lib.dafne_graph_capture(self._ctx, images.data_ptr(), dtype, sizes, osz,
+                                                     int(do_postprocess), out.dets.data_ptr(), out.counts.data_ptr(),
+                                                     cap, _capi.stream_ptr()), "dafne_graph_capture")
+        cur.wait_stream(side)
+        self._graph_refs = (images, out)  # the graph holds raw pointers into these
+        return out.dets, out.counts
+
+    def replay(self) -> None:
+        """One step = one cudaGraphLaunch on the current stream."""
+        _capi.check(self.lib.dafne_graph_launch(self._ctx, _capi.stream_ptr()), "dafne_graph_launch")
+
     def _check_host_buffers(self, host_images, host_dets, host_counts, N, cap):
         """The C side copies N * cap * 20 floats packed at row stride `cap`, asynchronously: shapes must match
         exactly, the tensors must be contiguous, and pinned (a pageable buffer would make the copies synchronous and

@@ -257,7 +257,11 @@ class DotaDatasetMapperTTA:
 
 # ------------------------------------------------------------------------------------------------ model (tta.py:138-268)
 class OneStageRCNNWithTTA(nn.Module):
-    def __init__(self, cfg, model, tta_mapper: Optional[Callable] = None, batch_size: int = 3):
+    def __init__(self, cfg, model, tta_mapper: Optional[Callable] = None, batch_size: int = 3,
+                 use_cuda_graphs: bool = True):
+        """`use_cuda_graphs` (not in the reference): replay each augmented shape as one captured CUDA graph -- the copies
+        of every image of a dataset repeat the same shapes and sizes, and at batch 3 a step is bound by the host's
+        ~200 launches, not by the GPU."""
         super().__init__()
         from .modeling import OneStageDetector
 
@@ -267,6 +271,7 @@ class OneStageRCNNWithTTA(nn.Module):
         self.model = model
         self.tta_mapper = DotaDatasetMapperTTA(cfg) if tta_mapper is None else tta_mapper
         self.batch_size = batch_size
+        self.use_cuda_graphs = use_cuda_graphs
 
     def _batch_inference(self, batched_inputs, detected_instances=None):
         outputs = []
@@ -300,8 +305,25 @@ class OneStageRCNNWithTTA(nn.Module):
         tfms = [x.pop("transforms") for x in augmented_inputs]
         return augmented_inputs, tfms
 
+    def _batch_inference_deferred(self, batched_inputs):
+        """`_batch_inference` without its host sync per batch: every batch of `batch_size` copies is enqueued first (one
+        engine per copy shape, so nothing waits on anything but the stream), then the result sizes of all of them come
+        back in one copy. Same batches, same kernels, same results as `_batch_inference`."""
+        launched, inputs = [], []
+        saved = self.model.use_cuda_graphs
+        self.model.use_cuda_graphs = self.use_cuda_graphs
+        try:
+            for idx, inp in zip(count(), batched_inputs):
+                inputs.append(inp)
+                if len(inputs) == self.batch_size or idx == len(batched_inputs) - 1:
+                    launched.append(self.model._launch(inputs, do_postprocess=False))
+                    inputs = []
+        finally:
+            self.model.use_cuda_graphs = saved
+        return [o for batch in self.model._collect(launched) for o in batch]
+
     def _get_augmented_corners(self, augmented_inputs, tfms):
-        outputs = self._batch_inference(augmented_inputs)
+        outputs = self._batch_inference_deferred(augmented_inputs)
         instances_list = []
         for output, tfm in zip(outputs, tfms):
             instances = output["instances"]

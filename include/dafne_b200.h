@@ -117,6 +117,16 @@ int dafne_postprocess_scratch_bytes(dafne_ctx* ctx, int N, const int32_t* level_
 int dafne_detect(dafne_ctx* ctx, const void* dev_images, int dtype, const int32_t* image_sizes,
                  const int32_t* output_sizes, float* dev_dets, int32_t* dev_counts, int capacity, void* stream);
 
+/* The same step as ONE instantiated CUDA graph (the launch list of a bound shape is static: dense forward, the fixed
+ * sequence of post-processing / NMS panel launches). dafne_graph_capture runs the step once eagerly, then captures it
+ * for exactly these buffers and sizes; dafne_graph_launch replays it on `stream` (new image CONTENTS in the same
+ * dev_images buffer, results in the same dev_dets / dev_counts). Re-binding the workspace drops the graph. What it
+ * buys is host time: one call instead of ~200 launches -- small batches (batch 1-3, TTA copies) are launch-bound. */
+int dafne_graph_capture(dafne_ctx* ctx, const void* dev_images, int dtype, const int32_t* image_sizes,
+                        const int32_t* output_sizes, int do_postprocess, float* dev_dets, int32_t* dev_counts,
+                        int capacity, void* stream);
+int dafne_graph_launch(dafne_ctx* ctx, void* stream);
+
 /* The reference-facing call with HOST buffers: copies images H2D, runs dafne_detect, copies detections and counts
  * D2H and synchronises `stream`. host_images should be pinned for full copy bandwidth. */
 int dafne_detect_host(dafne_ctx* ctx, const void* host_images, int dtype, const int32_t* image_sizes,

@@ -151,3 +151,61 @@ def test_unsupported_config_fails_loudly():
     cfg.MODEL.DAFNE.CORNER_PREDICTION = "direct"
     with pytest.raises(NotImplementedError):
         build_model(cfg)
+
+
+def test_graph_replay_equals_eager_step(model):
+    """dafne_graph_capture / _launch: the step replayed as one CUDA graph returns the eager step's bits, and follows new
+    image contents written into the captured input buffer."""
+    from dafne_b200.engine import DafneEngine, DetectionWire
+
+    eng = DafneEngine(model.spec, torch.device("cuda:0"))
+    eng.load_state_dict(model.state_dict())
+    g = torch.Generator().manual_seed(21)
+    a = torch.randint(0, 256, (2, 3, 192, 256), dtype=torch.uint8, generator=g).cuda()
+    b = torch.randint(0, 256, (2, 3, 192, 256), dtype=torch.uint8, generator=g).cuda()
+    sizes = [(192, 256), (180, 250)]
+    want_a = [t.clone() for t in eng.detect(a, sizes)]
+    want_b = [t.clone() for t in eng.detect(b, sizes)]
+    buf = a.clone()
+    wire = DetectionWire(2, model.spec.post_nms_topk + 64, torch.device("cuda:0"))
+    dets, counts = eng.capture(buf, sizes, out=wire)
+    eng.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(counts, want_a[1]) and torch.equal(dets, want_a[0])
+    buf.copy_(b)
+    eng.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(counts, want_b[1]) and torch.equal(dets, want_b[0])
+    assert int(counts.min()) > 0
+    launches, _ = eng.stats()
+    assert launches > 4 * 100  # two eager steps, the capture's eager step and two replays are all accounted for
+    eng.close()
+
+
+def test_tta_deferred_batches_equal_the_per_batch_path(model):
+    """OneStageRCNNWithTTA enqueues all batches before its one host sync: same outputs as the reference-shaped
+    `_batch_inference` (one sync per batch)."""
+    from dafne_b200 import tta
+
+    cfg = model.cfg.clone() if hasattr(model.cfg, "clone") else model.cfg
+    wrapper = tta.OneStageRCNNWithTTA(cfg, model)
+    g = torch.Generator().manual_seed(5)
+    inputs = [{"image": torch.randint(0, 256, (3, 160 + 32 * (k // 3), 192), dtype=torch.uint8, generator=g),
+               "height": 320, "width": 384} for k in range(7)]
+    a = wrapper._batch_inference(inputs)
+    assert wrapper.use_cuda_graphs
+    b = wrapper._batch_inference_deferred(inputs)  # captures one graph per batch shape
+    c = wrapper._batch_inference_deferred(inputs)  # replays them
+    # other image contents through the captured graphs, then the first ones again
+    other = [{**d, "image": torch.randint(0, 256, tuple(d["image"].shape), dtype=torch.uint8, generator=g)} for d in inputs]
+    o_eager = wrapper._batch_inference(other)
+    o_graph = wrapper._batch_inference_deferred(other)
+    assert len(a) == len(b) == len(c) == 7
+    for x, y, z in zip(a + o_eager, b + o_graph, c + o_graph):
+        for w in (y, z):
+            assert torch.equal(x["instances"].pred_corners, w["instances"].pred_corners)
+            assert torch.equal(x["instances"].scores, w["instances"].scores)
+            assert torch.equal(x["instances"].pred_boxes.tensor, w["instances"].pred_boxes.tensor)
+            assert x["instances"].image_size == w["instances"].image_size
+    assert not torch.equal(a[0]["instances"].scores, o_eager[0]["instances"].scores)
+    assert model.use_cuda_graphs is False  # the wrapper restores the model's own setting
