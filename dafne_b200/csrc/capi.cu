@@ -8,6 +8,7 @@
 #include "elementwise.cuh"
 #include "merge_nms.cuh"
 #include "resize.cuh"
+#include "tail_tc.cuh"
 #include "model.cuh"
 #include "postprocess.cuh"
 #include <string.h>
@@ -79,6 +80,47 @@ int dafne_conv_nhwc(const void* in, int N, int H, int W, int Cin, const void* w,
     return conv_group_launch(dev_prob, 1, plan.prob.p.total_tiles, plan.block_n, plan.epi_wgs, plan.mode, plan.res_tma, plan.row_shared,
                              plan.breg_bytes,
                              num_sms_cached(), s);
+}
+
+int dafne_bottleneck_tail_nhwc(const void* in, int N, int H, int W, int K1, const void* w3, int N1, const float* scale1,
+                               const float* shift1, const void* residual, void* out, const void* w1, int N2,
+                               const float* scale2, const float* shift2, void* mid, void* stream) {
+    if (!in || !w3 || !residual || !out || !w1 || !mid || !scale1 || !shift1 || !scale2 || !shift2) {
+        set_error("dafne_bottleneck_tail_nhwc: null argument");
+        return -1;
+    }
+    TailDesc d;
+    d.in = static_cast<const __half*>(in);
+    d.N = N;
+    d.H = H;
+    d.W = W;
+    d.K1 = K1;
+    d.w3 = static_cast<const __half*>(w3);
+    d.N1 = N1;
+    d.scale1 = scale1;
+    d.shift1 = shift1;
+    d.residual = static_cast<const __half*>(residual);
+    d.out = static_cast<__half*>(out);
+    d.w1 = static_cast<const __half*>(w1);
+    d.N2 = N2;
+    d.scale2 = scale2;
+    d.shift2 = shift2;
+    d.mid = static_cast<__half*>(mid);
+    TailPlan plan;
+    if (tail_plan_build(d, &plan, num_sms_cached())) return -1;
+    // test / A-B hook: the problem descriptor goes through a small per-thread device buffer (synchronous upload)
+    static thread_local TailProblem* dev_prob = nullptr;
+    if (!dev_prob && cudaMalloc(&dev_prob, sizeof(TailProblem)) != cudaSuccess) {
+        set_error("dafne_bottleneck_tail_nhwc: cudaMalloc of the problem descriptor failed");
+        return -1;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaStreamSynchronize(s) != cudaSuccess ||
+        cudaMemcpy(dev_prob, &plan.prob, sizeof(TailProblem), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("dafne_bottleneck_tail_nhwc: descriptor upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    return tail_plan_launch(dev_prob, plan, s);
 }
 
 int dafne_gn_relu_nhwc(const void* in, void* out, int N, int HW, int C, int groups, const int64_t* sums,

@@ -766,8 +766,8 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, CUtensorMapL2promotion promo, const char* what) {
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, CUtensorMapL2promotion promo, const char* what) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return -1;
     cuuint64_t gdim[5];

@@ -94,6 +94,10 @@ struct ConvPlan {
     double flops;  // 2*MACs, algorithmic (unpadded)
 };
 
+// fp16 tiled tensor map with 128-byte swizzle (shared with tail_tc.cu)
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, CUtensorMapL2promotion promo, const char* what);
+
 inline void conv_out_dims(ConvDesc& d) {
     int pad = d.ksize / 2;
     d.Hout = (d.Hin + 2 * pad - d.ksize) / d.stride + 1;

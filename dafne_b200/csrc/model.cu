@@ -14,6 +14,7 @@
 
 #include "elementwise.cuh"
 #include "stem_tc.cuh"
+#include "tail_tc.cuh"
 
 namespace dafne {
 
@@ -290,6 +291,7 @@ int ctx_finalize(dafne_ctx* c, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------ plan
 namespace {
 constexpr size_t kMaxPlanProblems = 512;
+constexpr size_t kMaxTailProblems = 40;  // bottleneck tails (conv3 + next conv1): 2 + 3 + 22 for ResNet-101
 struct Builder {
     dafne_ctx* c;
     uint8_t* base;  // nullptr = dry run (size query)
@@ -307,6 +309,8 @@ struct Builder {
     std::string group_name;
     OpInfo group_info;
     bool reverse_next = false;  // the next conv() walks its pixel tiles back to front (ConvParams::reverse_m)
+    std::vector<TailProblem> tails;
+    TailProblem* dev_tails = nullptr;
 
     void begin_group(const std::string& name) {
         grouping = true;
@@ -391,6 +395,51 @@ struct Builder {
         return base ? reinterpret_cast<T*>(base + off) : nullptr;
     }
     const ConvLayer& layer(const std::string& prefix) { return c->convs[c->conv_index.at(prefix)]; }
+
+    // Bottleneck tail (tail_tc.cu): out = relu(bn3(conv3(in)) + sc) and mid = relu(bn1'(conv1'(out))) in one launch
+    void tail(const ConvLayer& L3, const ConvLayer& L1, const Act& in, const Act& sc, Act* out, Act* mid,
+              const std::string& nm) {
+        *out = new_act(in.N, in.H, in.W, L3.Cout);
+        *mid = new_act(in.N, in.H, in.W, L1.Cout);
+        ++launches;
+        const double fl = 2.0 * in.N * in.H * in.W * ((double)L3.Cout * L3.Cin + (double)L1.Cout * L1.Cin);
+        flops += fl;
+        if (!base || failed) return;
+        if (in.C != L3.Cin || sc.C != L3.Cout || L1.Cin != L3.Cout || tails.size() >= kMaxTailProblems) {
+            set_error("plan: bottleneck tail '%s' has inconsistent shapes", nm.c_str());
+            failed = true;
+            return;
+        }
+        TailDesc d;
+        d.in = in.p;
+        d.N = in.N;
+        d.H = in.H;
+        d.W = in.W;
+        d.K1 = L3.Cin;
+        d.w3 = L3.w;
+        d.N1 = L3.Cout;
+        d.scale1 = L3.scale;
+        d.shift1 = L3.shift;
+        d.residual = sc.p;
+        d.out = out->p;
+        d.w1 = L1.w;
+        d.N2 = L1.Cout;
+        d.scale2 = L1.scale;
+        d.shift2 = L1.shift;
+        d.mid = mid->p;
+        TailPlan plan;
+        if (tail_plan_build(d, &plan, c->num_sms)) {
+            failed = true;
+            return;
+        }
+        const TailProblem* dp = dev_tails + tails.size();
+        tails.push_back(plan.prob);
+        c->ops.push_back([dp, plan](cudaStream_t s) { return tail_plan_launch(dp, plan, s); });
+        const double px = (double)in.N * in.H * in.W;
+        info(nm.size() > 46 ? nm.substr(nm.size() - 46).c_str() : nm.c_str(), 1, fl,
+             px * 2.0 * (L3.Cin + 2.0 * L3.Cout + L1.Cout) + 2.0 * ((double)L3.Cout * L3.Cin + (double)L1.Cout * L1.Cin),
+             128, 1, 1, L3.Cin, L3.Cout, in.H, in.W);
+    }
 
     // out = epilogue(conv(in)); allocates the fp16 output unless out_f32 is given
     Act conv(const ConvLayer& L, const Act& in, bool relu, const Act* residual = nullptr, int res_shift = 0,
@@ -537,6 +586,7 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     }
     int32_t* sizes_dev = B.persistent<int32_t>(static_cast<size_t>(N) * 4 * sizeof(int32_t));
     B.dev_probs = B.persistent<ConvProblem>(kMaxPlanProblems * sizeof(ConvProblem));
+    B.dev_tails = B.persistent<TailProblem>(kMaxTailProblems * sizeof(TailProblem));
     const size_t sums_per = static_cast<size_t>(N) * 32 * 2 * sizeof(long long);
     const size_t sums_bytes = sums_per * 3 * 4 * 5;
     long long* sums_all = B.persistent<long long>(sums_bytes);
@@ -595,7 +645,13 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     // ---- bottlenecks
     const int* nb = stage_blocks(sp.resnet_depth);
     Act feats[3];
+    // Which stages run conv3 + the next block's conv1 as one fused tail launch: bit (s - 2) of DAFNE_CONV_TAIL
+    // (default 3 = res2 and res3; 0 = every 1x1 is its own launch; 7 adds res4, where the fused form is SLOWER: the
+    // two weight matrices, 1 MB per 128-pixel tile, are re-streamed from L2 faster than a 64 KB ring can pull them).
+    static const int tail_mask = getenv("DAFNE_CONV_TAIL") ? atoi(getenv("DAFNE_CONV_TAIL")) : 3;
     for (int s = 2; s <= 5; ++s) {
+        Act next_a;  // conv1 output of the NEXT block when the previous block's tail has already produced it
+        bool have_a = false;
         for (int b = 0; b < nb[s - 2]; ++b) {
             const std::string pre = kBU + "res" + std::to_string(s) + "." + std::to_string(b);
             Act sc = x;
@@ -604,14 +660,32 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
                 sc = B.conv(B.layer(pre + ".shortcut"), x, false);
                 own_sc = true;
             }
-            // conv1 reads the block input the previous block's conv3 has just written (268 MB at 32 x 1024^2 in res4,
-            // twice the L2): back to front, the part L2 still holds comes first. DAFNE_CONV_REVERSE=0: A/B switch.
-            static const bool reverse_on = !(getenv("DAFNE_CONV_REVERSE") && atoi(getenv("DAFNE_CONV_REVERSE")) == 0);
-            B.reverse_next = reverse_on && b > 0;
-            Act a = B.conv(B.layer(pre + ".conv1"), x, true);
+            Act a;
+            if (have_a) {
+                a = next_a;
+                have_a = false;
+            } else {
+                // conv1 reads the block input the previous block's conv3 has just written (268 MB at 32 x 1024^2 in
+                // res4, twice the L2): back to front, the part L2 still holds comes first. DAFNE_CONV_REVERSE=0: A/B.
+                static const bool reverse_on = !(getenv("DAFNE_CONV_REVERSE") && atoi(getenv("DAFNE_CONV_REVERSE")) == 0);
+                B.reverse_next = reverse_on && b > 0;
+                a = B.conv(B.layer(pre + ".conv1"), x, true);
+            }
             Act m = B.conv(B.layer(pre + ".conv2"), a, true);
             B.free_act(a);
-            Act o = B.conv(B.layer(pre + ".conv3"), m, true, &sc, 0);
+            Act o;
+            const ConvLayer& L3 = B.layer(pre + ".conv3");
+            bool fused = false;
+            if (((tail_mask >> (s - 2)) & 1) && b + 1 < nb[s - 2]) {
+                const ConvLayer& L1n = B.layer(kBU + "res" + std::to_string(s) + "." + std::to_string(b + 1) + ".conv1");
+                if (L1n.stride == 1 && L1n.k == 1 && tail_supported(L3.Cin, L3.Cout, L1n.Cout)) {
+                    // conv3 of this block + conv1 of the next one: the block output is written once, never read back
+                    B.tail(L3, L1n, m, sc, &o, &next_a, pre + ".conv3+next.conv1");
+                    have_a = true;
+                    fused = true;
+                }
+            }
+            if (!fused) o = B.conv(L3, m, true, &sc, 0);
             B.free_act(m);
             if (own_sc) B.free_act(sc);
             B.free_act(x);  // block input (== sc for b > 0)
@@ -755,6 +829,8 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     if (base) {
         // the kernels read their problem descriptors (tensor maps + parameters) from device memory
         CUDA_OK(cudaMemcpy(B.dev_probs, B.probs.data(), B.probs.size() * sizeof(ConvProblem), cudaMemcpyHostToDevice));
+        if (!B.tails.empty())
+            CUDA_OK(cudaMemcpy(B.dev_tails, B.tails.data(), B.tails.size() * sizeof(TailProblem), cudaMemcpyHostToDevice));
     }
 
     if (needed) *needed = B.arena.peak;

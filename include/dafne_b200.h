@@ -196,6 +196,16 @@ int dafne_conv_nhwc(const void* dev_in_f16, int N, int H, int W, int Cin, const 
                     const void* dev_residual_f16, int res_H, int res_W, int res_shift, int64_t* dev_gn_sums,
                     void* dev_out_f16, float* dev_out_f32, int out_ld, void* stream);
 
+/* Bottleneck tail through the two-GEMM tcgen05 kernel (csrc/tail_tc.cu): conv3 + FrozenBN + shortcut + ReLU of one
+ * detectron2 BottleneckBlock and conv1 + FrozenBN + ReLU of the next one, both 1x1 / stride 1, in ONE launch:
+ *   out = relu(scale1 * (in x w3^T) + shift1 + residual)   in [N,H,W,K1], w3 [N1][K1], residual / out [N,H,W,N1]
+ *   mid = relu(scale2 * (out x w1^T) + shift2)              w1 [N2][N1], mid [N,H,W,N2]
+ * K1 in {64,128,256}, N1 a multiple of 256, N2 in {64,128,256}; NHWC fp16 tensors, fp32 scale / shift. */
+int dafne_bottleneck_tail_nhwc(const void* dev_in_f16, int N, int H, int W, int K1, const void* dev_w3_f16, int N1,
+                               const float* dev_scale1, const float* dev_shift1, const void* dev_residual_f16,
+                               void* dev_out_f16, const void* dev_w1_f16, int N2, const float* dev_scale2,
+                               const float* dev_shift2, void* dev_mid_f16, void* stream);
+
 /* GroupNorm apply + ReLU on NHWC fp16 from per-(image, group) sums produced by dafne_conv_nhwc. */
 int dafne_gn_relu_nhwc(const void* dev_in_f16, void* dev_out_f16, int N, int HW, int C, int groups,
                        const int64_t* dev_gn_sums, const float* dev_gamma, const float* dev_beta, float eps,

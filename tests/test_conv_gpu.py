@@ -155,3 +155,63 @@ def test_gn_relu_matches_torch():
     assert st == 0, lib.dafne_last_error()
     ref = F.relu(F.group_norm(x.float(), 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
     assert torch.allclose(out.float(), ref, rtol=2e-3, atol=2e-3)
+
+
+TAIL_CASES = [
+    # name, N, H, W, K1, N1, N2: the bottleneck tails of res2 / res3 / res4, ragged sizes, several tiles per CTA
+    ("res2_64_256_64", 2, 64, 64, 64, 256, 64),
+    ("res3_128_512_128", 2, 48, 40, 128, 512, 128),
+    ("res4_256_1024_256", 3, 32, 32, 256, 1024, 256),
+    ("res4_odd_25x19", 2, 25, 19, 256, 1024, 256),
+    ("res4_multiwave", 8, 64, 64, 256, 1024, 256),
+    ("res3_multiwave", 2, 128, 128, 128, 512, 128),
+    ("res2_small_7x5_n3", 3, 7, 5, 64, 256, 64),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", TAIL_CASES, ids=[c[0] for c in TAIL_CASES])
+def test_bottleneck_tail_matches_two_torch_convs(case):
+    """csrc/tail_tc.cu: conv3 + BN + shortcut + ReLU and the next block's conv1 + BN + ReLU in one two-GEMM launch, against
+    torch fp32 on the same fp16 inputs -- `out` rounded to fp16 before it feeds the second product (as through HBM)."""
+    from dafne_b200 import _capi
+
+    lib = _capi.lib()
+    name, N, H, W, K1, N1, N2 = case
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(len(name))
+    x = torch.randn(N, K1, H, W, generator=g).half()
+    w3 = (torch.randn(N1, K1, 1, 1, generator=g) / K1 ** 0.5).half()
+    w1 = (torch.randn(N2, N1, 1, 1, generator=g) / N1 ** 0.5).half()
+    s1, b1 = torch.rand(N1, generator=g) * 0.5 + 0.25, torch.randn(N1, generator=g) * 0.5
+    s2, b2 = torch.rand(N2, generator=g) + 0.5, torch.randn(N2, generator=g) * 0.5
+    res = torch.randn(N, N1, H, W, generator=g).half()
+
+    def nhwc(t):
+        return t.to(dev).permute(0, 2, 3, 1).contiguous()
+
+    x_d, res_d = nhwc(x), nhwc(res)
+    w3_d, w1_d = w3.to(dev).reshape(N1, K1).contiguous(), w1.to(dev).reshape(N2, N1).contiguous()
+    s1_d, b1_d, s2_d, b2_d = (t.to(dev).contiguous() for t in (s1, b1, s2, b2))
+    out_d = torch.full((N, H, W, N1), float("nan"), device=dev, dtype=torch.float16)
+    mid_d = torch.full((N, H, W, N2), float("nan"), device=dev, dtype=torch.float16)
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    _capi.check(lib.dafne_bottleneck_tail_nhwc(vp(x_d), N, H, W, K1, vp(w3_d), N1, vp(s1_d), vp(b1_d), vp(res_d),
+                                               vp(out_d), vp(w1_d), N2, vp(s2_d), vp(b2_d), vp(mid_d),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                "dafne_bottleneck_tail_nhwc")
+    torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xr, rr = x.to(dev).float(), res.to(dev).float()
+    ref_out = F.relu(F.conv2d(xr, w3.to(dev).float()) * s1_d.view(1, -1, 1, 1) + b1_d.view(1, -1, 1, 1) + rr)
+    got_out = out_d.permute(0, 3, 1, 2).float()
+    assert torch.isfinite(got_out).all()
+    err = (got_out - ref_out).abs()
+    assert bool((err <= 2e-3 * ref_out.abs().max() + 2e-3 * ref_out.abs()).all()), f"out: max err {err.max().item()}"
+    # the second product sees the fp16-rounded block output the kernel itself wrote
+    ref_mid = F.relu(F.conv2d(got_out, w1.to(dev).float()) * s2_d.view(1, -1, 1, 1) + b2_d.view(1, -1, 1, 1))
+    got_mid = mid_d.permute(0, 3, 1, 2).float()
+    assert torch.isfinite(got_mid).all()
+    err = (got_mid - ref_mid).abs()
+    assert bool((err <= 2e-3 * ref_mid.abs().max() + 2e-3 * ref_mid.abs()).all()), f"mid: max err {err.max().item()}"
