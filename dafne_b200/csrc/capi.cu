@@ -82,6 +82,47 @@ int dafne_conv_nhwc(const void* in, int N, int H, int W, int Cin, const void* w,
                              num_sms_cached(), s);
 }
 
+int dafne_conv_gn_in_nhwc(const void* in_raw, int N, int H, int W, int Cin, const int64_t* in_gn_sums,
+                          const float* in_gamma, const float* in_beta, const void* w, int Cout, const float* shift,
+                          int64_t* gn_sums, void* out_f16, void* stream) {
+    if (!in_raw || !w || !out_f16 || !in_gn_sums || !in_gamma || !in_beta || !gn_sums) {
+        set_error("dafne_conv_gn_in_nhwc: null argument");
+        return -1;
+    }
+    ConvDesc d;
+    d.in = static_cast<const __half*>(in_raw);
+    d.N = N;
+    d.Hin = H;
+    d.Win = W;
+    d.Cin = Cin;
+    d.w = static_cast<const __half*>(w);
+    d.Cout = Cout;
+    d.ksize = 3;
+    d.stride = 1;
+    conv_out_dims(d);
+    d.out = static_cast<__half*>(out_f16);
+    d.shift = shift;
+    d.gn_sums = reinterpret_cast<long long*>(gn_sums);
+    d.in_gn_sums = reinterpret_cast<const long long*>(in_gn_sums);
+    d.in_gamma = in_gamma;
+    d.in_beta = in_beta;
+    ConvPlan plan;
+    if (conv_plan_build(d, &plan, num_sms_cached())) return -1;
+    static thread_local ConvProblem* dev_prob = nullptr;
+    if (!dev_prob && cudaMalloc(&dev_prob, sizeof(ConvProblem)) != cudaSuccess) {
+        set_error("dafne_conv_gn_in_nhwc: cudaMalloc of the problem descriptor failed");
+        return -1;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaStreamSynchronize(s) != cudaSuccess ||
+        cudaMemcpy(dev_prob, &plan.prob, sizeof(ConvProblem), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("dafne_conv_gn_in_nhwc: descriptor upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    return conv_group_launch(dev_prob, 1, plan.prob.p.total_tiles, plan.block_n, plan.epi_wgs, plan.mode, plan.res_tma,
+                             plan.row_shared, plan.breg_bytes, num_sms_cached(), s);
+}
+
 int dafne_bottleneck_tail_nhwc(const void* in, int N, int H, int W, int K1, const void* w3, int N1, const float* scale1,
                                const float* shift1, const void* residual, void* out, const void* w1, int N2,
                                const float* scale2, const float* shift2, void* mid, void* stream) {

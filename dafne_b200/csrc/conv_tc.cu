@@ -75,9 +75,17 @@ struct ConvCfg {
     static constexpr int STAGE_BYTES_HALO = A_HALO_BYTES + 9 * B_BYTES;
     // mode 3 = halo box with the whole weight tensor of the problem RESIDENT in shared memory (all taps x channel
     // blocks, <= kMaxResidentB bytes): it is loaded once per run of tiles that share it, a stage is the A box alone
+    // mode 5 = halo boxes in their OWN two-slot ring in front of the stages (A5_RING_BYTES + the GroupNorm table), a
+    // stage is the weight tile of ONE tap: the A box of a channel block is loaded once and serves nine stages
+    static constexpr int A5_SLOTS = 3;
+    static constexpr int A5_RING_BYTES = A5_SLOTS * A_HALO_BYTES;  // 69 KB
+    static constexpr int GN_TAB_BYTES = 256 * 8;                    // [2][32] (mean, rstd) per group, rounded up to 2 KB
+    static constexpr int A5_REGION_BYTES = A5_RING_BYTES + GN_TAB_BYTES;  // 71 KB, a multiple of 1024
     __host__ __device__ static constexpr int stage_bytes(int row_shared) {
-        return row_shared == 3 ? A_HALO_BYTES
-                               : (row_shared == 2 ? STAGE_BYTES_HALO : (row_shared ? STAGE_BYTES_RS : STAGE_BYTES));
+        return row_shared == 5 ? B_BYTES
+                               : (row_shared == 3 ? A_HALO_BYTES
+                                                  : (row_shared == 2 ? STAGE_BYTES_HALO
+                                                                     : (row_shared ? STAGE_BYTES_RS : STAGE_BYTES)));
     }
     static constexpr int smem_bytes(int stages, int ring, int row_shared = 0, int breg_bytes = 0, int mode = 0) {
         return breg_bytes + stages * stage_bytes(row_shared) +
@@ -219,6 +227,10 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
     const uint32_t bar_rfull = s_aux + 256;      // [2][MAX_RING] x 8 B: residual chunk landed in the slot
     const uint32_t bar_rempty = s_aux + 352;     // [2][MAX_RING] x 8 B: the slot's output store has been read out
     const uint32_t bar_bfull = s_aux + 448;      // resident weights landed
+    // mode 5 (never together with the residual ring: MODE 2 has none), 3 x 8 B each, in the residual barriers' space
+    const uint32_t bar_afull = s_aux + 256;      // halo box landed
+    const uint32_t bar_aready = s_aux + 280;     // ... and GroupNorm + ReLU applied to it
+    const uint32_t bar_aempty = s_aux + 304;     // its nine taps have been multiplied
     float2* s_tab_all = reinterpret_cast<float2*>(aux + Cfg::AUX_HDR);
 
     if (warp == 0 && lane < nprob) {
@@ -237,11 +249,18 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
         }
-        for (int i = 0; i < 2 * RS; ++i) {
-            mbar_init(bar_rfull + 8 * i, 1);
-            mbar_init(bar_rempty + 8 * i, 1);
-        }
+        if (row_shared != 5)
+            for (int i = 0; i < 2 * RS; ++i) {
+                mbar_init(bar_rfull + 8 * i, 1);
+                mbar_init(bar_rempty + 8 * i, 1);
+            }
         mbar_init(bar_bfull, 1);
+        if (row_shared == 5)
+            for (int i = 0; i < Cfg::A5_SLOTS; ++i) {
+                mbar_init(bar_afull + 8 * i, 1);
+                mbar_init(bar_aready + 8 * i, 1);
+                mbar_init(bar_aempty + 8 * i, 1);
+            }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -270,6 +289,58 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             long long bkey = -1;  // mode 3: which weights are resident
             int last_stage = -1;
             uint32_t last_phase = 0;
+            if (row_shared == 5) {
+                // Halo boxes run two channel blocks ahead of the weight stages (three slots): the box of block cb + 2 (of
+                // the next tile after the last block) is requested right after the nine weight tiles of block cb -- the
+                // slot it takes, block cb - 1's, is free by then, so the request never stalls the weight stream -- and
+                // has about thirteen stages' worth of tensor work (6 600 cycles) to arrive from HBM and be transformed.
+                int as = 0;  // A ring position of the next box to request
+                uint32_t aph = 0;
+                int at = blockIdx.x, acb = 0, ag = 0;  // (tile, channel block, problem) of the next box to request
+                auto request_box = [&]() {
+                    if (at >= total_tiles) return;
+                    while (at >= s_begin[ag + 1]) ++ag;
+                    const ConvProblem* pa = probs + ag;
+                    const TileCoord ta = tile_coord(pa->p, at - s_begin[ag]);
+                    mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+                    mbar_arrive_expect_tx(bar_afull + 8 * as, Cfg::A_HALO_BOX_BYTES);
+                    tma_load_4d(s_bres + as * Cfg::A_HALO_BYTES, &pa->tmA[0], bar_afull + 8 * as, acb * 64, ta.x0 - 1,
+                                ta.y0 - 1, ta.n0);
+                    if (++as == Cfg::A5_SLOTS) {
+                        as = 0;
+                        aph ^= 1;
+                    }
+                    if (++acb == pa->p.cin_blocks) {
+                        acb = 0;
+                        at += gridDim.x;
+                    }
+                };
+                request_box();
+                request_box();
+                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                    while (t >= s_begin[g + 1]) ++g;
+                    const ConvProblem* pr = probs + g;
+                    const ConvParams& p = pr->p;
+                    const TileCoord tc = tile_coord(p, t - s_begin[g]);
+                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
+#pragma unroll 1
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            const uint32_t full = bar_full + 8 * stage;
+                            mbar_arrive_expect_tx(full, Cfg::B_BYTES);
+                            tma_load_2d(s_tiles + stage * stage_bytes, &pr->tmB, full, tap * p.Cin + cb * 64,
+                                        tc.nt * BLOCK_N);
+                            if (++stage == stages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                        // AFTER this block's weight tiles: its slot's predecessor (block cb - 1) is done by now, so
+                        // this never blocks the weight stream behind the tensor core
+                        request_box();
+                    }
+                }
+            } else
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 while (t >= s_begin[g + 1]) ++g;
                 const ConvProblem* pr = probs + g;
@@ -372,6 +443,8 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             int g = 0;
             long long bkey = -1;
             uint32_t bphase = 0;
+            int a5s = 0;  // mode 5: A ring position
+            uint32_t a5ph = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 while (t >= s_begin[g + 1]) ++g;
                 const int num_kb =
@@ -388,6 +461,34 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * BLOCK_N;
+                if (row_shared == 5) {
+                    const bool gn_in = probs[g].p.in_gn_sums != nullptr;
+                    const int cbs = probs[g].p.cin_blocks;
+                    for (int cb = 0; cb < cbs; ++cb) {
+                        mbar_wait((gn_in ? bar_aready : bar_afull) + 8 * a5s, a5ph);
+                        tc_fence_after();
+                        const uint64_t a_base = umma_desc_sw128_ex(s_bres + a5s * Cfg::A_HALO_BYTES, 1280, 0);
+#pragma unroll 1
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(bar_full + 8 * stage, phase);
+                            tc_fence_after();
+                            const uint64_t ad = a_base + (((tap / 3) * 10 + (tap % 3)) * 128 >> 4);
+                            const uint64_t bd = umma_desc_sw128(s_tiles + stage * stage_bytes);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_f16(d, ad + 2 * k, bd + 2 * k, idesc, (cb | tap | k) != 0);
+                            umma_commit(bar_empty + 8 * stage);
+                            if (++stage == stages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                        umma_commit(bar_aempty + 8 * a5s);  // the box may be overwritten once its 36 MMAs are done
+                        if (++a5s == Cfg::A5_SLOTS) {
+                            a5s = 0;
+                            a5ph ^= 1;
+                        }
+                    }
+                } else
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
@@ -436,6 +537,134 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
+        }
+    } else if ((warp == 2 || warp == 3) && row_shared == 5) {
+        // ------------------------------------------------------------ GroupNorm + ReLU of the INPUT, on the landed box
+        // (mode 5, tower layers 2-4): the previous layer stored its RAW convolution output and its statistics; instead
+        // of a separate read-modify-write pass over that tensor (2 x 512 B per location and layer, 1.4 ms per forward at
+        // 32 x 1024^2), the two spare warps rewrite each 18 x 10 pixel x 64 channel box in shared memory between the TMA
+        // load and the MMAs: y = max(x * a + b, 0) with a = rstd * gamma, b = beta - mean * a (fp32, rounded to fp16 once,
+        // like the separate pass). Every element is touched ONCE per tile (the box serves all nine taps) -- 46 KB of shared-memory
+        // traffic per channel block next to the 432 KB the nine taps' MMAs read. Pixels outside the image are the
+        // convolution's zero padding (TMA zero fill) and stay zero: the padding applies to the NORMALISED map.
+        const int tid = threadIdx.x - 64;  // 0..63
+        // [2][32] (mean, rstd) of the image's 32 groups (8 channels each), double-buffered over tiles: with a grid
+        // stride of 148 and 128 tiles per P3 image nearly every tile of a CTA belongs to another image
+        float2* gstat = reinterpret_cast<float2*>(smem + Cfg::A5_RING_BYTES);
+        // Thread tid takes sixteen-byte unit qs = tid & 7 of pixels px = (tid >> 3) + 8 k, k < 22.5. With the
+        // address-based 128-byte swizzle that unit holds channels 8 * (qs ^ (px & 7)) ... + 7, and px & 7 = (tid >> 3) & 7
+        // for every k: the thread always meets the SAME eight channels of a channel block -- exactly one GroupNorm
+        // group -- whose (a, b) pairs it keeps in registers for the whole box.
+        const int qs = tid & 7, pxb = tid >> 3;
+        const int grp_in_cb = qs ^ (pxb & 7);
+        int as = 0;
+        uint32_t aph = 0;
+        int g = 0;
+        int buf = 0;
+        // raw statistics of this thread's group (tid < 32) for the tile it is about to work on, fetched one tile ahead
+        long long pre1 = 0, pre2 = 0;
+        auto fetch_stats = [&](int t, int g_from) {
+            if (t >= total_tiles || tid >= 32) return;
+            int gg = g_from;
+            while (t >= s_begin[gg + 1]) ++gg;
+            const ConvParams& q = probs[gg].p;
+            if (q.in_gn_sums == nullptr || tid >= (q.Cin >> 3)) return;
+            const int n0 = tile_coord(q, t - s_begin[gg]).n0;
+            const long long* sp = q.in_gn_sums + (static_cast<size_t>(n0) * (q.Cin >> 3) + tid) * 2;
+            pre1 = __ldg(sp);
+            pre2 = __ldg(sp + 1);
+        };
+        fetch_stats(blockIdx.x, 0);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            while (t >= s_begin[g + 1]) ++g;
+            const ConvParams& p = probs[g].p;
+            const int cbs = p.cin_blocks;
+            if (p.in_gn_sums == nullptr) {  // plain input: the MMA warp waits for the TMA itself
+                for (int cb = 0; cb < cbs; ++cb)
+                    if (++as == Cfg::A5_SLOTS) {
+                        as = 0;
+                        aph ^= 1;
+                    }
+                fetch_stats(t + gridDim.x, g);
+                continue;
+            }
+            const TileCoord tc = tile_coord(p, t - s_begin[g]);
+            const int Wout = p.Wout, Hout = p.Hout;
+            const float* gamma = p.in_gamma;
+            const float* beta = p.in_beta;
+            if (tid < (p.Cin >> 3)) {
+                const float inv_cnt = 1.0f / (static_cast<float>(Hout * Wout) * 8.0f);
+                const float s1 = static_cast<float>(static_cast<double>(pre1) * (1.0 / kGnSumScale));
+                const float s2 = static_cast<float>(static_cast<double>(pre2) * (1.0 / kGnSqScale));
+                const float mean = s1 * inv_cnt;
+                const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
+                gstat[buf * 32 + tid] = make_float2(mean, rsqrtf(var + 1e-5f));
+            }
+            fetch_stats(t + gridDim.x, g);
+            // which of this thread's 23 pixels lie inside the image (the others are the convolution's zero padding and
+            // stay zero): once per tile, the four channel blocks share it
+            uint32_t on = 0;
+#pragma unroll 1
+            for (int k = 0; k < 23; ++k) {
+                const int px = pxb + 8 * k;
+                const int x = tc.x0 - 1 + px % 10, y = tc.y0 - 1 + px / 10;
+                if (px < 180 && x >= 0 && y >= 0 && x < Wout && y < Hout) on |= 1u << k;
+            }
+            named_bar_sync(3, 64);  // the table of this tile is complete (the other buffer belongs to the previous tile)
+            for (int cb = 0; cb < cbs; ++cb) {
+                // y = max(x * a + b, 0) with a = rstd * gamma, b = beta - mean * a: one FMA per element
+                float2 ab[8];
+                {
+                    const int grp = cb * 8 + grp_in_cb;
+                    const float2 mr = gstat[buf * 32 + grp];
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + grp * 8));
+                    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + grp * 8) + 1);
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + grp * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + grp * 8) + 1);
+                    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = mr.y * gm[j];
+                        ab[j] = make_float2(a, bt[j] - mr.x * a);
+                    }
+                }
+                mbar_wait(bar_afull + 8 * as, aph);
+                const uint32_t unit0 = s_bres + as * Cfg::A_HALO_BYTES + pxb * 128 + qs * 16;
+                uint32_t m = on;
+#pragma unroll 1
+                for (int k0 = 0; k0 < 23; k0 += 4, m >>= 4) {  // four units in flight
+                    uint32_t w[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (m & (1u << i))
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(w[i][0]), "=r"(w[i][1]), "=r"(w[i][2]), "=r"(w[i][3])
+                                         : "r"(unit0 + (k0 + i) * 1024));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (!(m & (1u << i))) continue;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i][j]));
+                            const float a0 = fmaf(f.x, ab[2 * j].x, ab[2 * j].y);
+                            const float a1 = fmaf(f.y, ab[2 * j + 1].x, ab[2 * j + 1].y);
+                            asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(w[i][j]) : "f"(a1), "f"(a0));
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(unit0 + (k0 + i) * 1024),
+                                     "r"(w[i][0]), "r"(w[i][1]), "r"(w[i][2]), "r"(w[i][3])
+                                     : "memory");
+                    }
+                }
+                fence_proxy_async_smem();  // the rewritten box is read by the tensor core (async proxy)
+                named_bar_sync(3, 64);
+                if (tid == 0) mbar_arrive(bar_aready + 8 * as);
+                if (++as == Cfg::A5_SLOTS) {
+                    as = 0;
+                    aph ^= 1;
+                }
+            }
+            buf ^= 1;
         }
     } else if (warp == 3) {
         // ------------------------------------------------------------ residual producer
@@ -863,7 +1092,22 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
                 plan->breg_bytes = 9 * (d.Cin / 64) * bn * 128;
             }
     }
-    if (row_shared) {
+    // mode 5: the 256-wide tower convolutions (GroupNorm statistics in the epilogue) take their input as halo boxes too
+    // -- one A load per channel block instead of nine, 28 % less L2 -> shared-memory traffic -- with the weights of one
+    // tap per stage, and can normalise the input while it is loaded (in_gn_sums). DAFNE_CONV_HALO256=0: A/B switch.
+    bool mode5 = !small && d.ksize == 3 && d.stride == 1 && bn == 256 && d.gn_sums != nullptr && d.Cin <= 256;
+    if (const char* ev = getenv("DAFNE_CONV_HALO256"))
+        if (atoi(ev) == 0) mode5 = false;
+    if (d.in_gn_sums != nullptr && !mode5) {
+        set_error("conv_tc: GroupNorm on load needs the 256-wide halo mode (3x3, stride 1, Cout %% 256 == 0, Cin <= 256)");
+        return -1;
+    }
+    if (mode5) {
+        plan->row_shared = 5;
+        plan->breg_bytes = ConvCfg<256, 1>::A5_REGION_BYTES;
+        halo = true;
+    }
+    if (row_shared || mode5) {
         p.tw = 8;
         p.th = 16;
         p.nb = 1;
@@ -888,6 +1132,9 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     p.res_W = d.res_W;
     p.res_shift = d.res_shift;
     p.gn_sums = d.gn_sums;
+    p.in_gn_sums = d.in_gn_sums;
+    p.in_gamma = d.in_gamma;
+    p.in_beta = d.in_beta;
     p.out_f32 = d.out_f32;
     p.out_ld = d.out_ld;
     p.w_id = d.w;
@@ -902,7 +1149,7 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     if (d.stride == 1) {
         const uint64_t dims[4] = {C, W, H, (uint64_t)d.N};
         const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
-        if (encode_map(&plan->prob.tmA[0], d.in, 4, dims, str, row_shared ? boxA_rs : boxA,
+        if (encode_map(&plan->prob.tmA[0], d.in, 4, dims, str, (row_shared || mode5) ? boxA_rs : boxA,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A"))
             return -1;
         for (int v = 1; v < 4; ++v) plan->prob.tmA[v] = plan->prob.tmA[0];
@@ -1057,7 +1304,7 @@ int conv_group_launch(const ConvProblem* dev_probs, int nprob, int total_tiles, 
     const int key = block_n * 10 + epi_wgs;
     if (mode == 2) {
         // GroupNorm statistics: only the 256-wide tower convolutions produce them
-        if (key == 2561) return launch_bn<256, 1, 2>(dev_probs, nprob, total_tiles, grid, 0, 0, 0, stream);
+        if (key == 2561) return launch_bn<256, 1, 2>(dev_probs, nprob, total_tiles, grid, 0, row_shared, breg, stream);
         if (key == 2562) return launch_bn<256, 2, 2>(dev_probs, nprob, total_tiles, grid, 0, 0, 0, stream);
         set_error("conv_tc: GroupNorm statistics need Cout %% 256 == 0 (tile width %d)", block_n);
         return -1;

@@ -37,6 +37,12 @@ struct ConvDesc {
     const float* shift = nullptr;  // per-Cout addend (folded FrozenBN shift or conv bias), nullptr = 0
     int relu = 0;
     int reverse_m = 0;  // walk the pixel tiles from the last to the first (see ConvParams::reverse_m)
+    // GroupNorm + ReLU of the INPUT applied while it is loaded (3x3 / stride 1 / Cout % 256 == 0 / Cin == 256, the tower
+    // convolutions): `in` holds the previous layer's RAW conv output, in_gn_sums its statistics (the format gn_sums has),
+    // in_gamma / in_beta the affine of the GroupNorm in between. nullptr: `in` is used as it is.
+    const long long* in_gn_sums = nullptr;
+    const float* in_gamma = nullptr;
+    const float* in_beta = nullptr;
     const __half* residual = nullptr;  // NHWC fp16 [N, res_H, res_W, Cout]; added at (y>>res_shift, x>>res_shift)
     int res_H = 0, res_W = 0, res_shift = 0;
     // [N][Cout/8][2] 64-bit fixed point, accumulated: (sum * 2^20, sum of squares * 2^12) of the fp16-rounded output
@@ -66,6 +72,9 @@ struct ConvParams {
     long long* gn_sums;
     float* out_f32;
     int out_ld;
+    const long long* in_gn_sums;  // GroupNorm of the input applied on load (mode 5), or nullptr
+    const float* in_gamma;
+    const float* in_beta;
     const void* w_id;  // identity of the weight tensor (its device pointer): tiles with equal w_id share resident weights
 };
 
@@ -88,7 +97,9 @@ struct ConvPlan {
     int res_tma;  // != 0: residual at the output's resolution, loaded by TMA into the epilogue ring; the value is the
                   // ring depth asked for (2..6)
     int row_shared;  // 3x3 stride 1, narrow N tile: 0 one A load per tap; 1 one per horizontal tap (18-row box);
-                     // 2 one halo box for all nine taps; 3 the same with the weights resident in shared memory
+                     // 2 one halo box for all nine taps; 3 the same with the weights resident in shared memory;
+                     // 5 (256-wide tiles) halo boxes in their own two-slot ring, the weights of one tap per stage,
+                     //   GroupNorm + ReLU of the input applied to the landed box by two transform warps
     int breg_bytes;  // mode 3: bytes of the resident weight region (9 x Cin/64 x BLOCK_N x 128)
     int grid;     // CTAs for a stand-alone launch
     double flops;  // 2*MACs, algorithmic (unpadded)

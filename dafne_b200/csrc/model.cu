@@ -442,8 +442,10 @@ struct Builder {
     }
 
     // out = epilogue(conv(in)); allocates the fp16 output unless out_f32 is given
+    // in_gn_sums / in_gamma / in_beta: `in` is a RAW tower output; its GroupNorm + ReLU is applied while it is loaded
     Act conv(const ConvLayer& L, const Act& in, bool relu, const Act* residual = nullptr, int res_shift = 0,
-             long long* gn_sums = nullptr, float* out_f32 = nullptr, int out_ld = 0) {
+             long long* gn_sums = nullptr, float* out_f32 = nullptr, int out_ld = 0,
+             const long long* in_gn_sums = nullptr, const float* in_gamma = nullptr, const float* in_beta = nullptr) {
         ConvDesc d;
         d.in = in.p;
         d.N = in.N;
@@ -477,6 +479,9 @@ struct Builder {
             d.res_shift = res_shift;
         }
         d.gn_sums = gn_sums;
+        d.in_gn_sums = in_gn_sums;
+        d.in_gamma = in_gamma;
+        d.in_beta = in_beta;
         d.reverse_m = reverse_next ? 1 : 0;
         reverse_next = false;
         const bool single = !grouping;
@@ -767,14 +772,25 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
         c->ops.push_back([gp](cudaStream_t s) { return launch_gn_relu_group(gp.data(), (int)gp.size(), 1e-5f, s); });
         B.info("gn_relu", 0, 0, bytes);
     };
+    // GroupNorm + ReLU between the tower layers is applied by the CONSUMING convolution while it loads its input
+    // (conv_tc mode 5): layers 0-2 of a tower store their raw output and statistics only; the explicit in-place pass
+    // remains for layer 3, whose consumers are the narrow prediction convolutions and corners_tower.0.
+    // DAFNE_CONV_GNFUSE=0 (or DAFNE_CONV_HALO256=0): every layer is followed by the separate pass again.
+    const bool gn_fuse = !(getenv("DAFNE_CONV_GNFUSE") && atoi(getenv("DAFNE_CONV_GNFUSE")) == 0) &&
+                         !(getenv("DAFNE_CONV_HALO256") && atoi(getenv("DAFNE_CONV_HALO256")) == 0);
+    auto gn_w = [&](int t, int layer) { return raw_of(c, kHead + kTowers[t] + "." + std::to_string(3 * layer + 1) + ".weight"); };
+    auto gn_b = [&](int t, int layer) { return raw_of(c, kHead + kTowers[t] + "." + std::to_string(3 * layer + 1) + ".bias"); };
     Act cur[3][5];
     for (int i = 0; i < 4; ++i) {  // cls_tower and center_tower, layer i, all levels
         Act raw[2][5];
+        const bool in_raw = gn_fuse && i > 0;  // cur[t][l] is the raw output of layer i - 1
         B.begin_group(std::string("cls_tower+center_tower.") + std::to_string(3 * i));
         for (int t = 0; t < 2; ++t)
             for (int l = 0; l < 5; ++l)
                 raw[t][l] = B.conv(B.layer(kHead + kTowers[t] + "." + std::to_string(3 * i)), i == 0 ? P[l] : cur[t][l],
-                                   false, nullptr, 0, sums_of(t, i, l));
+                                   false, nullptr, 0, sums_of(t, i, l), nullptr, 0,
+                                   in_raw ? sums_of(t, i - 1, l) : nullptr, in_raw && base ? gn_w(t, i - 1) : nullptr,
+                                   in_raw && base ? gn_b(t, i - 1) : nullptr);
         B.end_group();
         if (B.failed) return -1;
         std::vector<std::pair<int, Act*>> items;
@@ -788,14 +804,17 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
                 cur[t][l] = raw[t][l];
                 items.push_back({t, &cur[t][l]});
             }
-        gn_group(items, i);
+        if (!gn_fuse || i == 3) gn_group(items, i);
     }
     for (int i = 0; i < 4; ++i) {  // corners_tower on top of the center tower
         Act raw[5];
+        const bool in_raw = gn_fuse && i > 0;
         B.begin_group(std::string("corners_tower.") + std::to_string(3 * i));
         for (int l = 0; l < 5; ++l)
             raw[l] = B.conv(B.layer(kHead + "corners_tower." + std::to_string(3 * i)), i == 0 ? cur[1][l] : cur[2][l],
-                            false, nullptr, 0, sums_of(2, i, l));
+                            false, nullptr, 0, sums_of(2, i, l), nullptr, 0,
+                            in_raw ? sums_of(2, i - 1, l) : nullptr, in_raw && base ? gn_w(2, i - 1) : nullptr,
+                            in_raw && base ? gn_b(2, i - 1) : nullptr);
         B.end_group();
         if (B.failed) return -1;
         std::vector<std::pair<int, Act*>> items;
@@ -804,7 +823,7 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
             cur[2][l] = raw[l];
             items.push_back({2, &cur[2][l]});
         }
-        gn_group(items, i);
+        if (!gn_fuse || i == 3) gn_group(items, i);
     }
     for (int t = 0; t < 3; ++t)
         for (int l = 0; l < 5; ++l) B.name(std::string(kTowers[t]) + ".l" + std::to_string(l), cur[t][l]);

@@ -196,6 +196,14 @@ int dafne_conv_nhwc(const void* dev_in_f16, int N, int H, int W, int Cin, const 
                     const void* dev_residual_f16, int res_H, int res_W, int res_shift, int64_t* dev_gn_sums,
                     void* dev_out_f16, float* dev_out_f32, int out_ld, void* stream);
 
+/* Head-tower convolution with the PREVIOUS layer's GroupNorm + ReLU applied to its input while it is loaded (3x3,
+ * stride 1, Cin = Cout = 256): dev_in_raw_f16 is the previous layer's raw convolution output, dev_in_gn_sums its
+ * statistics (the dev_gn_sums format of dafne_conv_nhwc), in_gamma / in_beta the affine of the GroupNorm in between.
+ *   out = conv3x3(relu(GroupNorm32(in_raw))) + shift,  dev_gn_sums += statistics of out (zero it first). */
+int dafne_conv_gn_in_nhwc(const void* dev_in_raw_f16, int N, int H, int W, int Cin, const int64_t* dev_in_gn_sums,
+                          const float* dev_in_gamma, const float* dev_in_beta, const void* dev_w_f16, int Cout,
+                          const float* dev_shift, int64_t* dev_gn_sums, void* dev_out_f16, void* stream);
+
 /* Bottleneck tail through the two-GEMM tcgen05 kernel (csrc/tail_tc.cu): conv3 + FrozenBN + shortcut + ReLU of one
  * detectron2 BottleneckBlock and conv1 + FrozenBN + ReLU of the next one, both 1x1 / stride 1, in ONE launch:
  *   out = relu(scale1 * (in x w3^T) + shift1 + residual)   in [N,H,W,K1], w3 [N1][K1], residual / out [N,H,W,N1]

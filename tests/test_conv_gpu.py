@@ -215,3 +215,80 @@ def test_bottleneck_tail_matches_two_torch_convs(case):
     assert torch.isfinite(got_mid).all()
     err = (got_mid - ref_mid).abs()
     assert bool((err <= 2e-3 * ref_mid.abs().max() + 2e-3 * ref_mid.abs()).all()), f"mid: max err {err.max().item()}"
+
+
+GN_IN_CASES = [
+    # name, N, H, W: the tower convolutions' shapes -- P3-like (several tiles per CTA, every tile another image), ragged
+    # sizes whose halo crosses the image border on every side, a single tiny level
+    ("p3_128x128_n4", 4, 128, 128),
+    ("ragged_50x37_n3", 3, 50, 37),
+    ("p7_8x8_n2", 2, 8, 8),
+    ("wide_16x200_n1", 1, 16, 200),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GN_IN_CASES, ids=[c[0] for c in GN_IN_CASES])
+def test_tower_conv_groupnorm_on_load(case):
+    """conv_tc.cu mode 5: the tower convolution reads the previous layer's RAW output and applies that layer's
+    GroupNorm(32) + ReLU to the landed halo box in shared memory (fcos/dafne head towers: Conv - GN - ReLU x 4). Against
+    (a) torch fp32 group_norm + relu + conv2d on the same fp16 raw tensor and (b) this library's two-pass path (separate
+    GroupNorm kernel, then the same convolution), whose only difference is the rounding of the affine form."""
+    from dafne_b200 import _capi
+
+    lib = _capi.lib()
+    name, N, H, W = case
+    Cc = 256
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(7 + len(name))
+    x0 = torch.randn(N, Cc, H, W, generator=g).half()
+    w0 = (torch.randn(Cc, Cc, 3, 3, generator=g) / (9 * Cc) ** 0.5).half()
+    w1 = (torch.randn(Cc, Cc, 3, 3, generator=g) / (9 * Cc) ** 0.5).half()
+    b0, b1 = torch.randn(Cc, generator=g) * 0.1, torch.randn(Cc, generator=g) * 0.1
+    gamma, beta = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g) * 0.3
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def nhwc(t):
+        return t.to(dev).permute(0, 2, 3, 1).contiguous()
+
+    def wk(t):  # [Cout][k*k][Cin]
+        return t.to(dev).permute(0, 2, 3, 1).reshape(Cc, 9, Cc).contiguous()
+
+    x_d, w0_d, w1_d = nhwc(x0), wk(w0), wk(w1)
+    b0_d, b1_d, gamma_d, beta_d = (t.to(dev).contiguous() for t in (b0, b1, gamma, beta))
+    # layer 0: raw output + statistics
+    raw = torch.empty((N, H, W, Cc), device=dev, dtype=torch.float16)
+    sums0 = torch.zeros((N, 32, 2), device=dev, dtype=torch.int64)
+    _capi.check(lib.dafne_conv_nhwc(vp(x_d), N, H, W, Cc, vp(w0_d), Cc, 3, 1, None, vp(b0_d), 0, None, 0, 0, 0,
+                                    vp(sums0), vp(raw), None, 0, stream), "dafne_conv_nhwc")
+    # layer 1, GroupNorm on load
+    out = torch.full((N, H, W, Cc), float("nan"), device=dev, dtype=torch.float16)
+    sums1 = torch.zeros((N, 32, 2), device=dev, dtype=torch.int64)
+    _capi.check(lib.dafne_conv_gn_in_nhwc(vp(raw), N, H, W, Cc, vp(sums0), vp(gamma_d), vp(beta_d), vp(w1_d), Cc,
+                                          vp(b1_d), vp(sums1), vp(out), stream), "dafne_conv_gn_in_nhwc")
+    # two-pass path of the same library
+    normed = raw.clone()
+    _capi.check(lib.dafne_gn_relu_nhwc(vp(normed), vp(normed), N, H * W, Cc, 32, vp(sums0), vp(gamma_d), vp(beta_d),
+                                       C.c_float(1e-5), stream), "dafne_gn_relu_nhwc")
+    out2 = torch.empty_like(out)
+    sums2 = torch.zeros_like(sums1)
+    _capi.check(lib.dafne_conv_nhwc(vp(normed), N, H, W, Cc, vp(w1_d), Cc, 3, 1, None, vp(b1_d), 0, None, 0, 0, 0,
+                                    vp(sums2), vp(out2), None, 0, stream), "dafne_conv_nhwc")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    raw_f = raw.permute(0, 3, 1, 2).float()
+    ref_in = F.relu(F.group_norm(raw_f, 32, gamma_d, beta_d, 1e-5))
+    ref = F.conv2d(ref_in.half().float(), w1.to(dev).float(), b1_d, padding=1)
+    got = out.permute(0, 3, 1, 2).float()
+    err = (got - ref).abs()
+    assert bool((err <= 3e-3 * ref.abs().max() + 3e-3 * ref.abs()).all()), f"vs torch: max err {err.max().item()}"
+    # against the two-pass path: the normalised input differs by at most one fp16 ulp on a few elements
+    d2 = (out.float() - out2.float()).abs()
+    assert d2.max().item() <= 4e-3 * out2.float().abs().max().item(), f"vs two-pass: {d2.max().item()}"
+    assert (d2 > 0).float().mean().item() < 0.05
+    # statistics of the output: fixed point, so equal wherever the outputs are equal; close otherwise
+    rel = (sums1 - sums2).abs().double() / sums2.abs().double().clamp_min(1.0)
+    assert rel.max().item() < 1e-3
