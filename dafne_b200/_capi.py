@@ -110,6 +110,7 @@ _SIGNATURES = {
         [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     ),
     "dafne_conv_gn_in_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "dafne_conv1x1_pair_nhwc": (_i, [_vp, C.c_int64, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "dafne_bottleneck_tail_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "dafne_gn_relu_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "dafne_sort_quadrilateral": (_i, [_vp, _vp, _i, _vp]),

@@ -8,6 +8,7 @@
 #include "elementwise.cuh"
 #include "merge_nms.cuh"
 #include "resize.cuh"
+#include "pair_tc.cuh"
 #include "tail_tc.cuh"
 #include "model.cuh"
 #include "postprocess.cuh"
@@ -121,6 +122,36 @@ int dafne_conv_gn_in_nhwc(const void* in_raw, int N, int H, int W, int Cin, cons
     }
     return conv_group_launch(dev_prob, 1, plan.prob.p.total_tiles, plan.block_n, plan.epi_wgs, plan.mode, plan.res_tma,
                              plan.row_shared, plan.breg_bytes, num_sms_cached(), s);
+}
+
+int dafne_conv1x1_pair_nhwc(const void* in, int64_t M, int K, const void* w, int N, const float* scale, const float* shift,
+                            int relu, const void* residual, void* out, void* stream) {
+    PairDesc d;
+    d.in = static_cast<const __half*>(in);
+    d.M = M;
+    d.K = K;
+    d.w = static_cast<const __half*>(w);
+    d.N = N;
+    d.scale = scale;
+    d.shift = shift;
+    d.relu = relu;
+    d.residual = static_cast<const __half*>(residual);
+    d.out = static_cast<__half*>(out);
+    PairPlan plan;
+    if (pair_plan_build(d, &plan, num_sms_cached())) return -1;
+    // test / A-B hook: the problem descriptor goes through a small per-thread device buffer (synchronous upload)
+    static thread_local PairProblem* dev_prob = nullptr;
+    if (!dev_prob && cudaMalloc(&dev_prob, sizeof(PairProblem)) != cudaSuccess) {
+        set_error("dafne_conv1x1_pair_nhwc: cudaMalloc of the problem descriptor failed");
+        return -1;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaStreamSynchronize(s) != cudaSuccess ||
+        cudaMemcpy(dev_prob, &plan.prob, sizeof(PairProblem), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("dafne_conv1x1_pair_nhwc: descriptor upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    return pair_plan_launch(dev_prob, plan, s);
 }
 
 int dafne_bottleneck_tail_nhwc(const void* in, int N, int H, int W, int K1, const void* w3, int N1, const float* scale1,

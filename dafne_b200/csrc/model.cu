@@ -14,6 +14,7 @@
 
 #include "elementwise.cuh"
 #include "stem_tc.cuh"
+#include "pair_tc.cuh"
 #include "tail_tc.cuh"
 
 namespace dafne {
@@ -291,6 +292,7 @@ int ctx_finalize(dafne_ctx* c, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------ plan
 namespace {
 constexpr size_t kMaxPlanProblems = 512;
+constexpr size_t kMaxPairProblems = 80;  // 1x1 convolutions on the CTA-pair kernel: conv1 + conv3 of res4 / res5
 constexpr size_t kMaxTailProblems = 40;  // bottleneck tails (conv3 + next conv1): 2 + 3 + 22 for ResNet-101
 struct Builder {
     dafne_ctx* c;
@@ -311,6 +313,8 @@ struct Builder {
     bool reverse_next = false;  // the next conv() walks its pixel tiles back to front (ConvParams::reverse_m)
     std::vector<TailProblem> tails;
     TailProblem* dev_tails = nullptr;
+    std::vector<PairProblem> pairs;
+    PairProblem* dev_pairs = nullptr;
 
     void begin_group(const std::string& name) {
         grouping = true;
@@ -439,6 +443,50 @@ struct Builder {
         info(nm.size() > 46 ? nm.substr(nm.size() - 46).c_str() : nm.c_str(), 1, fl,
              px * 2.0 * (L3.Cin + 2.0 * L3.Cout + L1.Cout) + 2.0 * ((double)L3.Cout * L3.Cin + (double)L1.Cout * L1.Cin),
              128, 1, 1, L3.Cin, L3.Cout, in.H, in.W);
+    }
+
+    // 1x1 / stride-1 convolution + FrozenBN (+ shortcut) (+ ReLU) on the CTA-pair kernel (pair_tc.cu)
+    Act pair(const ConvLayer& L, const Act& in, bool relu, const Act* residual, const std::string& nm) {
+        Act out = new_act(in.N, in.H, in.W, L.Cout);
+        ++launches;
+        const double px = (double)in.N * in.H * in.W;
+        const double fl = 2.0 * px * (double)L.Cout * L.Cin;
+        flops += fl;
+        const bool rev = reverse_next;
+        reverse_next = false;
+        if (!base || failed) return out;
+        if (in.C != L.Cin || (residual && (residual->C != L.Cout || residual->H != in.H || residual->W != in.W)) ||
+            pairs.size() >= kMaxPairProblems) {
+            set_error("plan: pair convolution '%s' has inconsistent shapes", nm.c_str());
+            failed = true;
+            return out;
+        }
+        PairDesc d;
+        d.in = in.p;
+        d.M = (long long)in.N * in.H * in.W;
+        d.K = L.Cin;
+        d.w = L.w;
+        d.N = L.Cout;
+        d.scale = L.scale;
+        d.shift = L.shift;
+        d.relu = relu ? 1 : 0;
+        d.residual = residual ? residual->p : nullptr;
+        d.out = out.p;
+        d.reverse_m = rev ? 1 : 0;
+        PairPlan plan;
+        if (pair_plan_build(d, &plan, c->num_sms)) {
+            failed = true;
+            return out;
+        }
+        const PairProblem* dp = dev_pairs + pairs.size();
+        pairs.push_back(plan.prob);
+        c->ops.push_back([dp, plan](cudaStream_t s) { return pair_plan_launch(dp, plan, s); });
+        info(nm.size() > 46 ? nm.substr(nm.size() - 46).c_str() : nm.c_str(), 1, fl, plan.bytes, 256, 1, 1, L.Cin, L.Cout,
+             in.H, in.W);
+        return out;
+    }
+    static bool pair_ok(const ConvLayer& L) {
+        return L.k == 1 && L.stride == 1 && L.scale != nullptr && L.shift != nullptr && pair_supported(L.Cin, L.Cout);
     }
 
     // out = epilogue(conv(in)); allocates the fp16 output unless out_f32 is given
@@ -592,6 +640,7 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     int32_t* sizes_dev = B.persistent<int32_t>(static_cast<size_t>(N) * 4 * sizeof(int32_t));
     B.dev_probs = B.persistent<ConvProblem>(kMaxPlanProblems * sizeof(ConvProblem));
     B.dev_tails = B.persistent<TailProblem>(kMaxTailProblems * sizeof(TailProblem));
+    B.dev_pairs = B.persistent<PairProblem>(kMaxPairProblems * sizeof(PairProblem));
     const size_t sums_per = static_cast<size_t>(N) * 32 * 2 * sizeof(long long);
     const size_t sums_bytes = sums_per * 3 * 4 * 5;
     long long* sums_all = B.persistent<long long>(sums_bytes);
@@ -654,6 +703,12 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     // (default 3 = res2 and res3; 0 = every 1x1 is its own launch; 7 adds res4, where the fused form is SLOWER: the
     // two weight matrices, 1 MB per 128-pixel tile, are re-streamed from L2 faster than a 64 KB ring can pull them).
     static const int tail_mask = getenv("DAFNE_CONV_TAIL") ? atoi(getenv("DAFNE_CONV_TAIL")) : 3;
+    // Which stages run their 1x1 / stride-1 convolutions on the CTA-pair kernel (pair_tc.cu, cta_group::2): bit (s - 2) of
+    // DAFNE_CONV_PAIR for conv1, bit (s - 2 + 4) for conv3 (0 = none). Default 0x8C = conv1 of res4 / res5 and conv3 of
+    // res5 (per launch at R101 32 x 1024^2: 79 -> 70 us, 75 -> 64 us, 101 -> 84 us); conv3 of res4 is SLOWER on the pair
+    // kernel (134 -> 146 us: K = 256 gives a 256 x 256 tile only four k-blocks of tensor work per 192 KB of HBM traffic, and
+    // three 32 KB residual slots prefetch less far ahead than conv_tc.cu's ring of 16 KB slots).
+    static const int pair_mask = getenv("DAFNE_CONV_PAIR") ? atoi(getenv("DAFNE_CONV_PAIR")) : 0x8C;
     for (int s = 2; s <= 5; ++s) {
         Act next_a;  // conv1 output of the NEXT block when the previous block's tail has already produced it
         bool have_a = false;
@@ -674,7 +729,9 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
                 // res4, twice the L2): back to front, the part L2 still holds comes first. DAFNE_CONV_REVERSE=0: A/B.
                 static const bool reverse_on = !(getenv("DAFNE_CONV_REVERSE") && atoi(getenv("DAFNE_CONV_REVERSE")) == 0);
                 B.reverse_next = reverse_on && b > 0;
-                a = B.conv(B.layer(pre + ".conv1"), x, true);
+                const ConvLayer& L1 = B.layer(pre + ".conv1");
+                a = (((pair_mask >> (s - 2)) & 1) && Builder::pair_ok(L1)) ? B.pair(L1, x, true, nullptr, pre + ".conv1")
+                                                                             : B.conv(L1, x, true);
             }
             Act m = B.conv(B.layer(pre + ".conv2"), a, true);
             B.free_act(a);
@@ -690,7 +747,9 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
                     fused = true;
                 }
             }
-            if (!fused) o = B.conv(L3, m, true, &sc, 0);
+            if (!fused)
+                o = (((pair_mask >> (s - 2 + 4)) & 1) && Builder::pair_ok(L3)) ? B.pair(L3, m, true, &sc, pre + ".conv3")
+                                                                                 : B.conv(L3, m, true, &sc, 0);
             B.free_act(m);
             if (own_sc) B.free_act(sc);
             B.free_act(x);  // block input (== sc for b > 0)
@@ -848,6 +907,8 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     if (base) {
         // the kernels read their problem descriptors (tensor maps + parameters) from device memory
         CUDA_OK(cudaMemcpy(B.dev_probs, B.probs.data(), B.probs.size() * sizeof(ConvProblem), cudaMemcpyHostToDevice));
+        if (!B.pairs.empty())
+            CUDA_OK(cudaMemcpy(B.dev_pairs, B.pairs.data(), B.pairs.size() * sizeof(PairProblem), cudaMemcpyHostToDevice));
         if (!B.tails.empty())
             CUDA_OK(cudaMemcpy(B.dev_tails, B.tails.data(), B.tails.size() * sizeof(TailProblem), cudaMemcpyHostToDevice));
     }

@@ -123,6 +123,14 @@ def batched_nms_poly(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tens
     assert boxes.shape[-1] == 8
     if boxes.numel() == 0:
         return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    keep, nkeep, _ = _batched_nms_poly_launch(boxes, scores, idxs, iou_threshold, vehicle_merge)
+    return keep[: int(nkeep.item())].to(torch.int64)
+
+
+def _batched_nms_poly_launch(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float,
+                             vehicle_merge: bool = True):
+    """Enqueue the NMS of `batched_nms_poly` on the current stream WITHOUT reading its result: (keep int32 [n], nkeep
+    int32 [1], tensors the kernels still use). Callers that run several images overlap them on separate streams."""
     if not boxes.is_cuda:
         raise _capi.DafneError("batched_nms_poly: CUDA tensors required (no CPU fallback in this package)")
     n = boxes.shape[0]
@@ -139,7 +147,7 @@ def batched_nms_poly(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tens
         _capi.check(lib.dafne_poly_nms(b.data_ptr(), s.data_ptr(), c.data_ptr(), n, float(iou_threshold),
                                        int(vehicle_merge), keep.data_ptr(), nkeep.data_ptr(), _aligned(scratch),
                                        need.value, _capi.stream_ptr()), "dafne_poly_nms")
-    return keep[: int(nkeep.item())].to(torch.int64)
+    return keep, nkeep, (b, s, c, scratch)
 
 
 def ml_nms(boxlist: Instances, nms_thresh: float, max_proposals: int = -1) -> Instances:
@@ -181,8 +189,9 @@ class DAFNeOutputs:
     def select_over_all_levels(self, boxlists: List[Instances]) -> List[Instances]:
         """dafne_outputs.py:907-925: polygon NMS per image, then keep the post_nms_topk best (ties kept)."""
         results = []
-        for boxlist in boxlists:
-            result = ml_nms(boxlist, self.nms_thresh)
+        nms_results = self._ml_nms_overlapped(boxlists) if len(boxlists) > 1 else None
+        for k, boxlist in enumerate(boxlists):
+            result = nms_results[k] if nms_results is not None else ml_nms(boxlist, self.nms_thresh)
             n = len(result)
             if n > self.post_nms_topk > 0:
                 scores = result.scores
@@ -190,6 +199,36 @@ class DAFNeOutputs:
                 result = result[torch.nonzero(scores >= thr).squeeze(1)]
             results.append(result)
         return results
+
+
+    _streams: List["torch.cuda.Stream"] = []
+
+    def _ml_nms_overlapped(self, boxlists: List[Instances]) -> Optional[List[Instances]]:
+        """`ml_nms` of several images at once: the NMS of one image is a chain of dependent launches that fills a
+        fraction of the GPU (the greedy sweep inside a 512-box panel runs on one CTA), so the images run side by side on
+        up to four streams and their results are read afterwards. None: nothing to overlap (the per-image path runs)."""
+        if self.nms_thresh <= 0 or not all(b.scores.is_cuda and b.scores.shape[0] > 0 for b in boxlists):
+            return None
+        dev = boxlists[0].scores.device
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream()
+            while len(DAFNeOutputs._streams) < min(4, len(boxlists)):
+                DAFNeOutputs._streams.append(torch.cuda.Stream(device=dev))
+            if any(st.device != dev for st in DAFNeOutputs._streams):
+                DAFNeOutputs._streams[:] = [torch.cuda.Stream(device=dev) for _ in DAFNeOutputs._streams]
+            pending = []
+            for k, b in enumerate(boxlists):
+                st = DAFNeOutputs._streams[k % len(DAFNeOutputs._streams)]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    keep, nkeep, held = _batched_nms_poly_launch(b.pred_corners, b.scores, b.pred_classes, self.nms_thresh)
+                for t in (keep, nkeep) + tuple(held):
+                    t.record_stream(cur)
+                pending.append((keep, nkeep, held))
+            for st in DAFNeOutputs._streams:
+                cur.wait_stream(st)
+            counts = torch.cat([nk for _, nk, _ in pending]).tolist()  # one sync for all images
+            return [b[keep[:n].to(torch.int64)] for b, (keep, _, _), n in zip(boxlists, pending, counts)]
 
 
 @PROPOSAL_GENERATOR_REGISTRY.register()
@@ -365,23 +404,28 @@ class OneStageDetector(nn.Module):
         for dets, counts, out_sizes, graph_state in launched:
             cap = dets.shape[1]
             results = []
+            # one contiguous copy per FIELD for the whole batch (seven launches per batch, not per image); an image's
+            # fields are the leading rows of its slice
+            f_boxes, f_corners = dets[:, :, 8:12].contiguous(), dets[:, :, 0:8].contiguous()
+            f_scores, f_ctr = dets[:, :, 12].contiguous(), dets[:, :, 13].contiguous()
+            f_cls, f_lvl = dets[:, :, 14].to(torch.int64), dets[:, :, 15].to(torch.int64)
+            f_loc = dets[:, :, 16:18].contiguous()
             for i in range(dets.shape[0]):
                 n = counts_h[k]
                 k += 1
                 if n > cap:
                     raise _capi.DafneError(f"{n} detections exceed the output capacity {cap} (score ties at the cut)")
-                d = dets[i, :n]
                 # detectron2's detector_postprocess runs inside ProposalNetwork.forward whatever do_postprocess says:
                 # the boxes are scaled / clipped / filtered and image_size is the requested output size either way;
                 # do_postprocess only gates the corner / location rescale (one_stage_detector.py:45-55, 78-98)
                 inst = Instances(out_sizes[i])
-                inst.pred_boxes = Boxes(d[:, 8:12].clone())
-                inst.pred_corners = d[:, 0:8].clone()
-                inst.scores = d[:, 12].clone()
-                inst.centerness = d[:, 13].clone()
-                inst.pred_classes = d[:, 14].to(torch.int64)
-                inst.locations = d[:, 16:18].clone()
-                inst.fpn_levels = d[:, 15].to(torch.int64)
+                inst.pred_boxes = Boxes(f_boxes[i, :n])
+                inst.pred_corners = f_corners[i, :n]
+                inst.scores = f_scores[i, :n]
+                inst.centerness = f_ctr[i, :n]
+                inst.pred_classes = f_cls[i, :n]
+                inst.locations = f_loc[i, :n]
+                inst.fpn_levels = f_lvl[i, :n]
                 results.append({"instances": inst})
             if graph_state is not None:
                 graph_state["busy"] = False  # every field above is a copy: the record may be overwritten again

@@ -258,10 +258,15 @@ class DotaDatasetMapperTTA:
 # ------------------------------------------------------------------------------------------------ model (tta.py:138-268)
 class OneStageRCNNWithTTA(nn.Module):
     def __init__(self, cfg, model, tta_mapper: Optional[Callable] = None, batch_size: int = 3,
-                 use_cuda_graphs: bool = True):
+                 use_cuda_graphs: bool = True, cross_image_batch: int = 12):
         """`use_cuda_graphs` (not in the reference): replay each augmented shape as one captured CUDA graph -- the copies
         of every image of a dataset repeat the same shapes and sizes, and at batch 3 a step is bound by the host's
-        ~200 launches, not by the GPU."""
+        ~200 launches, not by the GPU.
+        `cross_image_batch` (not in the reference): when ONE call holds several images, copies of the same shape from
+        different images run as one batch of up to this many copies instead of `batch_size` copies of one image (the
+        reference loops over the images, tta.py:178-196). A copy's detections do not depend on what else is in its batch
+        (per-image GroupNorm statistics, per-image NMS), so the results are those of the per-image loop; batches of 12
+        instead of 3 simply fill the GPU. <= batch_size: the reference's batches."""
         super().__init__()
         from .modeling import OneStageDetector
 
@@ -272,6 +277,7 @@ class OneStageRCNNWithTTA(nn.Module):
         self.tta_mapper = DotaDatasetMapperTTA(cfg) if tta_mapper is None else tta_mapper
         self.batch_size = batch_size
         self.use_cuda_graphs = use_cuda_graphs
+        self.cross_image_batch = cross_image_batch
 
     def _batch_inference(self, batched_inputs, detected_instances=None):
         outputs = []
@@ -293,7 +299,40 @@ class OneStageRCNNWithTTA(nn.Module):
                 ret["width"] = ret["image"].shape[2]
             return ret
 
-        return [self._inference_one_image(_maybe_read_image(x)) for x in batched_inputs]
+        inputs = [_maybe_read_image(x) for x in batched_inputs]
+        if len(inputs) > 1 and self.cross_image_batch > self.batch_size:
+            return self._inference_images_batched(inputs)
+        return [self._inference_one_image(x) for x in inputs]
+
+    def _inference_images_batched(self, inputs):
+        """All images of the call at once: their copies are grouped by shape across images (see `cross_image_batch`),
+        every group is enqueued, ONE host sync collects all of them, then each image's copies are merged as in
+        `_inference_one_image`."""
+        per_image = [self._get_augmented_inputs(x) for x in inputs]
+        groups = {}
+        for k, (aug, _) in enumerate(per_image):
+            for j, a in enumerate(aug):
+                key = (tuple(a["image"].shape), a["image"].dtype, a.get("height"), a.get("width"))
+                groups.setdefault(key, []).append((k, j, a))
+        launched, owners = [], []
+        saved = self.model.use_cuda_graphs
+        self.model.use_cuda_graphs = self.use_cuda_graphs
+        try:
+            for items in groups.values():
+                for s0 in range(0, len(items), self.cross_image_batch):
+                    chunk = items[s0 : s0 + self.cross_image_batch]
+                    launched.append(self.model._launch([a for _, _, a in chunk], do_postprocess=False))
+                    owners.append([(k, j) for k, j, _ in chunk])
+        finally:
+            self.model.use_cuda_graphs = saved
+        outputs = [[None] * len(aug) for aug, _ in per_image]
+        for res, own in zip(self.model._collect(launched), owners):
+            for o, (k, j) in zip(res, own):
+                outputs[k][j] = o
+        # the union NMS of all images side by side (select_over_all_levels overlaps the images of its list)
+        merged = self.model.proposal_generator.dafne_outputs.select_over_all_levels(
+            [self._to_original_frame(outputs[k], per_image[k][1]) for k in range(len(inputs))])
+        return [{"instances": m} for m in merged]
 
     def _inference_one_image(self, input):
         augmented_inputs, tfms = self._get_augmented_inputs(input)
@@ -323,7 +362,9 @@ class OneStageRCNNWithTTA(nn.Module):
         return [o for batch in self.model._collect(launched) for o in batch]
 
     def _get_augmented_corners(self, augmented_inputs, tfms):
-        outputs = self._batch_inference_deferred(augmented_inputs)
+        return self._to_original_frame(self._batch_inference_deferred(augmented_inputs), tfms)
+
+    def _to_original_frame(self, outputs, tfms):
         instances_list = []
         for output, tfm in zip(outputs, tfms):
             instances = output["instances"]

@@ -204,6 +204,14 @@ int dafne_conv_gn_in_nhwc(const void* dev_in_raw_f16, int N, int H, int W, int C
                           const float* dev_in_gamma, const float* dev_in_beta, const void* dev_w_f16, int Cout,
                           const float* dev_shift, int64_t* dev_gn_sums, void* dev_out_f16, void* stream);
 
+/* 1x1 / stride-1 convolution through the CTA-pair kernel (csrc/pair_tc.cu: tcgen05.mma.cta_group::2, 256 x 256 tiles over
+ * two SMs, each loading half of the weight tile): detectron2 BottleneckBlock conv1 / conv3 + FrozenBN (+ shortcut) + ReLU.
+ *   out = act(scale * (in x w^T) + shift (+ residual))   in [M, K], w [N, K], residual / out [M, N] fp16, M = N * H * W
+ * K a multiple of 64, N a multiple of 256; residual may be NULL; act = ReLU when relu != 0. */
+int dafne_conv1x1_pair_nhwc(const void* dev_in_f16, int64_t M, int K, const void* dev_w_f16, int N,
+                            const float* dev_scale, const float* dev_shift, int relu, const void* dev_residual_f16,
+                            void* dev_out_f16, void* stream);
+
 /* Bottleneck tail through the two-GEMM tcgen05 kernel (csrc/tail_tc.cu): conv3 + FrozenBN + shortcut + ReLU of one
  * detectron2 BottleneckBlock and conv1 + FrozenBN + ReLU of the next one, both 1x1 / stride 1, in ONE launch:
  *   out = relu(scale1 * (in x w3^T) + shift1 + residual)   in [N,H,W,K1], w3 [N1][K1], residual / out [N,H,W,N1]

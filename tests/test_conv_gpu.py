@@ -292,3 +292,52 @@ def test_tower_conv_groupnorm_on_load(case):
     # statistics of the output: fixed point, so equal wherever the outputs are equal; close otherwise
     rel = (sums1 - sums2).abs().double() / sums2.abs().double().clamp_min(1.0)
     assert rel.max().item() < 1e-3
+
+
+PAIR_CASES = [
+    # name, M, K, N, residual, relu: conv1 / conv3 of res4 and res5, ragged M (a pair tile whose second CTA is partly or
+    # wholly outside), more tiles than pairs, one tile
+    ("res4_conv1_1024_256", 3 * 32 * 32, 1024, 256, False, True),
+    ("res4_conv3_256_1024_res", 3 * 32 * 32, 256, 1024, True, True),
+    ("res5_conv3_512_2048_res", 2 * 16 * 16, 512, 2048, True, True),
+    ("lateral_2048_256_linear", 2 * 16 * 16, 2048, 256, False, False),
+    ("ragged_m_1000", 1000, 256, 512, True, True),
+    ("ragged_m_130_one_cta_empty", 130, 128, 256, True, True),
+    ("tiny_m_7", 7, 64, 256, False, True),
+    ("multiwave_conv3", 8 * 64 * 64, 256, 1024, True, True),
+    ("multiwave_conv1", 8 * 64 * 64, 1024, 256, False, True),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_pair_kernel_matches_torch(case):
+    """csrc/pair_tc.cu: 1x1 convolutions as 256 x 256 tiles over a CTA pair (tcgen05.mma.cta_group::2), against torch fp32
+    on the same fp16 inputs."""
+    from dafne_b200 import _capi
+
+    lib = _capi.lib()
+    name, M, K, N, has_res, relu = case
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(11 + len(name))
+    x = torch.randn(M, K, generator=g).half().to(dev)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).half().to(dev)
+    sc = (torch.rand(N, generator=g) + 0.5).to(dev)
+    sh = (torch.randn(N, generator=g) * 0.5).to(dev)
+    res = torch.randn(M, N, generator=g).half().to(dev) if has_res else None
+    out = torch.full((M, N), float("nan"), device=dev, dtype=torch.float16)
+    vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    _capi.check(lib.dafne_conv1x1_pair_nhwc(vp(x), M, K, vp(w), N, vp(sc), vp(sh), int(relu), vp(res), vp(out),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                "dafne_conv1x1_pair_nhwc")
+    torch.cuda.synchronize()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = (x.float() @ w.float().t()) * sc + sh
+    if has_res:
+        ref = ref + res.float()
+    if relu:
+        ref = F.relu(ref)
+    got = out.float()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs()
+    assert bool((err <= 2e-3 * ref.abs().max() + 2e-3 * ref.abs()).all()), f"max err {err.max().item()}"

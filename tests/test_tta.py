@@ -126,6 +126,37 @@ def test_tta_wrapper_equals_oracle_merge_of_the_copies():
 
 
 @pytest.mark.gpu
+def test_tta_cross_image_batches_equal_the_per_image_loop():
+    """A call with several images batches same-shaped copies ACROSS images (cross_image_batch, not in the reference): the
+    merged detections of every image are bit-identical to the reference-shaped loop over the images (tta.py:178-196)."""
+    from dafne_b200.modeling import build_model
+
+    cfg = _cfg(min_sizes=(160, 192, 256), max_size=320)
+    cfg.MODEL.DEVICE = "cuda:0"
+    model = build_model(cfg)
+    g = torch.Generator().manual_seed(9)
+    # three images of one size and one of another: its copies form groups of their own
+    inputs = [{"image": torch.randint(0, 256, (3, 200, 256), dtype=torch.uint8, generator=g), "height": 400, "width": 512}
+              for _ in range(3)]
+    inputs.append({"image": torch.randint(0, 256, (3, 224, 224), dtype=torch.uint8, generator=g), "height": 224,
+                   "width": 224})
+    loop = tta.OneStageRCNNWithTTA(cfg, model, cross_image_batch=0)
+    batched = tta.OneStageRCNNWithTTA(cfg, model, cross_image_batch=5)  # 9 copies per shape of the first three: 5 + 4
+    want = loop(inputs)
+    for rep in range(2):  # the second call replays the captured graphs
+        got = batched(inputs)
+        assert len(got) == len(want) == 4
+        for a, b in zip(want, got):
+            ia, ib = a["instances"], b["instances"]
+            assert len(ia) == len(ib) and len(ia) > 20
+            assert torch.equal(ia.pred_corners, ib.pred_corners)
+            assert torch.equal(ia.scores, ib.scores)
+            assert torch.equal(ia.pred_classes, ib.pred_classes)
+            assert ia.image_size == ib.image_size
+    assert not torch.equal(want[0]["instances"].scores, want[1]["instances"].scores)
+
+
+@pytest.mark.gpu
 def test_poly_nms_beyond_the_shared_memory_sort():
     """The TTA union can hold 27 copies x 1000 boxes: more than the 16 384 keys one CTA sorts in shared memory."""
     from dafne_b200.modeling import batched_nms_poly
