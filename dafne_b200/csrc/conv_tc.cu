@@ -198,6 +198,10 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                    int res_tma_arg, int row_shared, int breg_bytes) {
     const int res_tma = MODE == 1 ? res_tma_arg : 0;
     using Cfg = ConvCfg<BLOCK_N, EPI_WGS>;
+    // mode 5 (halo-box ring + GroupNorm on load) exists only in the variant the tower convolutions use: compiled into
+    // every variant, its transform role made ptxas spill in the 88-register producer side of the two-warpgroup kernels
+    constexpr bool kHalo5 = BLOCK_N == 256 && EPI_WGS == 1 && MODE == 2;
+    const bool halo5 = kHalo5 && row_shared == 5;
     extern __shared__ __align__(1024) uint8_t smem[];
 
     const uint32_t smem_base = smem_u32(smem);
@@ -249,13 +253,13 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
         }
-        if (row_shared != 5)
+        if (!halo5)
             for (int i = 0; i < 2 * RS; ++i) {
                 mbar_init(bar_rfull + 8 * i, 1);
                 mbar_init(bar_rempty + 8 * i, 1);
             }
         mbar_init(bar_bfull, 1);
-        if (row_shared == 5)
+        if (halo5)
             for (int i = 0; i < Cfg::A5_SLOTS; ++i) {
                 mbar_init(bar_afull + 8 * i, 1);
                 mbar_init(bar_aready + 8 * i, 1);
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
             long long bkey = -1;  // mode 3: which weights are resident
             int last_stage = -1;
             uint32_t last_phase = 0;
-            if (row_shared == 5) {
+            if (halo5) {
                 // Halo boxes run two channel blocks ahead of the weight stages (three slots): the box of block cb + 2 (of
                 // the next tile after the last block) is requested right after the nine weight tiles of block cb -- the
                 // slot it takes, block cb - 1's, is free by then, so the request never stalls the weight stream -- and
@@ -461,7 +465,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * BLOCK_N;
-                if (row_shared == 5) {
+                if (halo5) {
                     const bool gn_in = probs[g].p.in_gn_sums != nullptr;
                     const int cbs = probs[g].p.cin_blocks;
                     for (int cb = 0; cb < cbs; ++cb) {
@@ -538,7 +542,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                 if (acc == 0) acc_phase ^= 1;
             }
         }
-    } else if ((warp == 2 || warp == 3) && row_shared == 5) {
+    } else if ((warp == 2 || warp == 3) && halo5) {
         // ------------------------------------------------------------ GroupNorm + ReLU of the INPUT, on the landed box
         // (mode 5, tower layers 2-4): the previous layer stored its RAW convolution output and its statistics; instead
         // of a separate read-modify-write pass over that tensor (2 x 512 B per location and layer, 1.4 ms per forward at
