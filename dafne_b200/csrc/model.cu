@@ -700,8 +700,11 @@ int ctx_plan(dafne_ctx* c, int N, int H, int W, uint8_t* base, size_t bytes, siz
     const int* nb = stage_blocks(sp.resnet_depth);
     Act feats[3];
     // Which stages run conv3 + the next block's conv1 as one fused tail launch: bit (s - 2) of DAFNE_CONV_TAIL
-    // (default 3 = res2 and res3; 0 = every 1x1 is its own launch; 7 adds res4, where the fused form is SLOWER: the
-    // two weight matrices, 1 MB per 128-pixel tile, are re-streamed from L2 faster than a 64 KB ring can pull them).
+    // (default 3 = res2 and res3; 0 = every 1x1 is its own launch; 7 adds res4). Measured at R101 32 x 1024^2 with the
+    // final kernels: the fused tail moves 28 % fewer bytes but at 3.6 TB/s where the two plain launches run at 5.7-6.2 --
+    // res2 738 vs 421 + 219 us, res3 378 vs 218 + 116 us per block pair -- and the power-capped STEP is the same either way
+    // (three interleaved same-box rounds: 1 098 / 1 097 / 1 077 images/s with 0, 1 094 / 1 090 / 1 088 with 3): fewer bytes
+    // buy back as clock what the longer launch costs. res4 (257 vs 134 + 79 us) is slower in both views.
     static const int tail_mask = getenv("DAFNE_CONV_TAIL") ? atoi(getenv("DAFNE_CONV_TAIL")) : 3;
     // Which stages run their 1x1 / stride-1 convolutions on the CTA-pair kernel (pair_tc.cu, cta_group::2): bit (s - 2) of
     // DAFNE_CONV_PAIR for conv1, bit (s - 2 + 4) for conv3 (0 = none). Default 0x8C = conv1 of res4 / res5 and conv3 of
