@@ -232,6 +232,7 @@ struct DiagSmem {
     u64 bits[64];
     unsigned short queue[(64 / kDiagSplit) * 64];
     int qn;
+    int mqn;  // pairs the cheap exits of the pre-filter left undecided (listed in terms.tq, which phase 2 reuses)
     int last;
     unsigned stat_pairs;
     float rt[64][4], ct[64][4];     // t(v) of the staged boxes' vertices (term_is_zero)
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
         }
         if (t == 0) {
             sm.qn = 0;
+            sm.mqn = 0;
             sm.stat_pairs = 0;
         }
         __syncthreads();
@@ -303,17 +305,42 @@ __global__ void __launch_bounds__(kDiagThreads) nms_diag_kernel(const float* __r
             for (int u = 0; u < kCols; ++u) {
                 const int j = jq + u;
                 bool want = row_on && j >= jlo && j < jhi && !((cdead >> j) & 1ull);
+                bool maybe = false;
                 if (want) {
                     ++npairs;
                     const NmsAux& Q = sm.caux[j];
-                    if (pair_inter_is_zero(P, Q, sm.rbox[r], sm.cbox[j]) && (P.area + Q.area) != 0.f) want = false;
+                    if ((P.area + Q.area) != 0.f) {
+                        const int cls = pair_filter_quick(P, Q);
+                        if (cls == 0) want = false;
+                        if (cls == 2) {
+                            want = false;
+                            maybe = true;
+                        }
+                    }
                 }
                 queue_push(sm.queue, &sm.qn, want, static_cast<unsigned short>((r << 6) | j), lane);
+                queue_push(sm.terms.tq, &sm.mqn, maybe, static_cast<unsigned short>((r << 6) | j), lane);
             }
             for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
             if (lane == 0 && npairs) atomicAdd(&sm.stat_pairs, npairs);
         }
         __syncthreads();
+        {
+            // phase 1b: the pairs the cheap exits left undecided, one per lane (see nms_bcast_kernel)
+            const int mq = sm.mqn;
+            const unsigned lane = t & 31;
+            for (int k0 = 0; k0 < mq; k0 += kDiagThreads) {
+                const int k = k0 + t;
+                bool want = k < mq;
+                const unsigned short e = want ? sm.terms.tq[k] : static_cast<unsigned short>(0);
+                if (want) {
+                    const int r = e >> 6, j = e & 63;
+                    if (pair_inter_is_zero(sm.raux[r], sm.caux[j], sm.rbox[r], sm.cbox[j])) want = false;
+                }
+                queue_push(sm.queue, &sm.qn, want, e, lane);
+            }
+            __syncthreads();
+        }
         // phase 2: the queued pairs, term by term
         const int qn = sm.qn;
         clip_queue<false, kDiagThreads>(sm.queue, qn, sm.rbox, sm.cbox, sm.raux, sm.caux, sm.rt, sm.ct, sm.terms,
@@ -407,6 +434,7 @@ struct BcastSmem {
     unsigned int newdead[kColChunk];  // 0 -> 1 flags, touched with atomics while phase 2 runs
     int rows[kRowChunk];
     int qn;
+    int mqn;  // pairs the cheap exits of the pre-filter left undecided (listed in terms.tq, which phase 2 reuses)
     unsigned stat_pairs;
     float2 poly[9 * kBcastThreads];  // tri_overlap's per-thread polygon columns
 };
@@ -479,6 +507,7 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
         }
         if (t == 0) {
             sm.qn = 0;
+            sm.mqn = 0;
             sm.stat_pairs = 0;
         }
         __syncthreads();
@@ -521,6 +550,7 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
             for (int u = 0; u < kRpt; ++u) {
                 const int r = part * kRpt + u;
                 bool want = col_on && r < nrows;
+                bool maybe = false;
                 if (want) {
                     const NmsAux& P = sm.raux[r];
                     // "close": squared centre distance below close_k x the smaller area (centres are kept x 4, hence
@@ -532,16 +562,42 @@ __global__ void __launch_bounds__(kBcastThreads) nms_bcast_kernel(const float* _
                         want = false;
                     } else {
                         ++npairs;
-                        if (pass != 0 && pair_inter_is_zero(P, Q, sm.rbox[r], sm.cbox[j]) && (P.area + Q.area) != 0.f)
-                            want = false;
+                        // the cheap exits of the pre-filter here; what they leave undecided goes to a list of its own
+                        // (pairs whose areas sum to 0 are always clipped: uni == 0 takes the reference's other formula)
+                        if (pass != 0 && (P.area + Q.area) != 0.f) {
+                            const int cls = pair_filter_quick(P, Q);
+                            if (cls == 0) want = false;
+                            if (cls == 2) {
+                                want = false;
+                                maybe = true;
+                            }
+                        }
                     }
                 }
                 queue_push(sm.queue, &sm.qn, want, static_cast<unsigned short>((r << 7) | j), lane);
+                if (pass != 0) queue_push(sm.terms.tq, &sm.mqn, maybe, static_cast<unsigned short>((r << 7) | j), lane);
             }
             for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
             if (lane == 0 && npairs) atomicAdd(&sm.stat_pairs, npairs);
         }
         __syncthreads();
+        // phase 1b: the undecided pairs, one per lane -- every lane of a warp runs the expensive part of the pre-filter
+        // (two divisions, up to 16 cross products) instead of the five that reached it inside the consult loop
+        if (pass != 0) {
+            const int mq = sm.mqn;
+            const unsigned lane = t & 31;
+            for (int k0 = 0; k0 < mq; k0 += kBcastThreads) {  // uniform trip count: every lane reaches queue_push
+                const int k = k0 + t;
+                bool want = k < mq;
+                const unsigned short e = want ? sm.terms.tq[k] : static_cast<unsigned short>(0);
+                if (want) {
+                    const int r = e >> 7, j = e & 127;
+                    if (pair_inter_is_zero(sm.raux[r], sm.caux[j], sm.rbox[r], sm.cbox[j])) want = false;
+                }
+                queue_push(sm.queue, &sm.qn, want, e, lane);
+            }
+            __syncthreads();
+        }
         // phase 2: the queued pairs, term by term
         const int qn = sm.qn;
         clip_queue<true, kBcastThreads>(sm.queue, qn, sm.rbox, sm.cbox, sm.raux, sm.caux, sm.rt, sm.ct, sm.terms,
