@@ -162,3 +162,53 @@ def test_r101_plan_runs_and_matches_oracle_heads():
     for l in range(5):
         assert (eng.head_outputs(l)["logits"].cpu() - ref["logits"][l]).abs().max() <= 5e-2
     eng.close()
+
+
+EDGE_SHAPES = [
+    # (images, H, W): the smallest legal canvas (p5-p7 are single pixels, every halo box is mostly padding, one CTA pair
+    # of the 1x1 kernels is mostly outside), a thin strip, an odd batch whose pixel count is no multiple of a tile
+    (1, 32, 32),
+    (3, 64, 32),
+    (5, 96, 160),
+]
+
+
+@pytest.mark.parametrize("shape", EDGE_SHAPES, ids=[f"{n}x{h}x{w}" for n, h, w in EDGE_SHAPES])
+def test_edge_shapes_layerwise_and_heads(shape):
+    """Tiny and ragged canvases through the whole dense forward (GroupNorm on load, CTA-pair 1x1s, fused tails included):
+    every named activation against the quantisation-matched oracle, head outputs against the fp32 arithmetic."""
+    from dafne_b200.engine import DafneEngine
+    from dafne_b200.spec import ModelSpec
+    from dafne_b200.weights import synthetic_state_dict
+
+    n, H, W = shape
+    spec = ModelSpec(resnet_depth=50, num_classes=15)
+    sd = synthetic_state_dict(spec, seed=3)
+    eng = DafneEngine(spec, torch.device("cuda:0"))
+    try:
+        eng.load_state_dict(sd)
+        eng.keep_activations(True)
+        g = torch.Generator().manual_seed(17 + n)
+        imgs = [torch.randint(0, 256, (3, H, W), dtype=torch.uint8, generator=g) for _ in range(n)]
+        sizes = [(H, W)] * n
+        eng.forward_dense(torch.stack(imgs).cuda(), sizes)
+        torch.cuda.synchronize()
+        batch, _ = omodel.preprocess(imgs, spec.pixel_mean, spec.pixel_std)
+        ref16 = omodel.forward_dense(sd, 50, batch, "o16")
+        ref32 = omodel.forward_dense(sd, 50, batch, "fp32")
+        for name, r in ref16["named"].items():
+            if name == "stem":
+                continue
+            a = eng.activation(name).cpu()
+            assert a.shape == r.shape, name
+            rel = ((a - r).norm() / (r.norm() + 1e-12)).item()
+            assert rel <= 8e-3, f"{name}: rel L2 {rel}"
+        for l in range(5):
+            h = eng.head_outputs(l)
+            lg, cd, ce = h["logits"].cpu(), h["ctr_delta"].cpu(), h["center"].cpu()
+            reg = ce.repeat(1, 4, 1, 1) + cd[:, 1:9]
+            assert (lg - ref32["logits"][l]).abs().max() <= 3e-2
+            assert (cd[:, :1] - ref32["ctr"][l]).abs().max() <= 3e-2
+            assert (reg - ref32["reg"][l]).abs().max() <= 5e-2
+    finally:
+        eng.close()
