@@ -906,7 +906,7 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                         }
                     }
                     fence_proxy_async_smem();
-                    if (et == 0 && !res_tma) {
+                    if (et == 0 && !res_tma && ring >= 2) {
                         // before anyone may write the NEXT chunk's slot, the store that last read it must be done
                         if (ring == 2)
                             tma_store_wait_read<0>();
@@ -924,6 +924,12 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WGS, 1)
                             tma_store_wait_read<1>();
                             mbar_arrive(bar_rempty + 8 * (wg * RS + (chunk_cnt - 1) % ring));
                         }
+                    }
+                    if (ring == 1 && !res_tma) {
+                        // one slot (the tower convolutions trade the second one for a fourth weight stage): the next
+                        // chunk goes into THIS slot, so its store must have read it before anyone writes again
+                        if (et == 0) tma_store_wait_read<0>();
+                        named_bar_sync(bar_id, 128);
                     }
                 }
             } else {
@@ -1099,6 +1105,9 @@ int conv_plan_build(const ConvDesc& d, ConvPlan* plan, int num_sms) {
     // mode 5: the 256-wide tower convolutions (GroupNorm statistics in the epilogue) take their input as halo boxes too
     // -- one A load per channel block instead of nine, 28 % less L2 -> shared-memory traffic -- with the weights of one
     // tap per stage, and can normalise the input while it is loaded (in_gn_sums). DAFNE_CONV_HALO256=0: A/B switch.
+    // (Measured and not adopted, r3zg: the same operand path for the plain 256-wide 3x3 convolutions -- conv2 of res4 /
+    // res5, the FPN output convolutions: 2.53 / 2.92 / 2.86 ms against 2.53 / 2.96 / 2.76 ms for res4's conv2 in three
+    // interleaved rounds, no difference; they already run four (A + B) stages.)
     bool mode5 = !small && d.ksize == 3 && d.stride == 1 && bn == 256 && d.gn_sums != nullptr && d.Cin <= 256;
     if (const char* ev = getenv("DAFNE_CONV_HALO256"))
         if (atoi(ev) == 0) mode5 = false;
@@ -1247,6 +1256,12 @@ template <int BN, int WGS>
 static void conv_smem_config(int res_tma, int row_shared, int breg, int mode, int* stages, int* ring) {
     using Cfg = ConvCfg<BN, WGS>;
     int r = BN < 64 ? 2 : (res_tma ? (res_tma >= 2 && res_tma <= Cfg::MAX_RING ? res_tma : 4) : (WGS == 2 ? 3 : 2));
+    if (row_shared == 5) {
+        // tower convolutions: the epilogue has a whole tile's 18 432 tensor cycles to drain 4 chunks; a one-slot output
+        // ring buys a fourth weight stage. DAFNE_CONV_RING5: tuning override.
+        r = 1;
+        if (const char* ev = getenv("DAFNE_CONV_RING5")) r = atoi(ev) >= 1 && atoi(ev) <= 4 ? atoi(ev) : r;
+    }
     int st = Cfg::MAX_STAGES;
     while (st > 2 && Cfg::smem_bytes(st, r, row_shared, breg, mode) > kMaxSmem) --st;
     while (r > 2 && Cfg::smem_bytes(st, r, row_shared, breg, mode) > kMaxSmem) --r;
